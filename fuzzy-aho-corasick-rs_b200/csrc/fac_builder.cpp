@@ -1,0 +1,535 @@
+// fac_builder.cpp -- host-side construction of the flattened automaton (see fac_builder.h).
+#include "fac_builder.h"
+#include "fac_core.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <unordered_map>
+
+#define FAC_TABLE_QUAL static const
+#include "unicode_tables.h"
+
+namespace fac {
+
+const UnicodeTables &host_unicode_tables() {
+    static const UnicodeTables U = {FAC_GCB_STAGE1, FAC_GCB_STAGE2, FAC_LOWER_KEYS, FAC_LOWER_VALS, FAC_LOWER_N};
+    return U;
+}
+
+size_t utf8_valid_up_to(const uint8_t *s, size_t n) {
+    size_t i = 0;
+    while (i < n) {
+        const uint8_t b = s[i];
+        if (b < 0x80) { i++; continue; }
+        size_t extra;
+        uint8_t lo = 0x80, hi = 0xBF;  // allowed range of the first continuation byte
+        if (b >= 0xC2 && b <= 0xDF) extra = 1;
+        else if (b == 0xE0) { extra = 2; lo = 0xA0; }
+        else if (b == 0xED) { extra = 2; hi = 0x9F; }
+        else if (b >= 0xE1 && b <= 0xEF) extra = 2;
+        else if (b == 0xF0) { extra = 3; lo = 0x90; }
+        else if (b >= 0xF1 && b <= 0xF3) extra = 3;
+        else if (b == 0xF4) { extra = 3; hi = 0x8F; }
+        else return i;
+        if (n - i <= extra) return i;
+        if (s[i + 1] < lo || s[i + 1] > hi) return i;
+        for (size_t k = 2; k <= extra; k++)
+            if ((s[i + k] & 0xC0) != 0x80) return i;
+        i += extra + 1;
+    }
+    return i;
+}
+
+static void grapheme_bounds(const std::string &s, std::vector<size_t> &starts) {
+    const UnicodeTables &U = host_unicode_tables();
+    const uint8_t *p = (const uint8_t *)s.data();
+    starts.clear();
+    for (size_t i = 0; i < s.size(); i++) {
+        if (fac_is_cont(p[i])) continue;
+        if (fac_break_before(U, p, 0, i)) starts.push_back(i);
+    }
+}
+
+size_t count_graphemes(const std::string &s) {
+    std::vector<size_t> st;
+    grapheme_bounds(s, st);
+    return st.size();
+}
+
+static std::string lower_grapheme(const uint8_t *p, size_t b, size_t e) {
+    const UnicodeTables &U = host_unicode_tables();
+    std::string out;
+    uint64_t i = b;
+    while (i < e) {
+        uint32_t cp = fac_decode(p, i), lo[2];
+        int n = fac_lower(U, cp, lo);
+        for (int k = 0; k < n; k++) {
+            uint8_t buf[4];
+            int nb = fac_encode(lo[k], buf);
+            out.append((const char *)buf, nb);
+        }
+    }
+    return out;
+}
+
+std::vector<std::string> fold_graphemes(const std::string &s, bool ci) {
+    std::vector<size_t> st;
+    grapheme_bounds(s, st);
+    std::vector<std::string> out;
+    out.reserve(st.size());
+    for (size_t k = 0; k < st.size(); k++) {
+        const size_t b = st[k], e = k + 1 < st.size() ? st[k + 1] : s.size();
+        out.push_back(ci ? lower_grapheme((const uint8_t *)s.data(), b, e) : s.substr(b, e - b));
+    }
+    return out;
+}
+
+static uint32_t first_scalar(const std::string &g) {
+    if (g.empty()) return 0;
+    uint64_t i = 0;
+    return fac_decode((const uint8_t *)g.data(), i);
+}
+
+static uint64_t fnv1a(const std::string &g) {
+    uint64_t h = 0xCBF29CE484222325ull;
+    for (unsigned char c : g) { h ^= c; h *= 0x100000001B3ull; }
+    return h;
+}
+
+static FacLimits limits_from_c(const fac_limits &c, bool finalize) {
+    FacLimits l;
+    memset(&l, 0, sizeof(l));
+    l.ins = c.insertions; l.del = c.deletions; l.sub = c.substitutions; l.swp = c.swaps; l.edits = c.edits;
+    auto norm = [](int16_t v) -> int16_t { return v < 0 ? (int16_t)-1 : (v > 255 ? (int16_t)255 : v); };
+    l.ins = norm(l.ins); l.del = norm(l.del); l.sub = norm(l.sub); l.swp = norm(l.swp); l.edits = norm(l.edits);
+    if (finalize && l.edits < 0) {  // FuzzyLimits::finalize, src/structs.rs:319-335
+        if (l.ins < 0) l.ins = 0;
+        if (l.del < 0) l.del = 0;
+        if (l.sub < 0) l.sub = 0;
+        if (l.swp < 0) l.swp = 0;
+    }
+    return l;
+}
+
+// Open-addressing symbol table keyed by FNV-1a of the folded grapheme bytes.
+static void build_symbol_table(const std::vector<std::string> &syms, std::vector<HostSymbol> &tab, std::vector<uint8_t> &pool) {
+    size_t cap = 16;
+    while (cap < syms.size() * 2 + 2) cap <<= 1;
+    tab.assign(cap, HostSymbol{0, 0, 0, 0, 0});
+    pool.clear();
+    for (size_t i = 0; i < syms.size(); i++) {
+        const uint64_t h = fnv1a(syms[i]);
+        size_t slot = (size_t)(h & (cap - 1));
+        while (tab[slot].gid != 0) slot = (slot + 1) & (cap - 1);
+        tab[slot] = HostSymbol{h, (uint32_t)(i + 1), (uint32_t)pool.size(), (uint32_t)syms[i].size(), 0};
+        pool.insert(pool.end(), syms[i].begin(), syms[i].end());
+    }
+    pool.resize(pool.size() + 8, 0);
+}
+
+namespace {
+struct TmpNode {
+    std::vector<std::pair<std::string, uint32_t>> order;  // edges in first-insertion order
+    std::unordered_map<std::string, uint32_t> trans;
+    std::vector<uint32_t> output;
+    uint32_t fail = 0;
+    int64_t pattern_index = -1;
+};
+}  // namespace
+
+static void build_default_similarity(std::map<std::pair<uint32_t, uint32_t>, float> &m) {  // src/builder.rs:492-526
+    const std::string vowels = "aeiou";
+    for (char a : vowels)
+        for (char b : vowels)
+            if (a != b) m[{(uint32_t)a, (uint32_t)b}] = 0.6f;
+    for (char a = 'a'; a <= 'z'; a++)
+        for (char b = 'a'; b <= 'z'; b++)
+            if (a != b && vowels.find(a) == std::string::npos && vowels.find(b) == std::string::npos) m[{(uint32_t)a, (uint32_t)b}] = 0.4f;
+    auto both = [&](char a, char b, float v) { m[{(uint32_t)a, (uint32_t)b}] = v; m[{(uint32_t)b, (uint32_t)a}] = v; };
+    both('o', '0', 0.6f); both('l', '1', 0.7f); both('i', '1', 0.6f); both('s', '5', 0.5f);
+}
+
+static bool k_from_limits(const FacLimits &l, size_t &k) {  // src/prefilter.rs:388-405
+    if (l.edits >= 0) { k = (l.swp == 0) ? (size_t)l.edits : 2 * (size_t)l.edits; return true; }
+    if (l.ins < 0 || l.del < 0 || l.sub < 0 || l.swp < 0) return false;
+    k = (size_t)l.ins + (size_t)l.del + (size_t)l.sub + 2 * (size_t)l.swp;
+    return true;
+}
+
+fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_t np, HostAutomaton &A, std::string &err) {
+    if (!cfg || (np && !pats)) { err = "null config or patterns"; return FAC_INVALID_ARGUMENT; }
+    A.ci = cfg->case_insensitive != 0;
+    {   // FuzzyPenalties::default(), src/structs.rs:381-393 -- f32 products
+        const float m = 1.3f;
+        volatile float s = 1.1f * m, i = 0.4f * m, d = 0.7f * m, w = 0.4f * m;
+        A.pen_sub = s; A.pen_ins = i; A.pen_del = d; A.pen_swap = w;
+    }
+    if (cfg->has_penalties) {
+        A.pen_sub = cfg->penalty_substitution; A.pen_ins = cfg->penalty_insertion;
+        A.pen_del = cfg->penalty_deletion; A.pen_swap = cfg->penalty_swap;
+    }
+    A.min_sym = cfg->min_symbol_similarity;
+    A.beam_width = cfg->beam_width;
+    A.has_auto_beam = cfg->has_auto_beam != 0;
+    A.ab_budget = cfg->auto_beam_budget; A.ab_width = cfg->auto_beam_width;
+
+    // ---- patterns ----
+    A.patterns.clear();
+    for (size_t i = 0; i < np; i++) {
+        HostPattern p;
+        if (pats[i].len && !pats[i].text) { err = "pattern with null text"; return FAC_INVALID_ARGUMENT; }
+        p.text.assign(pats[i].text ? pats[i].text : "", pats[i].len);
+        if (utf8_valid_up_to((const uint8_t *)p.text.data(), p.text.size()) != p.text.size()) {
+            err = "pattern " + std::to_string(i) + " is not valid UTF-8";
+            return FAC_INVALID_UTF8;
+        }
+        p.glen = (uint32_t)count_graphemes(p.text);
+        p.byte_len = (uint32_t)p.text.size();
+        p.weight = pats[i].weight;
+        p.has_limits = pats[i].has_limits != 0;
+        if (p.has_limits) p.limits = limits_from_c(pats[i].limits, true);  // Pattern::fuzzy, src/structs.rs:647-650
+        p.unique_id = pats[i].unique_id;
+        A.patterns.push_back(std::move(p));
+    }
+
+    // ---- trie (src/builder.rs:195-237) ----
+    std::vector<TmpNode> nodes(1);
+    for (size_t i = 0; i < A.patterns.size(); i++) {
+        const std::vector<std::string> word = fold_graphemes(A.patterns[i].text, A.ci);
+        uint32_t cur = 0;
+        for (const std::string &g : word) {
+            uint32_t next;
+            auto it = nodes[cur].trans.find(g);
+            if (it != nodes[cur].trans.end()) next = it->second;
+            else {
+                next = (uint32_t)nodes.size();
+                nodes[cur].trans.emplace(g, next);
+                nodes[cur].order.emplace_back(g, next);
+                nodes.emplace_back();
+            }
+            if (nodes[next].pattern_index < 0) nodes[next].pattern_index = (int64_t)i;
+            cur = next;
+        }
+        nodes[cur].output.push_back((uint32_t)i);
+    }
+    if (nodes.size() >= 0x7FFFFFFFull) { err = "too many trie nodes"; return FAC_UNSUPPORTED; }
+
+    // ---- fail links + output merge (src/builder.rs:240-276) ----
+    {
+        std::deque<uint32_t> q;
+        for (auto &kv : nodes[0].order) { nodes[kv.second].fail = 0; q.push_back(kv.second); }
+        while (!q.empty()) {
+            const uint32_t cur = q.front();
+            q.pop_front();
+            for (auto &kv : nodes[cur].order) {
+                const uint32_t next = kv.second;
+                uint32_t f = nodes[cur].fail;
+                while (f != 0 && !nodes[f].trans.count(kv.first)) f = nodes[f].fail;
+                uint32_t fallback = 0;
+                auto it = nodes[f].trans.find(kv.first);
+                if (it != nodes[f].trans.end()) fallback = it->second;
+                nodes[next].fail = fallback;
+                if (fallback != next) {
+                    const std::vector<uint32_t> fo = nodes[fallback].output;
+                    for (uint32_t e : fo)
+                        if (std::find(nodes[next].output.begin(), nodes[next].output.end(), e) == nodes[next].output.end())
+                            nodes[next].output.push_back(e);
+                }
+                q.push_back(next);
+            }
+        }
+    }
+
+    // ---- effective limits (src/builder.rs:289-329) ----
+    A.lim.clear();
+    FacLimits global;
+    memset(&global, 0, sizeof(global));
+    global.ins = global.del = global.sub = global.swp = global.edits = -1;
+    A.has_global_limits = false;
+    if (cfg->has_limits) { A.has_global_limits = true; global = limits_from_c(cfg->limits, true); }
+    else {
+        bool any = false;
+        for (auto &p : A.patterns)
+            if (p.has_limits) {
+                any = true;
+                auto up = [](int16_t &acc, int16_t v) { if (v >= 0) acc = std::max<int16_t>(std::max<int16_t>(acc, 0), v); };
+                up(global.edits, p.limits.edits); up(global.ins, p.limits.ins); up(global.del, p.limits.del);
+                up(global.sub, p.limits.sub); up(global.swp, p.limits.swp);
+            }
+        A.has_global_limits = any;
+    }
+    A.lim.push_back(global);
+    A.has_pattern_limits = false;
+    A.pat_lim.assign(A.patterns.size(), FAC_NONE);
+    for (size_t i = 0; i < A.patterns.size(); i++)
+        if (A.patterns[i].has_limits) {
+            A.has_pattern_limits = true;
+            A.pat_lim[i] = (uint32_t)A.lim.size();
+            A.lim.push_back(A.patterns[i].limits);
+        }
+    // max_edits_fast (src/builder.rs:451-468) and its dispatch (src/search.rs:205-247)
+    if (A.has_pattern_limits) A.max_edits_fast_raw = 255;
+    else if (!A.has_global_limits) A.max_edits_fast_raw = 0;
+    else if (global.edits >= 0 && global.ins < 0 && global.del < 0 && global.sub < 0 && global.swp < 0) A.max_edits_fast_raw = global.edits;
+    else A.max_edits_fast_raw = 255;
+    A.mef = (A.max_edits_fast_raw >= 1 && A.max_edits_fast_raw <= 6) ? A.max_edits_fast_raw : 255;
+
+    // ---- grapheme ids + mappings (src/builder.rs:390-442) ----
+    struct Directed { std::vector<std::string> pat, hay; float pen; };
+    std::vector<Directed> directed;
+    for (size_t k = 0; k < cfg->n_mappings; k++) {
+        const fac_mapping &mp = cfg->mappings[k];
+        const std::string a(mp.a ? mp.a : "", mp.a_len), b(mp.b ? mp.b : "", mp.b_len);
+        if (utf8_valid_up_to((const uint8_t *)a.data(), a.size()) != a.size() ||
+            utf8_valid_up_to((const uint8_t *)b.data(), b.size()) != b.size()) { err = "mapping is not valid UTF-8"; return FAC_INVALID_UTF8; }
+        const std::vector<std::string> ga = fold_graphemes(a, A.ci), gb = fold_graphemes(b, A.ci);
+        if (ga.empty() || gb.empty() || ga == gb) continue;
+        const float pen = A.pen_sub * (1.0f - mp.score);
+        directed.push_back({ga, gb, pen});
+        directed.push_back({gb, ga, pen});
+    }
+    const size_t N = nodes.size();
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> node_maps(N);  // (directed idx, reached node)
+    A.has_mappings = false;
+    A.max_map_hay = 1;
+    {
+        size_t mmh = 0;
+        for (size_t start = 0; start < N && !directed.empty(); start++)
+            for (size_t d = 0; d < directed.size(); d++) {
+                uint32_t cur = (uint32_t)start;
+                bool ok = true;
+                for (const std::string &g : directed[d].pat) {
+                    auto it = nodes[cur].trans.find(g);
+                    if (it == nodes[cur].trans.end()) { ok = false; break; }
+                    cur = it->second;
+                }
+                if (ok) { node_maps[start].emplace_back((uint32_t)d, cur); A.has_mappings = true; mmh = std::max(mmh, directed[d].hay.size()); }
+            }
+        A.max_map_hay = (uint32_t)std::max<size_t>(mmh, 1);
+    }
+    std::unordered_map<std::string, uint32_t> gid_of;
+    std::vector<std::string> gid_syms;
+    auto intern = [&](const std::string &g) -> uint32_t {
+        auto it = gid_of.find(g);
+        if (it != gid_of.end()) return it->second;
+        gid_syms.push_back(g);
+        gid_of.emplace(g, (uint32_t)gid_syms.size());
+        return (uint32_t)gid_syms.size();
+    };
+    if (A.has_mappings) {
+        for (auto &nd : nodes) for (auto &kv : nd.order) intern(kv.first);
+        for (auto &d : directed) for (auto &g : d.hay) intern(g);
+    }
+
+    // ---- flatten nodes / edges ----
+    A.node_edge_off.assign(N + 1, 0); A.node_out_off.assign(N + 1, 0); A.node_map_off.assign(N + 1, 0);
+    A.node_bitmap.assign(N * 4, 0); A.node_lim.assign(N, FAC_NONE);
+    A.edge_char.clear(); A.edge_next.clear(); A.out_pat.clear();
+    A.map_hay_off.assign(1, 0); A.map_hay_gid.clear(); A.map_next.clear(); A.map_pen.clear();
+    size_t n_trans = 0;
+    for (size_t i = 0; i < N; i++) {
+        A.node_edge_off[i] = (uint32_t)A.edge_char.size();
+        A.node_out_off[i] = (uint32_t)A.out_pat.size();
+        A.node_map_off[i] = (uint32_t)A.map_next.size();
+        for (auto &kv : nodes[i].order) {  // Edge::new(first char, next, g.len()==1), src/builder.rs:336-342
+            const uint32_t fc = first_scalar(kv.first);
+            A.edge_char.push_back(fc);
+            A.edge_next.push_back(kv.second | (nodes[kv.second].output.empty() ? 0u : 0x80000000u));
+            if (kv.first.size() == 1 && fc < 128) A.node_bitmap[i * 4 + (fc >> 5)] |= 1u << (fc & 31);
+            n_trans++;
+        }
+        for (uint32_t p : nodes[i].output) A.out_pat.push_back(p);
+        for (auto &mp : node_maps[i]) {
+            const Directed &d = directed[mp.first];
+            for (auto &g : d.hay) A.map_hay_gid.push_back(gid_of[g]);
+            A.map_hay_off.push_back((uint32_t)A.map_hay_gid.size());
+            A.map_next.push_back(mp.second);
+            A.map_pen.push_back(d.pen);
+        }
+        if (nodes[i].pattern_index >= 0) A.node_lim[i] = A.pat_lim[(size_t)nodes[i].pattern_index];  // get_node_limits, src/search.rs:67-71
+    }
+    A.node_edge_off[N] = (uint32_t)A.edge_char.size();
+    A.node_out_off[N] = (uint32_t)A.out_pat.size();
+    A.node_map_off[N] = (uint32_t)A.map_next.size();
+
+    // ---- exact-transition table ----
+    {
+        size_t cap = 64;
+        while (cap < n_trans * 2 + 2) cap <<= 1;
+        A.trans.assign(cap, FacTrans{FAC_NONE, 0, 0, 0});
+        const uint32_t mask = (uint32_t)(cap - 1);
+        for (size_t i = 0; i < N; i++)
+            for (auto &kv : nodes[i].order) {
+                const uint32_t sym = A.has_mappings ? gid_of[kv.first] : first_scalar(kv.first);
+                uint32_t h = fac_hash2((uint32_t)i, sym) & mask;
+                bool dup = false;
+                while (A.trans[h].node != FAC_NONE) {
+                    if (A.trans[h].node == (uint32_t)i && A.trans[h].sym == sym) { dup = true; break; }  // first edge in build order wins
+                    h = (h + 1) & mask;
+                }
+                if (!dup) A.trans[h] = FacTrans{(uint32_t)i, sym, kv.second, 0};
+            }
+    }
+
+    // ---- prune coefficients (src/builder.rs:348-381) ----
+    {
+        std::vector<size_t> rl(N, 0);
+        std::vector<float> rw(N, 0.f);
+        for (size_t i = 0; i < N; i++)
+            for (uint32_t p : nodes[i].output) { rl[i] = std::max<size_t>(rl[i], A.patterns[p].glen); rw[i] = std::max(rw[i], A.patterns[p].weight); }
+        for (size_t i = N; i-- > 0;)  // children have higher indices than parents: one reverse pass
+            for (auto &kv : nodes[i].order) { rl[i] = std::max(rl[i], rl[kv.second]); rw[i] = std::max(rw[i], rw[kv.second]); }
+        A.node_prune_len.resize(N); A.node_prune_low.resize(N);
+        for (size_t i = 0; i < N; i++) {
+            const float len = (float)rl[i];
+            A.node_prune_len[i] = len;
+            A.node_prune_low[i] = len / rw[i];
+        }
+    }
+
+    // ---- patterns / similarity ----
+    A.pat_glen.resize(A.patterns.size()); A.pat_weight.resize(A.patterns.size());
+    A.pat_bytes.resize(A.patterns.size()); A.pat_uid.resize(A.patterns.size());
+    for (size_t i = 0; i < A.patterns.size(); i++) {
+        A.pat_glen[i] = (float)A.patterns[i].glen;
+        A.pat_weight[i] = A.patterns[i].weight;
+        A.pat_bytes[i] = A.patterns[i].byte_len;
+        // UniqueId derives Ord with Automatic < Custom (src/structs.rs:586-592)
+        A.pat_uid[i] = A.patterns[i].unique_id >= 0 ? ((int64_t)1 << 62) | A.patterns[i].unique_id : (int64_t)i;
+    }
+    std::map<std::pair<uint32_t, uint32_t>, float> simmap;
+    if (cfg->has_similarity) for (size_t i = 0; i < cfg->n_similarity; i++) simmap[{cfg->similarity[i].a, cfg->similarity[i].b}] = cfg->similarity[i].similarity;
+    else build_default_similarity(simmap);
+    A.sim_ascii.assign(128 * 128, 0.f);
+    for (int i = 0; i < 128; i++) A.sim_ascii[i * 128 + i] = 1.f;
+    A.sim_keys.clear(); A.sim_vals.clear();
+    float max_off_diag = 0.f;  // Similarity::max_off_diagonal, src/structs.rs:61-76
+    for (auto &kv : simmap) {
+        const uint32_t a = kv.first.first, b = kv.first.second;
+        if (a < 128 && b < 128) A.sim_ascii[a * 128 + b] = kv.second;
+        else { A.sim_keys.push_back(((uint64_t)a << 32) | b); A.sim_vals.push_back(kv.second); }  // std::map order == sorted keys
+        if (a != b && !(a < 128 && b < 128)) max_off_diag = std::max(max_off_diag, kv.second);
+    }
+    for (int i = 0; i < 128; i++) for (int j = 0; j < 128; j++) if (i != j) max_off_diag = std::max(max_off_diag, A.sim_ascii[i * 128 + j]);
+
+    // ---- grapheme-id tables ----
+    A.ascii_gid.assign(128, 0);
+    if (A.has_mappings) {
+        build_symbol_table(gid_syms, A.symbols, A.symbol_pool);
+        for (int b = 0; b < 128; b++) {
+            auto it = gid_of.find(std::string(1, (char)b));
+            if (it != gid_of.end()) A.ascii_gid[b] = it->second;
+        }
+    } else { A.symbols.assign(1, HostSymbol{0, 0, 0, 0, 0}); A.symbol_pool.assign(8, 0); }
+
+    // ---- window skip bitmaps (src/search.rs:504-521) ----
+    A.wskip = false;
+    if (A.mef == 1 && !A.has_mappings && nodes[0].output.empty()) {
+        bool child_output = false;
+        uint32_t first[4], second[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 4; k++) first[k] = A.node_bitmap[k];
+        for (auto &kv : nodes[0].order) {
+            for (int k = 0; k < 4; k++) { second[k] |= A.node_bitmap[kv.second * 4 + k]; first[k] |= A.node_bitmap[kv.second * 4 + k]; }
+            if (!nodes[kv.second].output.empty()) child_output = true;
+        }
+        if (!child_output) { A.wskip = true; for (int k = 0; k < 4; k++) { A.ws_first[k] = first[k]; A.ws_second[k] = second[k]; } }
+    }
+
+    // ---- max_match_graphemes (src/stream.rs:213-253) ----
+    {
+        size_t max_pattern = 0, max_edits = 0;
+        auto edits_of = [](const FacLimits &l) -> size_t {
+            if (l.edits >= 0) return (size_t)l.edits;
+            return (size_t)std::max<int>(l.ins, 0) + (size_t)std::max<int>(l.del, 0) + (size_t)std::max<int>(l.sub, 0) + (size_t)std::max<int>(l.swp, 0);
+        };
+        for (auto &p : A.patterns) {
+            max_pattern = std::max<size_t>(max_pattern, p.glen);
+            size_t e = 0;
+            if (p.has_limits) e = edits_of(p.limits);
+            else if (A.has_global_limits) e = edits_of(global);
+            max_edits = std::max(max_edits, e);
+        }
+        A.max_match_graphemes = max_pattern + max_edits * A.max_map_hay;
+    }
+    if (A.max_match_graphemes + 3 > FAC_MAX_SPAN) {
+        err = "max_match_graphemes() = " + std::to_string(A.max_match_graphemes) + " exceeds the device state layout (" + std::to_string(FAC_MAX_SPAN - 3) + ")";
+        return FAC_UNSUPPORTED;
+    }
+
+    // ---- bitap pre-filter model (BitapFilter::build, src/prefilter.rs:161-245) ----
+    HostBitap &B = A.bitap;
+    B = HostBitap();
+    do {
+        if (A.has_mappings || A.patterns.empty()) break;
+        const float p_sub_min = A.pen_sub * (1.0f - max_off_diag);
+        const float mults[4] = {1.0f / A.pen_ins, 1.0f / A.pen_del, 1.0f / p_sub_min, 2.0f / A.pen_swap};
+        bool bad = false;
+        float mult = 0.f;
+        for (float m : mults) { if (!std::isfinite(m) || m <= 0.0f) bad = true; mult = std::max(mult, m); }
+        if (bad) break;
+        std::unordered_map<std::string, uint32_t> ids;
+        std::vector<std::string> id_syms;
+        std::vector<std::vector<uint32_t>> pat_ids;
+        bool ok = true;
+        for (auto &p : A.patterns) {
+            const std::vector<std::string> gs = fold_graphemes(p.text, A.ci);
+            if (gs.empty() || gs.size() > 63) { ok = false; break; }
+            std::vector<uint32_t> v;
+            for (auto &g : gs) {
+                auto it = ids.find(g);
+                uint32_t id;
+                if (it == ids.end()) { id = (uint32_t)ids.size() + 1; ids.emplace(g, id); id_syms.push_back(g); } else id = it->second;
+                if (id > 255) { ok = false; break; }
+                v.push_back(id);
+            }
+            if (!ok) break;
+            pat_ids.push_back(v);
+            B.m.push_back((uint32_t)gs.size());
+            B.weight.push_back(p.weight);
+            size_t kl = 0;
+            bool has = false;
+            if (p.has_limits) has = k_from_limits(p.limits, kl);
+            else if (A.has_global_limits) has = k_from_limits(global, kl);
+            B.k_limit.push_back(has ? (int32_t)std::min<size_t>(kl, 1u << 20) : -1);
+        }
+        if (!ok) { B = HostBitap(); break; }
+        B.edit_cost_mult = mult;
+        B.alphabet = (uint32_t)ids.size();
+        for (int b = 0; b < 128; b++) {
+            std::string f(1, (char)((A.ci && b >= 'A' && b <= 'Z') ? b + 32 : b));
+            auto it = ids.find(f);
+            if (it != ids.end()) B.ascii_id[b] = (uint8_t)it->second;
+        }
+        B.masks.assign(pat_ids.size() * (size_t)(B.alphabet + 1), 0);
+        for (size_t i = 0; i < pat_ids.size(); i++)
+            for (size_t k = 0; k < pat_ids[i].size(); k++) B.masks[i * (B.alphabet + 1) + pat_ids[i][k]] |= 1ull << k;
+        build_symbol_table(id_syms, B.symbols, B.symbol_pool);
+        B.active = true;
+    } while (0);
+    if (!B.active) { B.symbols.assign(1, HostSymbol{0, 0, 0, 0, 0}); B.symbol_pool.assign(8, 0); }
+    return FAC_OK;
+}
+
+AutomatonView HostAutomaton::host_view() const {
+    AutomatonView V;
+    memset(&V, 0, sizeof(V));
+    V.n_nodes = n_nodes(); V.n_edges = (uint32_t)edge_char.size(); V.n_patterns = (uint32_t)patterns.size(); V.n_outputs = (uint32_t)out_pat.size();
+    V.node_edge_off = node_edge_off.data(); V.node_prune_len = node_prune_len.data(); V.node_prune_low = node_prune_low.data();
+    V.node_out_off = node_out_off.data(); V.node_bitmap = node_bitmap.data(); V.node_lim = node_lim.data(); V.node_map_off = node_map_off.data();
+    V.edge_char = edge_char.data(); V.edge_next = edge_next.data();
+    V.trans = trans.data(); V.trans_mask = (uint32_t)trans.size() - 1;
+    V.out_pat = out_pat.data(); V.pat_glen = pat_glen.data(); V.pat_weight = pat_weight.data(); V.pat_lim = pat_lim.data(); V.lim = lim.data();
+    V.sim_ascii = sim_ascii.data(); V.sim_keys = sim_keys.data(); V.sim_vals = sim_vals.data(); V.n_sim = (uint32_t)sim_keys.size();
+    V.map_hay_off = map_hay_off.data(); V.map_hay_gid = map_hay_gid.data(); V.map_next = map_next.data(); V.map_pen = map_pen.data();
+    V.ascii_gid = ascii_gid.data();
+    V.pen_sub = pen_sub; V.pen_ins = pen_ins; V.pen_del = pen_del; V.pen_swap = pen_swap; V.min_sym = min_sym;
+    V.mef = mef; V.has_mappings = has_mappings; V.has_pattern_limits = has_pattern_limits; V.has_global_limits = has_global_limits; V.ci = ci;
+    V.wskip = wskip;
+    for (int k = 0; k < 4; k++) { V.ws_first[k] = ws_first[k]; V.ws_second[k] = ws_second[k]; }
+    return V;
+}
+
+}  // namespace fac

@@ -1,0 +1,101 @@
+// fac_builder.h -- host-side automaton construction and flattening.
+//
+// Restates FuzzyAhoCorasickBuilder::build (src/builder.rs:181-484) for the B200 layout: the trie,
+// the output merge along fail links, derived limits, prune coefficients and mapping transitions
+// are computed on the host (build is not on the timed path) and emitted directly as the CSR /
+// dense arrays of fac_types.h, ready for one bulk upload into HBM.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/fac.h"
+#include "fac_types.h"
+#include "fac_unicode.h"
+
+namespace fac {
+
+const UnicodeTables &host_unicode_tables();
+
+// `graphemes(true)` + optional per-grapheme `to_lowercase` of a UTF-8 string.
+std::vector<std::string> fold_graphemes(const std::string &s, bool case_insensitive);
+size_t count_graphemes(const std::string &s);
+// Strict UTF-8 validation (what `str::from_utf8` accepts): returns valid_up_to.
+size_t utf8_valid_up_to(const uint8_t *s, size_t n);
+
+struct HostPattern {
+    std::string text;
+    uint32_t glen = 0;     // graphemes of the original text (src/structs.rs:664)
+    uint32_t byte_len = 0; // Pattern::len() (src/structs.rs:628-630)
+    float weight = 1.f;
+    bool has_limits = false;
+    FacLimits limits{};    // finalized
+    int64_t unique_id = -1;
+};
+
+// One symbol of the grapheme-id table (engines with mappings): folded grapheme text -> id >= 1.
+struct HostSymbol {  // layout must equal FacSymbol (fac_unicode.h)
+    uint64_t hash;
+    uint32_t gid;
+    uint32_t pool_off;
+    uint32_t len;
+    uint32_t pad;
+};
+
+// Bitap pre-filter model (BitapFilter, src/prefilter.rs:66-93 / build :161-245).
+struct HostBitap {
+    bool active = false;
+    float edit_cost_mult = 0.f;
+    uint32_t alphabet = 0;                 // symbol ids are 1..=alphabet, 0 = other
+    uint8_t ascii_id[128] = {0};
+    std::vector<HostSymbol> symbols;       // folded grapheme -> id (hash table content, ids <= 255)
+    std::vector<uint8_t> symbol_pool;
+    std::vector<uint32_t> m;               // per pattern: length in graphemes
+    std::vector<float> weight;             // per pattern
+    std::vector<int32_t> k_limit;          // per pattern: -1 = none
+    std::vector<uint64_t> masks;           // [P * (alphabet+1)]
+};
+
+struct HostAutomaton {
+    // flattened arrays, exactly the members of AutomatonView
+    std::vector<uint32_t> node_edge_off, node_out_off, node_bitmap, node_lim, node_map_off;
+    std::vector<float> node_prune_len, node_prune_low;
+    std::vector<uint32_t> edge_char, edge_next;
+    std::vector<FacTrans> trans;
+    std::vector<uint32_t> out_pat;
+    std::vector<float> pat_glen, pat_weight;
+    std::vector<uint32_t> pat_lim, pat_bytes;
+    std::vector<int64_t> pat_uid;  // UniqueId ordering key: (custom? 1:0)<<62 | id
+    std::vector<FacLimits> lim;
+    std::vector<float> sim_ascii;
+    std::vector<uint64_t> sim_keys;
+    std::vector<float> sim_vals;
+    std::vector<uint32_t> map_hay_off, map_hay_gid, map_next;
+    std::vector<float> map_pen;
+    std::vector<uint32_t> ascii_gid;
+    std::vector<HostSymbol> symbols;  // open-addressing table (size power of two), gid 0 = empty
+    std::vector<uint8_t> symbol_pool;
+    // scalars
+    float pen_sub, pen_ins, pen_del, pen_swap, min_sym;
+    int32_t mef = 255;              // after dispatch (1..6 or 255)
+    int32_t max_edits_fast_raw = 0; // the reference's field (0, 1.., 255)
+    bool has_mappings = false, has_pattern_limits = false, has_global_limits = false, ci = false;
+    bool wskip = false;
+    uint32_t ws_first[4] = {0, 0, 0, 0}, ws_second[4] = {0, 0, 0, 0};
+    uint64_t beam_width = 0;  // 0 = None
+    bool has_auto_beam = false;
+    uint64_t ab_budget = 0, ab_width = 0;
+    size_t max_match_graphemes = 0;  // src/stream.rs:213-253
+    uint32_t max_map_hay = 1;
+    std::vector<HostPattern> patterns;
+    HostBitap bitap;
+
+    uint32_t n_nodes() const { return (uint32_t)node_prune_len.size(); }
+    // View over the host vectors (used by the CPU-side emulator in tests).
+    AutomatonView host_view() const;
+};
+
+// Returns FAC_OK or an error status with `err` filled.
+fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_t n, HostAutomaton &out, std::string &err);
+
+}  // namespace fac
