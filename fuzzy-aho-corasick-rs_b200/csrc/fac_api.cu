@@ -1,0 +1,836 @@
+// fac_api.cu -- the C ABI of include/fac.h over the sm_100a kernels.
+//
+// Host orchestration only: device memory, one stream per in-flight call (workspaces are pooled so
+// an engine is re-entrant), kernel launches, and the small synchronous read-backs the control flow
+// needs (classification flag, counters).  There is NO CPU implementation of the search path here:
+// every entry point fails with FAC_CUDA_ERROR when no device is usable.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fac.h"
+#include "fac_apply.cuh"
+#include "fac_builder.h"
+#include "fac_kernels.cuh"
+#include "fac_segment.cuh"
+
+#define FAC_TABLE_QUAL static const
+#include "unicode_tables.h"
+
+namespace {
+
+thread_local std::string g_err;
+thread_local uint64_t g_last_graphemes = 0;
+
+void set_err(const std::string &s) { g_err = s; }
+
+#define CK(call)                                                                                                  \
+    do {                                                                                                          \
+        cudaError_t e_ = (call);                                                                                  \
+        if (e_ != cudaSuccess) {                                                                                  \
+            set_err(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+            return e_ == cudaErrorMemoryAllocation ? FAC_OOM : FAC_CUDA_ERROR;                                    \
+        }                                                                                                         \
+    } while (0)
+#define CKS(call)                     \
+    do {                              \
+        fac_status s_ = (call);       \
+        if (s_ != FAC_OK) return s_;  \
+    } while (0)
+
+struct DBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    fac_status ensure(size_t bytes) {
+        if (bytes <= cap && p) return FAC_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { set_err(std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e)); p = nullptr; return FAC_OOM; }
+        cap = want;
+        return FAC_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+inline uint32_t next_pow2(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return (uint32_t)std::min<uint64_t>(p, 1ull << 31); }
+inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+struct U8ToU32 {
+    __host__ __device__ __forceinline__ uint32_t operator()(const uint8_t &v) const { return v; }
+};
+
+struct SearchStats {
+    uint64_t states = 0;
+    double device_ms = 0, expand_ms = 0;
+    uint32_t launches = 0;
+};
+
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, evk0 = nullptr, evk1 = nullptr;
+    DBuf hay, mark, gidx, first, gid, off, pfsym;
+    DBuf queue, nxt, hslot, gtab_rep, gtab_head, gtab_min;
+    uint32_t grid = 0, qcap = 0, gtab_size = 0;
+    DBuf cands, counters, failed_tiles, failed_bitmap, tiles;
+    DBuf best_rep, best_val, cslot;
+    DBuf m_a, m_b, idx_a, idx_b, winend, st_a, st_b, flags8, sel, nsel, outm, keep8, windows, misc, cubtmp, used;
+    uint64_t *h_counters = nullptr;  // pinned
+    uint32_t *h_flags = nullptr;     // pinned
+    fac_status init() {
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&ev_begin)); CK(cudaEventCreate(&ev_end)); CK(cudaEventCreate(&evk0)); CK(cudaEventCreate(&evk1));
+        CK(cudaMallocHost(&h_counters, 16 * sizeof(uint64_t)));
+        CK(cudaMallocHost(&h_flags, 16 * sizeof(uint32_t)));
+        return FAC_OK;
+    }
+    void destroy() {
+        for (DBuf *b : {&hay, &mark, &gidx, &first, &gid, &off, &pfsym, &queue, &nxt, &hslot, &gtab_rep, &gtab_head, &gtab_min, &cands, &counters,
+                        &failed_tiles, &failed_bitmap, &tiles, &best_rep, &best_val, &cslot, &m_a, &m_b, &idx_a, &idx_b, &winend, &st_a, &st_b,
+                        &flags8, &sel, &nsel, &outm, &keep8, &windows, &misc, &cubtmp, &used})
+            b->release();
+        if (h_counters) cudaFreeHost(h_counters);
+        if (h_flags) cudaFreeHost(h_flags);
+        if (ev_begin) cudaEventDestroy(ev_begin);
+        if (ev_end) cudaEventDestroy(ev_end);
+        if (evk0) cudaEventDestroy(evk0);
+        if (evk1) cudaEventDestroy(evk1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+}  // namespace
+
+struct fac_engine {
+    int device = 0;
+    fac::HostAutomaton host;
+    AutomatonView dview;
+    std::vector<void *> dallocs;
+    UnicodeTables dU;
+    FacSymbol *d_symbols = nullptr;
+    uint32_t sym_mask = 0;
+    uint8_t *d_pool = nullptr;
+    uint32_t *d_pat_bytes = nullptr;
+    uint32_t *d_pat_uid_dense = nullptr;
+    uint32_t n_uid = 0;
+    int sm_count = 148;
+    uint32_t lookahead = 0;
+    uint32_t default_tile = 0;  // 0 = adaptive
+    uint32_t qcap = 1u << 17;
+    uint32_t smem_tab = 4096;
+    int ctas_per_sm = 2;
+    int use_tma = 1;
+    mutable std::mutex mu;
+    mutable std::vector<Workspace *> pool;
+};
+
+struct fac_matches {
+    std::vector<fac_match> v;
+    SearchStats stats;
+};
+
+namespace {
+
+template <class T>
+fac_status upload(fac_engine *E, const std::vector<T> &v, const T **out) {
+    void *p = nullptr;
+    const size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    CK(cudaMalloc(&p, bytes));
+    E->dallocs.push_back(p);
+    if (!v.empty()) CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T *)p;
+    return FAC_OK;
+}
+template <class T>
+fac_status upload_raw(fac_engine *E, const T *src, size_t n, const T **out) {
+    std::vector<T> v(src, src + n);
+    return upload(E, v, out);
+}
+
+Workspace *acquire_ws(const fac_engine *E, fac_status &st) {
+    {
+        std::lock_guard<std::mutex> g(E->mu);
+        if (!E->pool.empty()) { Workspace *w = E->pool.back(); E->pool.pop_back(); st = FAC_OK; return w; }
+    }
+    Workspace *w = new Workspace();
+    st = w->init();
+    if (st != FAC_OK) { w->destroy(); delete w; return nullptr; }
+    return w;
+}
+void release_ws(const fac_engine *E, Workspace *w) {
+    std::lock_guard<std::mutex> g(E->mu);
+    E->pool.push_back(w);
+}
+
+int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+template <bool ASCII, bool MAPP>
+fac_status launch_expand_t(const ExpandParams &P, uint32_t grid, size_t smem, cudaStream_t s) {
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_expand<ASCII, MAPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_expand<ASCII, MAPP><<<grid, FAC_BLOCK, smem, s>>>(P);
+    CK(cudaGetLastError());
+    return FAC_OK;
+}
+fac_status launch_expand(const ExpandParams &P, uint32_t grid, size_t smem, cudaStream_t s) {
+    const bool ascii = P.tv.ascii != 0, mapp = P.A.has_mappings != 0;
+    if (ascii && !mapp) return launch_expand_t<true, false>(P, grid, smem, s);
+    if (ascii && mapp) return launch_expand_t<true, true>(P, grid, smem, s);
+    if (!ascii && !mapp) return launch_expand_t<false, false>(P, grid, smem, s);
+    return launch_expand_t<false, true>(P, grid, smem, s);
+}
+
+size_t expand_smem_bytes(const fac_engine *E, bool ascii, uint32_t text_cap) {
+    const size_t tb = ascii ? ((text_cap + 31u) & ~15u) : ((text_cap * 4u + 31u) & ~15u);
+    const size_t mult = (!ascii && E->host.has_mappings) ? 2 : 1;
+    return tb * mult + (size_t)E->smem_tab * 8;
+}
+
+// Make sure the per-CTA expansion scratch exists for `grid` CTAs of `qcap` states.
+fac_status ensure_scratch(const fac_engine *E, Workspace *ws, uint32_t grid, uint32_t qcap) {
+    const uint32_t gts = next_pow2((uint64_t)qcap * 2);
+    const bool fresh_tab = ws->gtab_rep.cap < (size_t)grid * gts * 4 || ws->grid != grid || ws->qcap != qcap;
+    CKS(ws->queue.ensure((size_t)grid * qcap * sizeof(FacState)));
+    CKS(ws->nxt.ensure((size_t)grid * qcap * 4));
+    CKS(ws->hslot.ensure((size_t)grid * qcap * 4));
+    CKS(ws->gtab_rep.ensure((size_t)grid * gts * 4));
+    CKS(ws->gtab_head.ensure((size_t)grid * gts * 4));
+    CKS(ws->gtab_min.ensure((size_t)grid * gts * 4));
+    if (fresh_tab) {
+        CK(cudaMemsetAsync(ws->gtab_rep.p, 0xFF, (size_t)grid * gts * 4, ws->stream));
+        CK(cudaMemsetAsync(ws->gtab_head.p, 0xFF, (size_t)grid * gts * 4, ws->stream));
+        k_fill_u32<<<1184, 256, 0, ws->stream>>>(ws->gtab_min.as<uint32_t>(), 0x7F800000u, (uint64_t)grid * gts);  // +inf
+        CK(cudaGetLastError());
+    }
+    ws->grid = grid; ws->qcap = qcap; ws->gtab_size = gts;
+    return FAC_OK;
+}
+
+// m_a must be able to grow while keeping its contents: ensure() frees, so grow through a copy.
+fac_status grow_keep(DBuf &b, size_t keep_bytes, size_t want_bytes, cudaStream_t s) {
+    if (want_bytes <= b.cap) return FAC_OK;
+    DBuf nb;
+    CKS(nb.ensure(want_bytes * 2));
+    if (keep_bytes) CK(cudaMemcpyAsync(nb.p, b.p, keep_bytes, cudaMemcpyDeviceToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    b.release();
+    b = nb;
+    return FAC_OK;
+}
+
+struct ExpandRun {
+    // description of what to expand
+    TextView tv;
+    std::vector<uint4> tiles;     // mode 1 descriptors (empty => mode 0)
+    uint32_t seg_begin = 0, seg_end = 0, text_end = 0;
+    const FacWindow *d_windows = nullptr;
+    float thr = 0.f;
+    uint32_t *d_per_window = nullptr;
+};
+
+// Run K3 (+ retry of failed tiles) and the best-per-span reduction; appends WMatch records to
+// ws->m_a starting at *n_matches.
+fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun &R, uint32_t tile, uint64_t *n_matches, SearchStats &stats,
+                             double *states_per_window_out) {
+    cudaStream_t s = ws->stream;
+    const bool ascii = R.tv.ascii != 0;
+    const bool explicit_tiles = !R.tiles.empty();
+    const uint64_t n_windows_total = explicit_tiles ? 0 : (uint64_t)(R.seg_end - R.seg_begin);
+    uint32_t n_tiles = explicit_tiles ? (uint32_t)R.tiles.size() : cdiv(n_windows_total, tile);
+    if (n_tiles == 0) return FAC_OK;
+    uint32_t max_count = tile;
+    if (explicit_tiles) { max_count = 1; for (auto &t : R.tiles) max_count = std::max(max_count, t.y); }
+
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)E->sm_count * E->ctas_per_sm, n_tiles);
+    CKS(ensure_scratch(E, ws, (uint32_t)E->sm_count * E->ctas_per_sm, E->qcap));
+    uint32_t cand_cap = (uint32_t)std::max<size_t>(ws->cands.cap / sizeof(FacCand), 1u << 20);
+    CKS(ws->cands.ensure((size_t)cand_cap * sizeof(FacCand)));
+    cand_cap = (uint32_t)std::min<size_t>(ws->cands.cap / sizeof(FacCand), 0x7FFFFFF0u);
+    CKS(ws->counters.ensure(16 * 8));
+    CKS(ws->failed_tiles.ensure((size_t)4 * std::max<uint32_t>(n_tiles, 1)));
+    CKS(ws->failed_bitmap.ensure((size_t)4 * (n_tiles / 32 + 1)));
+    if (explicit_tiles) {
+        CKS(ws->tiles.ensure(R.tiles.size() * sizeof(uint4)));
+        CK(cudaMemcpyAsync(ws->tiles.p, R.tiles.data(), R.tiles.size() * sizeof(uint4), cudaMemcpyHostToDevice, s));
+    }
+
+    ExpandParams P;
+    memset(&P, 0, sizeof(P));
+    P.A = E->dview; P.tv = R.tv; P.thr = R.thr;
+    P.maxpen = E->host.node_prune_len[0] - E->host.node_prune_low[0] * R.thr;  // search.rs:487 (f32, host compiled without contraction)
+    P.mode = explicit_tiles ? 1 : 0;
+    P.seg_begin = R.seg_begin; P.seg_end = R.seg_end; P.text_end = R.text_end; P.tile = tile; P.n_tiles = n_tiles;
+    P.tiles = ws->tiles.as<uint4>();
+    P.lookahead = E->lookahead;
+    P.queue = ws->queue.as<FacState>(); P.nxt = ws->nxt.as<uint32_t>(); P.hslot = ws->hslot.as<uint32_t>(); P.qcap = ws->qcap;
+    P.gtab_rep = ws->gtab_rep.as<uint32_t>(); P.gtab_head = ws->gtab_head.as<uint32_t>(); P.gtab_min = ws->gtab_min.as<float>();
+    P.gtab_size = ws->gtab_size; P.smem_tab_size = E->smem_tab;
+    P.smem_text_cap = max_count + E->lookahead + 32;
+    P.cands = ws->cands.as<FacCand>(); P.cand_cap = cand_cap;
+    P.counters = ws->counters.as<unsigned long long>();
+    P.failed_tiles = ws->failed_tiles.as<uint32_t>(); P.failed_cap = n_tiles;
+    P.failed_bitmap = ws->failed_bitmap.as<uint32_t>();
+    P.per_window = R.d_per_window;
+    P.use_tma = E->use_tma;
+    const size_t smem = expand_smem_bytes(E, ascii, P.smem_text_cap);
+
+    for (int attempt = 0; attempt < 3; attempt++) {
+        CK(cudaMemsetAsync(ws->counters.p, 0, 16 * 8, s));
+        CK(cudaMemsetAsync(ws->failed_bitmap.p, 0, (size_t)4 * (n_tiles / 32 + 1), s));
+        P.pass = 0; P.cand_cap = cand_cap; P.cands = ws->cands.as<FacCand>();
+        CK(cudaEventRecord(ws->evk0, s));
+        CKS(launch_expand(P, grid, smem, s));
+        CK(cudaEventRecord(ws->evk1, s));
+        stats.launches++;
+        CK(cudaMemcpyAsync(ws->h_counters, ws->counters.p, 8 * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ws->evk0, ws->evk1));
+        stats.expand_ms += ms;
+        uint64_t n_cand = ws->h_counters[1], n_failed = ws->h_counters[3];
+        uint64_t states = ws->h_counters[2];
+        if (n_cand > cand_cap) {  // candidate buffer too small: grow to the exact need and redo the segment
+            cand_cap = (uint32_t)std::min<uint64_t>(n_cand + n_cand / 4 + 1024, 0x7FFFFFF0u);
+            if (n_cand > cand_cap) { set_err("candidate volume exceeds the 31-bit candidate index space; search a smaller haystack slice"); return FAC_UNSUPPORTED; }
+            CKS(ws->cands.ensure((size_t)cand_cap * sizeof(FacCand)));
+            continue;
+        }
+        if (n_failed) {
+            // retry the windows of failed tiles one window per tile on a few CTAs with a large queue
+            std::vector<uint32_t> failed(n_failed);
+            CK(cudaMemcpy(failed.data(), ws->failed_tiles.p, n_failed * 4, cudaMemcpyDeviceToHost));
+            std::vector<uint4> rt;
+            for (uint32_t t : failed) {
+                uint32_t start, count, tend, tag;
+                if (explicit_tiles) { start = R.tiles[t].x; count = R.tiles[t].y; tend = R.tiles[t].z; tag = R.tiles[t].w; }
+                else { start = R.seg_begin + t * tile; count = std::min(tile, R.seg_end - start); tend = R.text_end; tag = 0; }
+                for (uint32_t w = 0; w < count; w++) rt.push_back(make_uint4(start + w, 1, tend, tag));
+            }
+            const uint32_t big_q = 1u << 21;
+            const uint32_t rgrid = (uint32_t)std::min<size_t>(16, rt.size());
+            // the retry uses its own scratch sizing; rebuild the regular scratch afterwards
+            const uint32_t keep_grid = ws->grid, keep_q = ws->qcap;
+            CKS(ensure_scratch(E, ws, rgrid, big_q));
+            DBuf rtiles;
+            CKS(rtiles.ensure(rt.size() * sizeof(uint4)));
+            CK(cudaMemcpyAsync(rtiles.p, rt.data(), rt.size() * sizeof(uint4), cudaMemcpyHostToDevice, s));
+            ExpandParams Q = P;
+            Q.mode = 1; Q.tiles = rtiles.as<uint4>(); Q.n_tiles = (uint32_t)rt.size(); Q.pass = 1;
+            Q.queue = ws->queue.as<FacState>(); Q.nxt = ws->nxt.as<uint32_t>(); Q.hslot = ws->hslot.as<uint32_t>(); Q.qcap = big_q;
+            Q.gtab_rep = ws->gtab_rep.as<uint32_t>(); Q.gtab_head = ws->gtab_head.as<uint32_t>(); Q.gtab_min = ws->gtab_min.as<float>();
+            Q.gtab_size = ws->gtab_size;
+            Q.failed_bitmap = nullptr; Q.failed_cap = 0;
+            // keep counters[1] (candidates) running; reset tile / failed counters
+            CK(cudaMemsetAsync(ws->counters.p, 0, 8, s));
+            CK(cudaMemsetAsync((uint8_t *)ws->counters.p + 24, 0, 8, s));
+            CK(cudaEventRecord(ws->evk0, s));
+            CKS(launch_expand(Q, rgrid, smem, s));
+            CK(cudaEventRecord(ws->evk1, s));
+            stats.launches++;
+            CK(cudaMemcpyAsync(ws->h_counters, ws->counters.p, 8 * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            CK(cudaEventElapsedTime(&ms, ws->evk0, ws->evk1));
+            stats.expand_ms += ms;
+            rtiles.release();
+            CKS(ensure_scratch(E, ws, keep_grid, keep_q));
+            if (ws->h_counters[3]) {
+                set_err("a start window expands more than " + std::to_string(big_q) + " states; lower the edit limits / raise the threshold or use a beam");
+                return FAC_UNSUPPORTED;
+            }
+            if (ws->h_counters[1] > cand_cap) {
+                cand_cap = (uint32_t)std::min<uint64_t>(ws->h_counters[1] * 2, 0x7FFFFFF0u);
+                CKS(ws->cands.ensure((size_t)cand_cap * sizeof(FacCand)));
+                continue;
+            }
+            n_cand = ws->h_counters[1];
+            states = ws->h_counters[2];
+        }
+        stats.states += states;
+        if (states_per_window_out && n_windows_total) *states_per_window_out = (double)states / (double)n_windows_total;
+        if (n_cand == 0) return FAC_OK;
+
+        // ---- best-per-span reduction ----
+        const uint32_t tab = next_pow2(n_cand * 2 + 16);
+        CKS(ws->best_rep.ensure((size_t)tab * 4));
+        CKS(ws->best_val.ensure((size_t)tab * 8));
+        CKS(ws->cslot.ensure((size_t)n_cand * 4));
+        CK(cudaMemsetAsync(ws->best_rep.p, 0xFF, (size_t)tab * 4, s));
+        CK(cudaMemsetAsync(ws->best_val.p, 0, (size_t)tab * 8, s));
+        CKS(grow_keep(ws->m_a, (size_t)*n_matches * sizeof(WMatch), (size_t)(*n_matches + n_cand) * sizeof(WMatch), s));
+        BestParams B;
+        memset(&B, 0, sizeof(B));
+        B.cands = ws->cands.as<FacCand>(); B.n_cands = (uint32_t)n_cand;
+        B.tab_rep = ws->best_rep.as<uint32_t>(); B.tab_val = ws->best_val.as<unsigned long long>(); B.tab_size = tab;
+        B.cslot = ws->cslot.as<uint32_t>();
+        B.failed_bitmap = n_failed ? ws->failed_bitmap.as<uint32_t>() : nullptr;
+        B.tv = R.tv; B.windows = R.d_windows;
+        B.out = ws->m_a.as<WMatch>() + *n_matches;
+        B.out_cap = (uint32_t)n_cand;
+        CK(cudaMemsetAsync((uint8_t *)ws->counters.p + 32, 0, 8, s));
+        B.out_count = ws->counters.as<unsigned long long>() + 4;
+        k_best_insert<<<cdiv(n_cand, 256), 256, 0, s>>>(B);
+        k_best_select<<<cdiv(n_cand, 256), 256, 0, s>>>(B);
+        CK(cudaGetLastError());
+        stats.launches += 2;
+        CK(cudaMemcpyAsync(ws->h_counters, ws->counters.p, 8 * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        *n_matches += ws->h_counters[4];
+        return FAC_OK;
+    }
+    set_err("candidate buffer kept overflowing");
+    return FAC_UNSUPPORTED;
+}
+
+template <class Cmp, class T>
+fac_status merge_sort(Workspace *ws, T *d, uint32_t n, Cmp cmp) {
+    size_t tb = 0;
+    CK(cub::DeviceMergeSort::SortKeys((void *)nullptr, tb, d, (int)n, cmp, ws->stream));
+    CKS(ws->cubtmp.ensure(tb));
+    CK(cub::DeviceMergeSort::SortKeys(ws->cubtmp.p, tb, d, (int)n, cmp, ws->stream));
+    return FAC_OK;
+}
+
+// FuzzyMatches::apply on the device.  In: ws->m_a[0..n) (any order).  Out: ws->m_a[0..*n_out) in final order.
+fac_status apply_device(const fac_engine *E, Workspace *ws, uint32_t n, int order, int overlap, uint32_t n_windows, uint32_t *n_out,
+                        SearchStats &stats) {
+    cudaStream_t s = ws->stream;
+    *n_out = n;
+    if (n == 0) return FAC_OK;
+    WMatch *R = ws->m_a.as<WMatch>();
+    RankLess rl{order, E->d_pat_bytes};
+    CKS(merge_sort(ws, R, n, rl));
+    stats.launches += 2;
+    if (overlap == FAC_OVERLAP_KEEP) return FAC_OK;
+    // position order
+    CKS(ws->idx_a.ensure((size_t)n * 4));
+    CKS(ws->winend.ensure((size_t)n * sizeof(WinEnd)));
+    CKS(ws->st_a.ensure(n)); CKS(ws->st_b.ensure(n)); CKS(ws->flags8.ensure(n));
+    CKS(ws->sel.ensure((size_t)n * 4)); CKS(ws->nsel.ensure(16)); CKS(ws->m_b.ensure((size_t)n * sizeof(WMatch)));
+    uint32_t *Pp = ws->idx_a.as<uint32_t>();
+    k_iota<<<cdiv(n, 256), 256, 0, s>>>(Pp, n);
+    CKS(merge_sort(ws, Pp, n, PosLess{R}));
+    k_gather_winend<<<cdiv(n, 256), 256, 0, s>>>(R, Pp, ws->winend.as<WinEnd>(), n);
+    {
+        size_t tb = 0;
+        CK(cub::DeviceScan::InclusiveScan((void *)nullptr, tb, ws->winend.as<WinEnd>(), ws->winend.as<WinEnd>(), WinEndMax(), (int)n, s));
+        CKS(ws->cubtmp.ensure(tb));
+        CK(cub::DeviceScan::InclusiveScan(ws->cubtmp.p, tb, ws->winend.as<WinEnd>(), ws->winend.as<WinEnd>(), WinEndMax(), (int)n, s));
+    }
+    stats.launches += 5;
+    uint8_t *st_final = nullptr;
+    if (overlap == FAC_OVERLAP_NON_OVERLAPPING) {
+        CK(cudaMemsetAsync(ws->st_a.p, 0, n, s));
+        uint8_t *a = ws->st_a.as<uint8_t>(), *b = ws->st_b.as<uint8_t>();
+        CKS(ws->misc.ensure(64));
+        for (uint32_t round = 0;; round++) {
+            CK(cudaMemsetAsync(ws->misc.p, 0, 4, s));
+            // a few rounds per host check
+            for (int k = 0; k < 4; k++) {
+                k_overlap_round<<<cdiv(n, 256), 256, 0, s>>>(R, Pp, ws->winend.as<WinEnd>(), a, b, n, ws->misc.as<uint32_t>());
+                std::swap(a, b);
+                stats.launches++;
+                if (k < 3) CK(cudaMemsetAsync(ws->misc.p, 0, 4, s));
+            }
+            CK(cudaMemcpyAsync(ws->h_flags, ws->misc.p, 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            if (ws->h_flags[0] == 0) break;
+            if (round > n) { set_err("overlap resolution did not converge"); return FAC_CUDA_ERROR; }
+        }
+        st_final = a;
+    } else {
+        CKS(ws->idx_b.ensure((size_t)n * 4));
+        CKS(ws->misc.ensure((size_t)(n_windows + 2) * 4));
+        const uint32_t uid_words = E->n_uid / 32 + 1;
+        const uint32_t ugrid = std::min<uint32_t>(n_windows, 1024);
+        const bool fresh = ws->used.cap < (size_t)1024 * uid_words * 4;
+        CKS(ws->used.ensure((size_t)1024 * uid_words * 4));
+        if (fresh) CK(cudaMemsetAsync(ws->used.p, 0, ws->used.cap, s));
+        k_posof<<<cdiv(n, 256), 256, 0, s>>>(Pp, ws->idx_b.as<uint32_t>(), n);
+        k_win_rank_off<<<cdiv(n + 1, 256), 256, 0, s>>>(R, n, ws->misc.as<uint32_t>(), n_windows);
+        CK(cudaMemsetAsync(ws->st_a.p, 0, n, s));
+        k_unique_select<<<ugrid, 32, 0, s>>>(R, Pp, ws->idx_b.as<uint32_t>(), ws->winend.as<WinEnd>(), ws->misc.as<uint32_t>(), n_windows, n,
+                                             E->d_pat_uid_dense, uid_words, ws->used.as<uint32_t>(), ws->st_a.as<uint8_t>());
+        stats.launches += 3;
+        st_final = ws->st_a.as<uint8_t>();
+    }
+    k_accept_flags<<<cdiv(n, 256), 256, 0, s>>>(st_final, ws->flags8.as<uint8_t>(), n);
+    {
+        size_t tb = 0;
+        CK(cub::DeviceSelect::Flagged((void *)nullptr, tb, Pp, ws->flags8.as<uint8_t>(), ws->sel.as<uint32_t>(), ws->nsel.as<int>(), (int)n, s));
+        CKS(ws->cubtmp.ensure(tb));
+        CK(cub::DeviceSelect::Flagged(ws->cubtmp.p, tb, Pp, ws->flags8.as<uint8_t>(), ws->sel.as<uint32_t>(), ws->nsel.as<int>(), (int)n, s));
+    }
+    CK(cudaMemcpyAsync(ws->h_flags, ws->nsel.p, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint32_t kept = ws->h_flags[0];
+    if (kept) {
+        k_gather_matches<<<cdiv(kept, 256), 256, 0, s>>>(R, ws->sel.as<uint32_t>(), kept, ws->m_b.as<WMatch>());
+        CK(cudaMemcpyAsync(R, ws->m_b.p, (size_t)kept * sizeof(WMatch), cudaMemcpyDeviceToDevice, s));
+    }
+    stats.launches += 4;
+    CK(cudaGetLastError());
+    *n_out = kept;
+    return FAC_OK;
+}
+
+// WMatch list -> fac_match on the host (optionally dropping matches a stream window does not own).
+fac_status finalize_and_fetch(Workspace *ws, uint32_t n, const FacWindow *d_windows, bool filter_commit, std::vector<fac_match> &out,
+                              SearchStats &stats) {
+    cudaStream_t s = ws->stream;
+    if (n == 0) return FAC_OK;
+    CKS(ws->outm.ensure((size_t)n * sizeof(fac_match)));
+    CKS(ws->keep8.ensure(n));
+    k_finalize<<<cdiv(n, 256), 256, 0, s>>>(ws->m_a.as<WMatch>(), n, d_windows, ws->outm.as<fac_match>(), ws->keep8.as<uint8_t>());
+    stats.launches++;
+    fac_match *src = ws->outm.as<fac_match>();
+    uint32_t cnt = n;
+    if (filter_commit) {
+        CKS(ws->m_b.ensure((size_t)n * sizeof(fac_match)));
+        CKS(ws->nsel.ensure(16));
+        size_t tb = 0;
+        CK(cub::DeviceSelect::Flagged((void *)nullptr, tb, src, ws->keep8.as<uint8_t>(), ws->m_b.as<fac_match>(), ws->nsel.as<int>(), (int)n, s));
+        CKS(ws->cubtmp.ensure(tb));
+        CK(cub::DeviceSelect::Flagged(ws->cubtmp.p, tb, src, ws->keep8.as<uint8_t>(), ws->m_b.as<fac_match>(), ws->nsel.as<int>(), (int)n, s));
+        CK(cudaMemcpyAsync(ws->h_flags, ws->nsel.p, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        cnt = ws->h_flags[0];
+        src = ws->m_b.as<fac_match>();
+        stats.launches += 2;
+    }
+    const size_t old = out.size();
+    out.resize(old + cnt);
+    if (cnt) CK(cudaMemcpyAsync(out.data() + old, src, (size_t)cnt * sizeof(fac_match), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return FAC_OK;
+}
+
+// Segment a non-ASCII text range on the device (K1).  Fills ws->first/gid/off and *n_graphemes.
+fac_status segment_device(const fac_engine *E, Workspace *ws, const uint8_t *d_text, uint64_t len, bool want_pf, uint64_t *n_graphemes,
+                          SearchStats &stats) {
+    cudaStream_t s = ws->stream;
+    if (len >= 0xFFFFFFF0ull) { set_err("non-ASCII haystacks of 4 GiB or more are not supported by the 32-bit offset streams yet"); return FAC_UNSUPPORTED; }
+    CKS(ws->misc.ensure(64));
+    CK(cudaMemsetAsync(ws->misc.p, 0, 8, s));
+    k_validate_utf8<<<cdiv(len, 256), 256, 0, s>>>(d_text, len, ws->misc.as<uint32_t>());
+    CKS(ws->mark.ensure(len + 16));
+    CKS(ws->gidx.ensure((len + 16) * 4));
+    k_seg_mark<<<cdiv(len, 256), 256, 0, s>>>(d_text, 0, len, E->dU, ws->mark.as<uint8_t>());
+    {
+        size_t tb = 0;
+        cub::TransformInputIterator<uint32_t, U8ToU32, const uint8_t *> it(ws->mark.as<uint8_t>(), U8ToU32());
+        CK(cub::DeviceScan::ExclusiveSum((void *)nullptr, tb, it, ws->gidx.as<uint32_t>(), (int64_t)len + 1, s));
+        CKS(ws->cubtmp.ensure(tb));
+        CK(cudaMemsetAsync(ws->mark.as<uint8_t>() + len, 0, 1, s));
+        CK(cub::DeviceScan::ExclusiveSum(ws->cubtmp.p, tb, it, ws->gidx.as<uint32_t>(), (int64_t)len + 1, s));
+    }
+    CK(cudaMemcpyAsync(ws->h_flags, ws->misc.p, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ws->h_flags + 1, ws->gidx.as<uint32_t>() + len, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    stats.launches += 4;
+    if (ws->h_flags[0]) { set_err("haystack is not valid UTF-8"); return FAC_INVALID_UTF8; }
+    const uint64_t n = ws->h_flags[1];
+    *n_graphemes = n;
+    CKS(ws->first.ensure((n + 4) * 4));
+    CKS(ws->off.ensure((n + 4) * 4));
+    if (E->host.has_mappings) CKS(ws->gid.ensure((n + 4) * 4));
+    if (want_pf) CKS(ws->pfsym.ensure(n + 16));
+    SegEmitParams P;
+    memset(&P, 0, sizeof(P));
+    P.s = d_text; P.lo = 0; P.hi = len; P.mark = ws->mark.as<uint8_t>(); P.gidx = ws->gidx.as<uint32_t>(); P.g_base = 0; P.U = E->dU;
+    if (E->host.has_mappings) { P.symbols = E->d_symbols; P.sym_mask = E->sym_mask; P.pool = E->d_pool; }
+    P.fold = E->host.ci; P.first = ws->first.as<uint32_t>(); P.gid = ws->gid.as<uint32_t>(); P.off32 = ws->off.as<uint32_t>();
+    k_seg_emit<<<cdiv(len, 256), 256, 0, s>>>(P);
+    const uint32_t len32 = (uint32_t)len;
+    CK(cudaMemcpyAsync(ws->off.as<uint32_t>() + n, &len32, 4, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));  // len32 is a stack variable
+    stats.launches++;
+    CK(cudaGetLastError());
+    return FAC_OK;
+}
+
+// The whole-haystack search on device-resident text: classification, (K1), K3 over segments of
+// start windows, reduction, apply.  Restricts start windows to the byte range [own_begin, own_end).
+fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_text, uint64_t len, float thr, int order, int overlap,
+                           uint64_t own_begin, uint64_t own_end, uint64_t base, uint64_t commit, bool apply, std::vector<fac_match> &out, SearchStats &stats) {
+    cudaStream_t s = ws->stream;
+    if (len == 0) return FAC_OK;
+    CKS(ws->misc.ensure(64));
+    CK(cudaMemsetAsync(ws->misc.p, 0, 4, s));
+    k_scan_bytes<<<(unsigned)std::min<uint64_t>(cdiv(len, 256 * 64), 148 * 8), 256, 0, s>>>(d_text, len, ws->misc.as<uint32_t>());
+    CK(cudaMemcpyAsync(ws->h_flags, ws->misc.p, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    stats.launches++;
+    const bool ascii = ws->h_flags[0] == 0;
+    TextView tv;
+    memset(&tv, 0, sizeof(tv));
+    tv.n_bytes = len; tv.ascii = ascii;
+    uint64_t n = len;
+    if (ascii) tv.bytes = d_text;
+    else {
+        CKS(segment_device(E, ws, d_text, len, false, &n, stats));
+        tv.first = ws->first.as<uint32_t>(); tv.gid = ws->gid.as<uint32_t>(); tv.off32 = ws->off.as<uint32_t>();
+    }
+    if (n > 0xFFFFFFFFull) {  // SearchError::HaystackTooLarge, search.rs:198-202
+        g_last_graphemes = n;
+        set_err("haystack has " + std::to_string(n) + " grapheme clusters, exceeding the u32 position space");
+        return FAC_HAYSTACK_TOO_LARGE;
+    }
+    tv.n = (uint32_t)n;
+    if (n == 0) return FAC_OK;
+    if (E->host.beam_width != 0 || E->host.has_auto_beam) {
+        set_err("beam / auto_beam engines are not supported by this build of the device path yet");
+        return FAC_UNSUPPORTED;
+    }
+    // owned grapheme range
+    uint32_t g_begin = 0, g_end = (uint32_t)n;
+    if (own_begin > 0 || own_end < len) {
+        if (ascii) { g_begin = (uint32_t)std::min<uint64_t>(own_begin, n); g_end = (uint32_t)std::min<uint64_t>(own_end, n); }
+        else {
+            // first grapheme with offset >= own_begin / own_end: read the offsets back around the cut (small)
+            std::vector<uint32_t> off(n + 1);
+            CK(cudaMemcpy(off.data(), ws->off.p, (n + 1) * 4, cudaMemcpyDeviceToHost));
+            g_begin = (uint32_t)(std::lower_bound(off.begin(), off.begin() + n, (uint32_t)std::min<uint64_t>(own_begin, len)) - off.begin());
+            g_end = (uint32_t)(std::lower_bound(off.begin(), off.begin() + n, (uint32_t)std::min<uint64_t>(own_end, len)) - off.begin());
+        }
+    }
+    FacWindow w;
+    memset(&w, 0, sizeof(w));
+    w.byte_begin = 0; w.byte_end = len; w.base = base; w.commit = commit; w.g_begin = 0; w.g_end = (uint32_t)n;
+    CKS(ws->windows.ensure(sizeof(FacWindow)));
+    CK(cudaMemcpyAsync(ws->windows.p, &w, sizeof(w), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+
+    uint64_t n_matches = 0;
+    const uint64_t SEG = (uint64_t)env_int("FAC_SEGMENT_WINDOWS", 1 << 25);
+    uint32_t tile = E->default_tile;
+    bool calibrated = tile != 0;
+    if (!calibrated) tile = 4;
+    uint64_t pos = g_begin;
+    while (pos < g_end) {
+        uint64_t seg = std::min<uint64_t>(SEG, g_end - pos);
+        if (!calibrated) seg = std::min<uint64_t>(seg, 1 << 16);  // small calibration segment decides the tile size
+        ExpandRun R;
+        R.tv = tv; R.seg_begin = (uint32_t)pos; R.seg_end = (uint32_t)(pos + seg); R.text_end = (uint32_t)n;
+        R.d_windows = ws->windows.as<FacWindow>(); R.thr = thr;
+        double spw = 0;
+        // keep what is already in m_a: grow by copy before the reduction writes
+        CKS(grow_keep(ws->m_a, n_matches * sizeof(WMatch), (n_matches + (1u << 20)) * sizeof(WMatch), s));
+        const uint64_t before = n_matches;
+        (void)before;
+        CKS(expand_and_reduce(E, ws, R, tile, &n_matches, stats, &spw));
+        if (!calibrated) {
+            calibrated = true;
+            // aim at ~1/6 of the queue per tile on average (levels are bursty); power of two, 1..256
+            const double target = (double)E->qcap / 6.0;
+            uint32_t t = 1;
+            while (t < 256 && (double)(t * 2) * std::max(spw, 1.0) <= target) t <<= 1;
+            tile = t;
+        }
+        pos += seg;
+    }
+    uint32_t n_final = (uint32_t)n_matches;
+    if (apply) CKS(apply_device(E, ws, (uint32_t)n_matches, order, overlap, 1, &n_final, stats));
+    CKS(finalize_and_fetch(ws, n_final, ws->windows.as<FacWindow>(), commit != ~0ull, out, stats));
+    return FAC_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char *fac_last_error_string(void) { return g_err.c_str(); }
+int fac_abi_version(void) { return FAC_ABI_VERSION; }
+uint64_t fac_last_haystack_graphemes(void) { return g_last_graphemes; }
+
+fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pattern *patterns, size_t n_patterns, fac_engine **out) {
+    if (!out) { set_err("null out pointer"); return FAC_INVALID_ARGUMENT; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        set_err(std::string("no usable CUDA device (") + cudaGetErrorString(ce) + "); this library has no CPU fallback");
+        return FAC_CUDA_ERROR;
+    }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= ndev) { set_err("device index out of range"); return FAC_INVALID_ARGUMENT; }
+    CK(cudaSetDevice(device));
+    fac_engine *E = new fac_engine();
+    E->device = device;
+    std::string err;
+    fac_status st = fac::build_automaton(cfg, patterns, n_patterns, E->host, err);
+    if (st != FAC_OK) { set_err(err); delete E; return st; }
+    auto fail = [&](fac_status s) { fac_engine_free(E); return s; };
+    const fac::HostAutomaton &H = E->host;
+    AutomatonView &V = E->dview;
+    V = H.host_view();
+#define UP(field, vec) do { fac_status s_ = upload(E, vec, &V.field); if (s_ != FAC_OK) return fail(s_); } while (0)
+    UP(node_edge_off, H.node_edge_off); UP(node_prune_len, H.node_prune_len); UP(node_prune_low, H.node_prune_low);
+    UP(node_out_off, H.node_out_off); UP(node_bitmap, H.node_bitmap); UP(node_lim, H.node_lim); UP(node_map_off, H.node_map_off);
+    UP(edge_char, H.edge_char); UP(edge_next, H.edge_next); UP(trans, H.trans); UP(out_pat, H.out_pat);
+    UP(pat_glen, H.pat_glen); UP(pat_weight, H.pat_weight); UP(pat_lim, H.pat_lim); UP(lim, H.lim);
+    UP(sim_ascii, H.sim_ascii); UP(sim_keys, H.sim_keys); UP(sim_vals, H.sim_vals);
+    UP(map_hay_off, H.map_hay_off); UP(map_hay_gid, H.map_hay_gid); UP(map_next, H.map_next); UP(map_pen, H.map_pen);
+    UP(ascii_gid, H.ascii_gid);
+#undef UP
+    {
+        const uint32_t *pb = nullptr;
+        if ((st = upload(E, H.pat_bytes, &pb)) != FAC_OK) return fail(st);
+        E->d_pat_bytes = (uint32_t *)pb;
+        // dense pattern identities for non_overlapping_unique
+        std::vector<int64_t> keys(H.pat_uid);
+        std::sort(keys.begin(), keys.end());
+        keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+        std::vector<uint32_t> dense(H.pat_uid.size());
+        for (size_t i = 0; i < dense.size(); i++) dense[i] = (uint32_t)(std::lower_bound(keys.begin(), keys.end(), H.pat_uid[i]) - keys.begin());
+        E->n_uid = (uint32_t)keys.size();
+        if ((st = upload(E, dense, &pb)) != FAC_OK) return fail(st);
+        E->d_pat_uid_dense = (uint32_t *)pb;
+        const uint16_t *s1; const uint8_t *s2; const uint32_t *lk, *lv;
+        if ((st = upload_raw(E, FAC_GCB_STAGE1, 0x1100, &s1)) != FAC_OK) return fail(st);
+        if ((st = upload_raw(E, FAC_GCB_STAGE2, (size_t)FAC_GCB_NBLOCKS * 256, &s2)) != FAC_OK) return fail(st);
+        if ((st = upload_raw(E, FAC_LOWER_KEYS, (size_t)FAC_LOWER_N, &lk)) != FAC_OK) return fail(st);
+        if ((st = upload_raw(E, FAC_LOWER_VALS, (size_t)FAC_LOWER_N, &lv)) != FAC_OK) return fail(st);
+        E->dU = UnicodeTables{s1, s2, lk, lv, FAC_LOWER_N};
+        const fac::HostSymbol *sy; const uint8_t *pool;
+        if ((st = upload(E, H.symbols, &sy)) != FAC_OK) return fail(st);
+        if ((st = upload(E, H.symbol_pool, &pool)) != FAC_OK) return fail(st);
+        E->d_symbols = (FacSymbol *)sy; E->sym_mask = (uint32_t)H.symbols.size() - 1; E->d_pool = (uint8_t *)pool;
+    }
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    E->sm_count = prop.multiProcessorCount;
+    E->lookahead = (uint32_t)H.max_match_graphemes + H.max_map_hay + 3;
+    E->default_tile = (uint32_t)env_int("FAC_TILE", 0);
+    E->qcap = (uint32_t)env_int("FAC_QCAP", 1 << 17);
+    E->smem_tab = (uint32_t)env_int("FAC_SMEM_TAB", 4096);
+    E->ctas_per_sm = env_int("FAC_CTAS_PER_SM", 4);
+    E->use_tma = env_int("FAC_USE_TMA", 1);
+    *out = E;
+    return FAC_OK;
+}
+
+fac_status fac_engine_create(const fac_config *cfg, const fac_pattern *patterns, size_t n_patterns, fac_engine **out) {
+    return fac_engine_create_on(-1, cfg, patterns, n_patterns, out);
+}
+
+void fac_engine_free(fac_engine *E) {
+    if (!E) return;
+    cudaSetDevice(E->device);
+    for (Workspace *w : E->pool) { w->destroy(); delete w; }
+    for (void *p : E->dallocs) cudaFree(p);
+    delete E;
+}
+
+size_t fac_engine_max_match_graphemes(const fac_engine *E) { return E ? E->host.max_match_graphemes : 0; }
+int fac_engine_prefilter_active(const fac_engine *E) { return E && E->host.bitap.active ? 1 : 0; }
+size_t fac_engine_num_nodes(const fac_engine *E) { return E ? E->host.n_nodes() : 0; }
+size_t fac_engine_num_patterns(const fac_engine *E) { return E ? E->host.patterns.size() : 0; }
+int fac_engine_device(const fac_engine *E) { return E ? E->device : -1; }
+
+static fac_status search_common(const fac_engine *E, const uint8_t *hay, size_t len, bool on_device, float thr, int order, int overlap,
+                                int use_prefilter, size_t own_begin, size_t own_end, uint64_t base, bool apply, fac_matches **out) {
+    if (!E || !out || (len && !hay)) { set_err("null argument"); return FAC_INVALID_ARGUMENT; }
+    *out = nullptr;
+    CK(cudaSetDevice(E->device));
+    fac_status st;
+    Workspace *ws = acquire_ws(E, st);
+    if (!ws) return st;
+    fac_matches *M = new fac_matches();
+    auto body = [&]() -> fac_status {
+        CK(cudaEventRecord(ws->ev_begin, ws->stream));
+        const uint8_t *d_text = hay;
+        if (!on_device && len) {
+            CKS(ws->hay.ensure(len + 64));
+            CK(cudaMemcpyAsync(ws->hay.p, hay, len, cudaMemcpyHostToDevice, ws->stream));
+            CK(cudaMemsetAsync((uint8_t *)ws->hay.p + len, 0, 64, ws->stream));
+            d_text = ws->hay.as<uint8_t>();
+        }
+        (void)use_prefilter;  // the pre-filter is result-neutral (src/prefilter.rs:1-21); wired in a later step
+        CKS(search_resident(E, ws, d_text, len, thr, order, overlap, own_begin, own_end, base, ~0ull, apply, M->v, M->stats));
+        CK(cudaEventRecord(ws->ev_end, ws->stream));
+        CK(cudaEventSynchronize(ws->ev_end));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ws->ev_begin, ws->ev_end));
+        M->stats.device_ms = ms;
+        return FAC_OK;
+    };
+    st = body();
+    release_ws(E, ws);
+    if (st != FAC_OK) { delete M; return st; }
+    *out = M;
+    return FAC_OK;
+}
+
+fac_status fac_search(const fac_engine *E, const uint8_t *haystack, size_t len, float threshold, fac_order order, fac_overlap overlap,
+                      int use_prefilter, fac_matches **out) {
+    return search_common(E, haystack, len, false, threshold, order, overlap, use_prefilter, 0, len, 0, true, out);
+}
+fac_status fac_search_device(const fac_engine *E, const uint8_t *d_haystack, size_t len, float threshold, fac_order order,
+                             fac_overlap overlap, int use_prefilter, fac_matches **out) {
+    return search_common(E, d_haystack, len, true, threshold, order, overlap, use_prefilter, 0, len, 0, true, out);
+}
+fac_status fac_search_shard(const fac_engine *E, const uint8_t *haystack, size_t len, size_t own_begin, size_t own_end, uint64_t base,
+                            float threshold, int on_device, fac_matches **out) {
+    return search_common(E, haystack, len, on_device != 0, threshold, FAC_ORDER_UNSORTED, FAC_OVERLAP_KEEP, 0, own_begin, own_end, base, true, out);
+}
+
+fac_status fac_matches_apply(const fac_engine *E, const fac_match *in, size_t n, fac_order order, fac_overlap overlap, fac_matches **out) {
+    if (!E || !out || (n && !in)) { set_err("null argument"); return FAC_INVALID_ARGUMENT; }
+    *out = nullptr;
+    CK(cudaSetDevice(E->device));
+    fac_status st;
+    Workspace *ws = acquire_ws(E, st);
+    if (!ws) return st;
+    fac_matches *M = new fac_matches();
+    auto body = [&]() -> fac_status {
+        if (n == 0) return FAC_OK;
+        std::vector<WMatch> w(n);
+        for (size_t i = 0; i < n; i++) {
+            w[i].start = in[i].start; w[i].end = in[i].end; w[i].pat = in[i].pattern_index; w[i].sim = in[i].similarity; w[i].win = 0;
+            w[i].cnt = in[i].insertions | (in[i].deletions << 8) | (in[i].substitutions << 16) | ((uint32_t)in[i].swaps << 24);
+            if (in[i].pattern_index >= E->host.patterns.size()) { set_err("pattern index out of range"); return FAC_INVALID_ARGUMENT; }
+        }
+        CKS(ws->m_a.ensure(n * sizeof(WMatch)));
+        CK(cudaMemcpyAsync(ws->m_a.p, w.data(), n * sizeof(WMatch), cudaMemcpyHostToDevice, ws->stream));
+        FacWindow fw;
+        memset(&fw, 0, sizeof(fw));
+        fw.commit = ~0ull;
+        CKS(ws->windows.ensure(sizeof(FacWindow)));
+        CK(cudaMemcpyAsync(ws->windows.p, &fw, sizeof(fw), cudaMemcpyHostToDevice, ws->stream));
+        CK(cudaStreamSynchronize(ws->stream));
+        uint32_t kept = 0;
+        CKS(apply_device(E, ws, (uint32_t)n, order, overlap, 1, &kept, M->stats));
+        CKS(finalize_and_fetch(ws, kept, ws->windows.as<FacWindow>(), false, M->v, M->stats));
+        return FAC_OK;
+    };
+    st = body();
+    release_ws(E, ws);
+    if (st != FAC_OK) { delete M; return st; }
+    *out = M;
+    return FAC_OK;
+}
+
+const fac_match *fac_matches_data(const fac_matches *m) { return m && !m->v.empty() ? m->v.data() : nullptr; }
+size_t fac_matches_len(const fac_matches *m) { return m ? m->v.size() : 0; }
+uint64_t fac_matches_states_pushed(const fac_matches *m) { return m ? m->stats.states : 0; }
+double fac_matches_device_ms(const fac_matches *m) { return m ? m->stats.device_ms : 0; }
+double fac_matches_expand_ms(const fac_matches *m) { return m ? m->stats.expand_ms : 0; }
+uint32_t fac_matches_kernel_launches(const fac_matches *m) { return m ? m->stats.launches : 0; }
+void fac_matches_free(fac_matches *m) { delete m; }
+
+}  // extern "C"
+
+#include "fac_stream.inc"

@@ -111,6 +111,25 @@ struct FacCand {
     float sim;
     uint32_t cnt;
     uint32_t seq;    // FIFO queue position of the emitting state within its tile
-    uint32_t text_end;  // grapheme index where this window's haystack ends (for end-byte resolution)
-    uint32_t pad;
+    uint32_t tile;   // tile index within the launch (failed tiles are superseded by the retry pass)
+    uint32_t tag;    // window id | pass << 31
+};
+
+// One haystack window of a call: a whole-haystack search has exactly one; the streaming API
+// (StreamWindow, src/stream.rs:67-73) and the pre-filter slices (src/prefilter.rs:346-350) have many.
+struct FacWindow {
+    uint64_t byte_begin, byte_end;  // in the device text buffer
+    uint64_t base;                  // absolute offset of byte_begin in the caller's stream
+    uint64_t commit;                // window-relative: the window owns matches with start < commit
+    uint32_t g_begin, g_end;        // grapheme range in the call's grapheme stream
+    uint32_t pad[2];
+};
+
+// Internal match record (window-relative byte offsets); converted to fac_match on the way out.
+struct WMatch {
+    uint64_t start, end;
+    uint32_t pat;
+    float sim;
+    uint32_t cnt;  // ins | del<<8 | sub<<16 | swap<<24
+    uint32_t win;
 };

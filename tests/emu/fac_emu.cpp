@@ -122,7 +122,7 @@ int emu_search(const fac_config *cfg, const fac_pattern *pats, size_t np, const 
                 for (uint32_t o = A.node_out_off[S.node]; o < A.node_out_off[S.node + 1]; o++) {
                     float sim;
                     if (fac_eval_output(A, thr, A.out_pat[o], S.pen, S.cnt, sim))
-                        cands.push_back(FacCand{start, start + mr, A.out_pat[o], sim, S.cnt, (uint32_t)i, text_end, 0});
+                        cands.push_back(FacCand{start, start + mr, A.out_pat[o], sim, S.cnt, (uint32_t)i, 0, 0});
                 }
                 FacCtx C;
                 fac_make_ctx(A, T, maxpen, start, text_end, S, C);
@@ -153,7 +153,7 @@ int emu_search(const fac_config *cfg, const fac_pattern *pats, size_t np, const 
         const FacCand &c = kv.second;
         fac_match m; memset(&m, 0, sizeof(m));
         m.start = c.sg < n ? fac_byte_offset(tv, c.sg) : 0;
-        m.end = c.eg < c.text_end ? fac_byte_offset(tv, c.eg) : (c.text_end == n ? tv.n_bytes : fac_byte_offset(tv, c.text_end));
+        m.end = fac_byte_offset(tv, c.eg);
         m.pattern_index = c.pat; m.similarity = c.sim;
         m.insertions = c.cnt & 0xFF; m.deletions = (c.cnt >> 8) & 0xFF; m.substitutions = (c.cnt >> 16) & 0xFF; m.swaps = c.cnt >> 24;
         m.edits = (uint8_t)fac_edits_of(c.cnt);

@@ -1,0 +1,140 @@
+"""GPU parity: the CUDA path through the C ABI against the CPU oracle on the same seeded inputs.
+Bit-exact on (start, end, pattern, similarity bits, ins, del, sub, swap, edits) and on the number of
+pushed search states."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+from fac_b200 import (FuzzyAhoCorasickBuilder, FuzzyLimits, Order, Overlap, SearchOptions, workload)
+from fac_b200._abi import fac_match
+from fuzzgen import rand_case
+
+pytestmark = pytest.mark.gpu
+
+ALL_OPTS = [(o, v) for o in (Order.Unsorted, Order.Default, Order.Greedy, Order.CoverageWeighted)
+            for v in (Overlap.Keep, Overlap.NonOverlapping, Overlap.NonOverlappingUnique)]
+
+
+def _fuzz(oracle, gpu, seed, unicode_, trials):
+    r1, r2 = random.Random(seed), random.Random(seed)
+    ropt = random.Random(seed + 7)
+    for t in range(trials):
+        eo, hay, thr, desc = rand_case(r1, oracle, unicode_)
+        eg, _, _, _ = rand_case(r2, gpu, unicode_)
+        order, overlap = ropt.choice(ALL_OPTS)
+        opts = SearchOptions(thr, order, overlap)
+        o = eo.search(hay, opts)
+        g = eg.search(hay, opts)
+        assert o.tuples() == g.tuples(), (t, order, overlap, desc)
+        assert o.stats["states_pushed"] == g.stats["states_pushed"], (t, desc)
+
+
+def test_fuzz_ascii(oracle, gpu):
+    _fuzz(oracle, gpu, 11, False, 400)
+
+
+def test_fuzz_unicode(oracle, gpu):
+    _fuzz(oracle, gpu, 12, True, 400)
+
+
+def _engines(oracle, gpu, cfg):
+    return workload.build_engine(cfg, oracle), workload.build_engine(cfg, gpu)
+
+
+def test_cfg1_slice_parity(oracle, gpu):
+    cfg = workload.cfg1(1 << 19)
+    eo, eg = _engines(oracle, gpu, cfg)
+    text = bytes(cfg["text"])
+    for opts in (SearchOptions.new().threshold(0.8), SearchOptions.new().threshold(0.8).sorted().non_overlapping()):
+        o, g = eo.search(text, opts), eg.search(text, opts)
+        assert len(o) > 100
+        assert o.tuples() == g.tuples()
+        assert o.stats["states_pushed"] == g.stats["states_pushed"]
+
+
+def test_cfg2_slice_parity(oracle, gpu):
+    cfg = workload.cfg2(1 << 15, n_patterns=2000)
+    eo, eg = _engines(oracle, gpu, cfg)
+    text = bytes(cfg["text"])
+    o = eo.search(text, SearchOptions.new().threshold(0.8))
+    g = eg.search(text, SearchOptions.new().threshold(0.8))
+    assert len(o) > 50
+    assert o.tuples() == g.tuples()
+    assert o.stats["states_pushed"] == g.stats["states_pushed"]
+    for order, overlap in ALL_OPTS[1:]:
+        assert eo.search(text, SearchOptions(0.8, order, overlap)).tuples() == \
+            eg.search(text, SearchOptions(0.8, order, overlap)).tuples(), (order, overlap)
+
+
+def test_low_threshold_many_matches(oracle, gpu):
+    cfg = workload.cfg2(1 << 12, n_patterns=500)
+    eo, eg = _engines(oracle, gpu, cfg)
+    text = bytes(cfg["text"])
+    o = eo.search(text, SearchOptions.new().threshold(0.0))
+    g = eg.search(text, SearchOptions.new().threshold(0.0))
+    assert len(o) > 1000
+    assert o.tuples() == g.tuples()
+
+
+def test_shards_with_halo_equal_whole(gpu):
+    cfg = workload.cfg1(1 << 18)
+    eg = workload.build_engine(cfg, gpu)
+    text = bytes(cfg["text"])
+    whole = eg.search(text, SearchOptions.new().threshold(0.8)).tuples()
+    halo = eg.max_match_graphemes() + 1
+    n = len(text)
+    cuts = [0, n // 3 + 5, 2 * n // 3 + 1, n]
+    got = []
+    for a, b in zip(cuts, cuts[1:]):
+        end = min(n, b + halo)
+        arr, _ = gpu.search_shard(eg._h, text[a:end], end - a, 0, b - a, a, 0.8, False)
+        got += [(m.start, m.end, m.pattern_index, C.c_uint32.from_buffer(C.c_float(m.similarity)).value,
+                 m.insertions, m.deletions, m.substitutions, m.swaps, m.edits) for m in arr]
+    assert sorted(got) == sorted(whole)
+
+
+def test_matches_apply_equals_oracle(oracle, gpu):
+    cfg = workload.cfg1(1 << 17)
+    eo, eg = _engines(oracle, gpu, cfg)
+    text = bytes(cfg["text"])
+    raw, _ = gpu.search(eg._h, text, 0.8, 0, 0, False)
+    for order, overlap in ALL_OPTS:
+        a, _ = gpu.apply(eg._h, raw, len(raw), order, overlap)
+        b, _ = oracle.apply(eo._h, raw, len(raw), order, overlap)
+        assert bytes(a) == bytes(b), (order, overlap)
+
+
+def test_device_resident_haystack(gpu):
+    import torch
+    cfg = workload.cfg1(1 << 18)
+    eg = workload.build_engine(cfg, gpu)
+    text = bytes(cfg["text"])
+    host = eg.search(text, SearchOptions.new().threshold(0.8).sorted()).tuples()
+    t = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+    arr, stats = gpu.search_device(eg._h, t.data_ptr(), t.numel(), 0.8, 1, 0, False)
+    assert [(m.start, m.end, m.pattern_index) for m in arr] == [(x[0], x[1], x[2]) for x in host]
+    assert stats["kernel_launches"] > 0
+
+
+def test_invalid_utf8_and_empty(gpu):
+    from fac_b200 import SearchError
+    eg = FuzzyAhoCorasickBuilder.new(gpu).fuzzy(FuzzyLimits.new().edits(1)).build(["abc"])
+    assert len(eg.search("", SearchOptions.new())) == 0
+    with pytest.raises(SearchError) as ei:
+        eg.search(b"ab\xffc\xe4", SearchOptions.new())
+    assert ei.value.status == 2
+
+
+def test_tile_failure_retry_path(oracle, gpu, monkeypatch):
+    # a tiny queue forces tiles to overflow and exercises the one-window-per-tile retry
+    monkeypatch.setenv("FAC_QCAP", "2048")
+    monkeypatch.setenv("FAC_TILE", "64")
+    cfg = workload.cfg2(1 << 12, n_patterns=1000)
+    eo, eg = _engines(oracle, gpu, cfg)
+    text = bytes(cfg["text"])
+    o = eo.search(text, SearchOptions.new().threshold(0.8))
+    g = eg.search(text, SearchOptions.new().threshold(0.8))
+    assert o.tuples() == g.tuples()
+    assert o.stats["states_pushed"] == g.stats["states_pushed"]
