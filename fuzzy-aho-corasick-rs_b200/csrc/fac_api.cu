@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -19,6 +20,7 @@
 #include "fac_apply.cuh"
 #include "fac_builder.h"
 #include "fac_kernels.cuh"
+#include "fac_beam.cuh"
 #include "fac_segment.cuh"
 
 #define FAC_TABLE_QUAL static const
@@ -236,6 +238,11 @@ struct ExpandRun {
     const FacWindow *d_windows = nullptr;
     float thr = 0.f;
     uint32_t *d_per_window = nullptr;
+    bool beam = false;            // use the one-window-per-CTA beamed kernel (bw == 0: exact)
+    uint32_t bw = 0;
+    // called after the expansion has completed (stream synchronised) and before the reduction;
+    // returns the exclusive upper bound of the start windows whose candidates count (auto_beam), default: all
+    std::function<uint32_t(uint64_t states)> limit_after_expand;
 };
 
 // Run K3 (+ retry of failed tiles) and the best-per-span reduction; appends WMatch records to
@@ -289,7 +296,10 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
         CK(cudaMemsetAsync(ws->failed_bitmap.p, 0, (size_t)4 * (n_tiles / 32 + 1), s));
         P.pass = 0; P.cand_cap = cand_cap; P.cands = ws->cands.as<FacCand>();
         CK(cudaEventRecord(ws->evk0, s));
-        CKS(launch_expand(P, grid, smem, s));
+        if (R.beam) {
+            k_expand_beam<<<grid, FAC_BLOCK, 0, s>>>(P, R.bw);
+            CK(cudaGetLastError());
+        } else CKS(launch_expand(P, grid, smem, s));
         CK(cudaEventRecord(ws->evk1, s));
         stats.launches++;
         CK(cudaMemcpyAsync(ws->h_counters, ws->counters.p, 8 * 8, cudaMemcpyDeviceToHost, s));
@@ -299,6 +309,10 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
         stats.expand_ms += ms;
         uint64_t n_cand = ws->h_counters[1], n_failed = ws->h_counters[3];
         uint64_t states = ws->h_counters[2];
+        if (R.beam && n_failed) {
+            set_err("a beamed start window exceeded the per-window queue capacity (" + std::to_string(ws->qcap / 4) + " states)");
+            return FAC_UNSUPPORTED;
+        }
         if (n_cand > cand_cap) {  // candidate buffer too small: grow to the exact need and redo the segment
             cand_cap = (uint32_t)std::min<uint64_t>(n_cand + n_cand / 4 + 1024, 0x7FFFFFF0u);
             if (n_cand > cand_cap) { set_err("candidate volume exceeds the 31-bit candidate index space; search a smaller haystack slice"); return FAC_UNSUPPORTED; }
@@ -355,7 +369,9 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
             n_cand = ws->h_counters[1];
             states = ws->h_counters[2];
         }
-        stats.states += states;
+        uint32_t sg_end = 0xFFFFFFFFu;
+        if (R.limit_after_expand) sg_end = R.limit_after_expand(states);
+        else stats.states += states;
         if (states_per_window_out && n_windows_total) *states_per_window_out = (double)states / (double)n_windows_total;
         if (n_cand == 0) return FAC_OK;
 
@@ -373,7 +389,7 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
         B.tab_rep = ws->best_rep.as<uint32_t>(); B.tab_val = ws->best_val.as<unsigned long long>(); B.tab_size = tab;
         B.cslot = ws->cslot.as<uint32_t>();
         B.failed_bitmap = n_failed ? ws->failed_bitmap.as<uint32_t>() : nullptr;
-        B.tv = R.tv; B.windows = R.d_windows;
+        B.tv = R.tv; B.windows = R.d_windows; B.sg_end = sg_end;
         B.out = ws->m_a.as<WMatch>() + *n_matches;
         B.out_cap = (uint32_t)n_cand;
         CK(cudaMemsetAsync((uint8_t *)ws->counters.p + 32, 0, 8, s));
@@ -558,6 +574,75 @@ fac_status segment_device(const fac_engine *E, Workspace *ws, const uint8_t *d_t
     return FAC_OK;
 }
 
+// Engines with a beam (src/search.rs:527-528, 577-589, 1096-1103).
+//  * beam_width: every start window runs the beamed kernel.
+//  * auto_beam(budget, width): windows are exact until the running total of queue.len() exceeds the
+//    budget; the window that crosses is still exact, every later one is beamed.  Exact chunks are
+//    run first with only their total; the chunk whose total crosses is redone with per-window
+//    counts to find the crossing window, its later windows are dropped from the reduction.
+fac_status search_beamed(const fac_engine *E, Workspace *ws, const TextView &tv, uint32_t g_begin, uint32_t g_end, float thr,
+                         uint64_t *n_matches, SearchStats &stats) {
+    cudaStream_t s = ws->stream;
+    const uint64_t SEG = 1u << 22;
+    auto run = [&](uint32_t a, uint32_t b, bool beamk, uint32_t bw, uint32_t *d_pw, std::function<uint32_t(uint64_t)> lim) -> fac_status {
+        for (uint64_t pos = a; pos < b; pos += SEG) {
+            ExpandRun R;
+            R.tv = tv; R.seg_begin = (uint32_t)pos; R.seg_end = (uint32_t)std::min<uint64_t>(b, pos + SEG); R.text_end = tv.n;
+            R.d_windows = ws->windows.as<FacWindow>(); R.thr = thr; R.beam = beamk; R.bw = bw; R.d_per_window = d_pw; R.limit_after_expand = lim;
+            CKS(grow_keep(ws->m_a, *n_matches * sizeof(WMatch), (*n_matches + (1u << 20)) * sizeof(WMatch), s));
+            CKS(expand_and_reduce(E, ws, R, beamk ? 1 : 8, n_matches, stats, nullptr));
+        }
+        return FAC_OK;
+    };
+    if (E->host.beam_width != 0) return run(g_begin, g_end, true, (uint32_t)std::min<uint64_t>(E->host.beam_width, 0x3FFFFFFFu), nullptr, nullptr);
+    // auto_beam
+    const uint64_t budget = E->host.ab_budget;
+    const uint32_t width = (uint32_t)std::min<uint64_t>(E->host.ab_width, 0x3FFFFFFFu);
+    uint64_t cum = 0;
+    uint32_t pos = g_begin;
+    uint32_t chunk = 1024;
+    while (pos < g_end) {
+        const uint32_t end = (uint32_t)std::min<uint64_t>(g_end, (uint64_t)pos + chunk);
+        // 1) exact pass over [pos, end) with the tiled kernel; only the chunk total is needed unless it crosses
+        bool crosses = false;
+        uint64_t chunk_states = 0;
+        auto lim1 = [&](uint64_t states) -> uint32_t {
+            chunk_states = states;
+            if (cum + states <= budget) return 0xFFFFFFFFu;  // the running total is monotone: no crossing inside
+            crosses = true;
+            return pos;  // discard this chunk's candidates; it is redone below with per-window counts
+        };
+        CKS(run(pos, end, false, 0, nullptr, lim1));
+        if (!crosses) {
+            stats.states += chunk_states;
+            cum += chunk_states;
+            pos = end;
+            if (chunk < (1u << 20)) chunk *= 4;
+            continue;
+        }
+        // 2) redo the chunk one window per CTA, recording every window's queue.len(), to find the crossing window
+        CKS(ws->pfsym.ensure((size_t)(end - pos) * 4 + 16));
+        CK(cudaMemsetAsync(ws->pfsym.p, 0, (size_t)(end - pos) * 4, s));
+        uint32_t *d_pw = ws->pfsym.as<uint32_t>() - pos;  // the kernel indexes by absolute start window
+        uint32_t crossing = end - 1;
+        auto lim2 = [&](uint64_t) -> uint32_t {
+            std::vector<uint32_t> pw(end - pos);
+            cudaMemcpy(pw.data(), ws->pfsym.p, pw.size() * 4, cudaMemcpyDeviceToHost);
+            uint64_t c = cum;
+            for (uint32_t w = 0; w < pw.size(); w++) {
+                c += pw[w];
+                if (c > budget) { crossing = pos + w; break; }
+            }
+            stats.states += c - cum;
+            return crossing + 1;
+        };
+        CKS(run(pos, end, true, 0, d_pw, lim2));
+        if (crossing + 1 < g_end) CKS(run(crossing + 1, g_end, true, width, nullptr, nullptr));
+        return FAC_OK;
+    }
+    return FAC_OK;
+}
+
 // The whole-haystack search on device-resident text: classification, (K1), K3 over segments of
 // start windows, reduction, apply.  Restricts start windows to the byte range [own_begin, own_end).
 fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_text, uint64_t len, float thr, int order, int overlap,
@@ -587,10 +672,6 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
     }
     tv.n = (uint32_t)n;
     if (n == 0) return FAC_OK;
-    if (E->host.beam_width != 0 || E->host.has_auto_beam) {
-        set_err("beam / auto_beam engines are not supported by this build of the device path yet");
-        return FAC_UNSUPPORTED;
-    }
     // owned grapheme range
     uint32_t g_begin = 0, g_end = (uint32_t)n;
     if (own_begin > 0 || own_end < len) {
@@ -611,6 +692,13 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
     CK(cudaStreamSynchronize(s));
 
     uint64_t n_matches = 0;
+    if (E->host.beam_width != 0 || E->host.has_auto_beam) {
+        CKS(search_beamed(E, ws, tv, g_begin, g_end, thr, &n_matches, stats));
+        uint32_t n_fin = (uint32_t)n_matches;
+        if (apply) CKS(apply_device(E, ws, (uint32_t)n_matches, order, overlap, 1, &n_fin, stats));
+        CKS(finalize_and_fetch(ws, n_fin, ws->windows.as<FacWindow>(), commit != ~0ull, out, stats));
+        return FAC_OK;
+    }
     const uint64_t SEG = (uint64_t)env_int("FAC_SEGMENT_WINDOWS", 1 << 25);
     uint32_t tile = E->default_tile;
     bool calibrated = tile != 0;

@@ -316,7 +316,15 @@ __global__ void __launch_bounds__(FAC_BLOCK) k_expand(const __grid_constant__ Ex
             const bool use_smem_tab = !MAPP && (C * 2u <= P.smem_tab_size);
             uint32_t *const rep = use_smem_tab ? s_rep : g_rep;
             uint32_t *const head = use_smem_tab ? s_head : g_head;
-            const uint32_t tmask = (use_smem_tab ? P.smem_tab_size : P.gtab_size) - 1u;
+            // the per-level table is sized to the level (power of two >= 2C) so its footprint stays
+            // L2-resident; the persistent table of engines with mappings keeps one size per tile
+            uint32_t tsize = use_smem_tab ? P.smem_tab_size : P.gtab_size;
+            if (!MAPP && !use_smem_tab) {
+                const uint32_t need = 2u * C;
+                uint32_t p2 = 1u << (32 - __clz(need - 1u));
+                if (p2 < tsize) tsize = p2;
+            }
+            const uint32_t tmask = tsize - 1u;
 
             // ---- phase A: group the level's states by dedup key (VisitedKey, search.rs:31-37) ----
             for (uint32_t i = lb + tid; i < le; i += FAC_BLOCK) {
@@ -468,6 +476,7 @@ struct BestParams {
     uint32_t *cslot;              // [n_cands]
     // candidates of the main pass whose tile failed are superseded by the retry pass
     const uint32_t *failed_bitmap;
+    uint32_t sg_end;              // candidates of start windows >= sg_end are ignored
     TextView tv;
     const FacWindow *windows;  // haystack windows of this call (a whole-haystack search has one)
     WMatch *out;
@@ -479,6 +488,7 @@ __device__ __forceinline__ unsigned long long fac_cand_val(const FacCand &c) {
     return ((unsigned long long)fac_total_order_u32(c.sim) << 32) | (unsigned long long)(0xFFFFFFFFu - c.seq);
 }
 __device__ __forceinline__ bool fac_cand_dead(const BestParams &P, const FacCand &c) {
+    if (c.sg >= P.sg_end) return true;  // windows past the auto_beam crossing are redone beamed
     if ((c.tag >> 31) != 0 || !P.failed_bitmap) return false;
     return (P.failed_bitmap[c.tile >> 5] >> (c.tile & 31u)) & 1u;
 }

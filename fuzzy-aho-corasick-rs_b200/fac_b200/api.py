@@ -433,6 +433,14 @@ class GpuBackend:
             raise self._err(st)
         return self._take(mh)
 
+    def search_host_ptr(self, h, ptr, n, thr, order, overlap, use_prefilter):
+        """fac_search on a caller-owned host buffer (e.g. pinned memory) given by address."""
+        mh = C.c_void_p()
+        st = self.lib.fac_search(h, C.c_void_p(ptr), n, thr, order, overlap, int(use_prefilter), C.byref(mh))
+        if st != 0:
+            raise self._err(st)
+        return self._take(mh)
+
     def search_device(self, h, dptr, n, thr, order, overlap, use_prefilter):
         mh = C.c_void_p()
         st = self.lib.fac_search_device(h, C.c_void_p(dptr), n, thr, order, overlap, int(use_prefilter), C.byref(mh))

@@ -1201,3 +1201,32 @@ size_t orc_to_lowercase(const uint8_t *s, size_t n, uint8_t *out, size_t cap) {
 size_t orc_utf8_valid_up_to(const uint8_t *s, size_t n) { return utf8_valid_up_to(s, n); }
 
 }  // extern "C"
+
+// ---- multi-core CPU baseline helper (bench.py only) ------------------------------------------------
+// Whole-input raw search split over `threads` host threads: contiguous shards of start positions,
+// each searched with a right halo of max_match_graphemes()+1 graphemes and ownership by start
+// offset -- the same decomposition rule the reference's streaming API uses (stream.rs:262-297),
+// applied to an in-memory ASCII input so that small samples still use every core.
+extern "C" int orc_search_parallel(void *e, const uint8_t *hay, size_t len, float thr, int threads, orc_matches **out) {
+    Engine *E = (Engine *)e;
+    for (size_t i = 0; i < len; i++) if (hay[i] >= 0x80) return -1;  // ASCII only (byte == grapheme)
+    const size_t nt = (size_t)std::max(1, threads);
+    const size_t halo = max_match_graphemes(*E) + 1;
+    std::vector<std::vector<Match>> res(nt);
+    std::vector<uint64_t> st(nt, 0);
+    auto work = [&](size_t t) {
+        const size_t a = len * t / nt, b = len * (t + 1) / nt;
+        if (a >= b) return;
+        const size_t end = std::min(len, b + halo);
+        std::vector<Match> v;
+        search_raw(*E, hay + a, end - a, thr, v, &st[t]);
+        for (auto &m : v) if (m.start < b - a) { m.start += a; m.end += a; res[t].push_back(m); }
+    };
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++) th.emplace_back(work, t);
+    for (auto &t : th) t.join();
+    orc_matches *o = new orc_matches();
+    for (size_t t = 0; t < nt; t++) { to_c(res[t], o); o->states += st[t]; }
+    *out = o;
+    return 0;
+}

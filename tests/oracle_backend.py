@@ -40,6 +40,7 @@ class OracleBackend:
         lib.orc_window_states.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_float, C.POINTER(C.c_uint32), C.c_size_t]
         lib.orc_apply.argtypes = [vp, C.POINTER(fac_match), C.c_size_t, C.c_int, C.c_int, C.POINTER(vp)]
         lib.orc_search_stream.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_size_t, C.c_float, C.c_int, C.POINTER(vp)]
+        lib.orc_search_parallel.argtypes = [vp, C.c_void_p, C.c_size_t, C.c_float, C.c_int, C.POINTER(vp)]
         lib.orc_cut_windows.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_uint64), C.c_size_t]
         lib.orc_replace_stream.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_size_t, C.c_float, _abi.REPLACE_FN,
                                            C.c_void_p, C.POINTER(C.POINTER(C.c_uint8)), C.POINTER(C.c_size_t)]
@@ -89,6 +90,14 @@ class OracleBackend:
             raise HaystackTooLarge(st, "haystack too large")
         if st != 0:
             raise SearchError(st, "oracle status %d" % st)
+        return self._take(mh)
+
+    def search_parallel(self, h, ptr, n, thr, threads):
+        """Raw search of n bytes at host address `ptr` over `threads` cores (ASCII input)."""
+        mh = C.c_void_p()
+        st = self.lib.orc_search_parallel(h, C.c_void_p(ptr), n, thr, threads, C.byref(mh))
+        if st != 0:
+            raise SearchError(st, "oracle parallel search status %d" % st)
         return self._take(mh)
 
     def apply(self, h, arr, n, order, overlap):

@@ -138,3 +138,36 @@ def test_tile_failure_retry_path(oracle, gpu, monkeypatch):
     g = eg.search(text, SearchOptions.new().threshold(0.8))
     assert o.tuples() == g.tuples()
     assert o.stats["states_pushed"] == g.stats["states_pushed"]
+
+
+def _beam_cases(seed, trials):
+    r = random.Random(seed)
+    words = ["saddam", "hussein", "tincidunt", "porta", "vestibulum", "accumsan", "hello", "world", "help", "shell",
+             "yellow", "abc", "abcd", "needle"]
+    fill = list("abcdehlorstu   ")
+    for t in range(trials):
+        pats = r.sample(words, r.randrange(1, 7))
+        edits = r.randrange(1, 5)
+        kind = r.randrange(3)
+        hay = ""
+        for _ in range(r.randrange(0, 80)):
+            hay += (r.choice(pats) + " ") if r.randrange(5) == 0 else r.choice(fill)
+        thr = r.choice([0.3, 0.5, 0.6, 0.7, 0.8])
+        yield t, pats, edits, kind, (r.choice([1, 2, 3, 8, 16, 100]), r.choice([1, 50, 500, 5000, 10 ** 9])), hay, thr
+
+
+def test_beam_and_auto_beam_parity(oracle, gpu):
+    for t, pats, edits, kind, (bw, budget), hay, thr in _beam_cases(21, 300):
+        def mk(b):
+            bb = FuzzyAhoCorasickBuilder.new(b).fuzzy(FuzzyLimits.new().edits(edits)).case_insensitive(True)
+            if kind == 0:
+                bb = bb.beam_width(bw)
+            elif kind == 1:
+                bb = bb.auto_beam(budget, bw)
+            else:
+                bb = bb.beam_width(bw).auto_beam(budget, 7)  # an explicit beam wins (search.rs:527)
+            return bb.build(pats)
+        o = mk(oracle).search(hay, SearchOptions.new().threshold(thr))
+        g = mk(gpu).search(hay, SearchOptions.new().threshold(thr))
+        assert o.tuples() == g.tuples(), (t, pats, edits, kind, bw, budget, thr, hay)
+        assert o.stats["states_pushed"] == g.stats["states_pushed"], (t, pats, edits, kind, bw, budget, thr, hay)
