@@ -21,6 +21,7 @@
 #include "fac_builder.h"
 #include "fac_kernels.cuh"
 #include "fac_beam.cuh"
+#include "fac_fastreduce.cuh"
 #include "fac_segment.cuh"
 
 #define FAC_TABLE_QUAL static const
@@ -72,6 +73,7 @@ struct U8ToU32 {
 
 struct SearchStats {
     uint64_t states = 0;
+    uint64_t dirty_windows = 0;
     double device_ms = 0, expand_ms = 0;
     uint32_t launches = 0;
 };
@@ -83,7 +85,7 @@ struct Workspace {
     DBuf queue, nxt, hslot, gtab_rep, gtab_head, gtab_min;
     uint32_t grid = 0, qcap = 0, gtab_size = 0;
     DBuf cands, counters, failed_tiles, failed_bitmap, tiles;
-    DBuf best_rep, best_val, cslot;
+    DBuf best_rep, best_val, cslot, tab_sim, tab_cmin, tab_cmax, tab_first, dirty;
     DBuf m_a, m_b, idx_a, idx_b, winend, st_a, st_b, flags8, sel, nsel, outm, keep8, windows, misc, cubtmp, used;
     uint64_t *h_counters = nullptr;  // pinned
     uint32_t *h_flags = nullptr;     // pinned
@@ -96,7 +98,7 @@ struct Workspace {
     }
     void destroy() {
         for (DBuf *b : {&hay, &mark, &gidx, &first, &gid, &off, &pfsym, &queue, &nxt, &hslot, &gtab_rep, &gtab_head, &gtab_min, &cands, &counters,
-                        &failed_tiles, &failed_bitmap, &tiles, &best_rep, &best_val, &cslot, &m_a, &m_b, &idx_a, &idx_b, &winend, &st_a, &st_b,
+                        &failed_tiles, &failed_bitmap, &tiles, &best_rep, &best_val, &cslot, &tab_sim, &tab_cmin, &tab_cmax, &tab_first, &dirty, &m_a, &m_b, &idx_a, &idx_b, &winend, &st_a, &st_b,
                         &flags8, &sel, &nsel, &outm, &keep8, &windows, &misc, &cubtmp, &used})
             b->release();
         if (h_counters) cudaFreeHost(h_counters);
@@ -130,6 +132,7 @@ struct fac_engine {
     uint32_t smem_tab = 4096;
     int ctas_per_sm = 2;
     int use_tma = 1;
+    bool fast_ok = false;  // FAST kernel allowed (fast-path edit ceiling, no beam); FAC_FAITHFUL=1 forces the order-faithful kernel
     mutable std::mutex mu;
     mutable std::vector<Workspace *> pool;
 };
@@ -177,19 +180,23 @@ int env_int(const char *name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-template <bool ASCII, bool MAPP>
+template <bool ASCII, bool MAPP, bool FAST>
 fac_status launch_expand_t(const ExpandParams &P, uint32_t grid, size_t smem, cudaStream_t s) {
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_expand<ASCII, MAPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_expand<ASCII, MAPP><<<grid, FAC_BLOCK, smem, s>>>(P);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_expand<ASCII, MAPP, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_expand<ASCII, MAPP, FAST><<<grid, FAC_BLOCK, smem, s>>>(P);
     CK(cudaGetLastError());
     return FAC_OK;
 }
-fac_status launch_expand(const ExpandParams &P, uint32_t grid, size_t smem, cudaStream_t s) {
+template <bool FAST>
+fac_status launch_expand_f(const ExpandParams &P, uint32_t grid, size_t smem, cudaStream_t s) {
     const bool ascii = P.tv.ascii != 0, mapp = P.A.has_mappings != 0;
-    if (ascii && !mapp) return launch_expand_t<true, false>(P, grid, smem, s);
-    if (ascii && mapp) return launch_expand_t<true, true>(P, grid, smem, s);
-    if (!ascii && !mapp) return launch_expand_t<false, false>(P, grid, smem, s);
-    return launch_expand_t<false, true>(P, grid, smem, s);
+    if (ascii && !mapp) return launch_expand_t<true, false, FAST>(P, grid, smem, s);
+    if (ascii && mapp) return launch_expand_t<true, true, FAST>(P, grid, smem, s);
+    if (!ascii && !mapp) return launch_expand_t<false, false, FAST>(P, grid, smem, s);
+    return launch_expand_t<false, true, FAST>(P, grid, smem, s);
+}
+fac_status launch_expand(const ExpandParams &P, uint32_t grid, size_t smem, cudaStream_t s, bool fast) {
+    return fast ? launch_expand_f<true>(P, grid, smem, s) : launch_expand_f<false>(P, grid, smem, s);
 }
 
 size_t expand_smem_bytes(const fac_engine *E, bool ascii, uint32_t text_cap) {
@@ -238,6 +245,8 @@ struct ExpandRun {
     const FacWindow *d_windows = nullptr;
     float thr = 0.f;
     uint32_t *d_per_window = nullptr;
+    bool fast = false;            // FAST kernel (exhausted chains walked in place) + tie detection + faithful redo
+    bool count_states = true;
     bool beam = false;            // use the one-window-per-CTA beamed kernel (bw == 0: exact)
     uint32_t bw = 0;
     // called after the expansion has completed (stream synchronised) and before the reduction;
@@ -299,7 +308,7 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
         if (R.beam) {
             k_expand_beam<<<grid, FAC_BLOCK, 0, s>>>(P, R.bw);
             CK(cudaGetLastError());
-        } else CKS(launch_expand(P, grid, smem, s));
+        } else CKS(launch_expand(P, grid, smem, s, R.fast));
         CK(cudaEventRecord(ws->evk1, s));
         stats.launches++;
         CK(cudaMemcpyAsync(ws->h_counters, ws->counters.p, 8 * 8, cudaMemcpyDeviceToHost, s));
@@ -348,7 +357,7 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
             CK(cudaMemsetAsync(ws->counters.p, 0, 8, s));
             CK(cudaMemsetAsync((uint8_t *)ws->counters.p + 24, 0, 8, s));
             CK(cudaEventRecord(ws->evk0, s));
-            CKS(launch_expand(Q, rgrid, smem, s));
+            CKS(launch_expand(Q, rgrid, smem, s, R.fast));
             CK(cudaEventRecord(ws->evk1, s));
             stats.launches++;
             CK(cudaMemcpyAsync(ws->h_counters, ws->counters.p, 8 * 8, cudaMemcpyDeviceToHost, s));
@@ -371,8 +380,8 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
         }
         uint32_t sg_end = 0xFFFFFFFFu;
         if (R.limit_after_expand) sg_end = R.limit_after_expand(states);
-        else stats.states += states;
-        if (states_per_window_out && n_windows_total) *states_per_window_out = (double)states / (double)n_windows_total;
+        else if (R.count_states) stats.states += states;
+        if (states_per_window_out && n_windows_total) *states_per_window_out = (double)ws->h_counters[6] / (double)n_windows_total;
         if (n_cand == 0) return FAC_OK;
 
         // ---- best-per-span reduction ----
@@ -394,13 +403,61 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
         B.out_cap = (uint32_t)n_cand;
         CK(cudaMemsetAsync((uint8_t *)ws->counters.p + 32, 0, 8, s));
         B.out_count = ws->counters.as<unsigned long long>() + 4;
-        k_best_insert<<<cdiv(n_cand, 256), 256, 0, s>>>(B);
-        k_best_select<<<cdiv(n_cand, 256), 256, 0, s>>>(B);
+        if (!R.fast) {
+            k_best_insert<<<cdiv(n_cand, 256), 256, 0, s>>>(B);
+            k_best_select<<<cdiv(n_cand, 256), 256, 0, s>>>(B);
+            CK(cudaGetLastError());
+            stats.launches += 2;
+            CK(cudaMemcpyAsync(ws->h_counters, ws->counters.p, 8 * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            *n_matches += ws->h_counters[4];
+            return FAC_OK;
+        }
+        // ---- FAST reduction: order-independent maximum, tie detection, faithful redo of dirty windows ----
+        const uint32_t n_win = R.seg_end - R.seg_begin;
+        const uint32_t dwords = n_win / 32 + 1;
+        CKS(ws->tab_sim.ensure((size_t)tab * 4)); CKS(ws->tab_cmin.ensure((size_t)tab * 4));
+        CKS(ws->tab_cmax.ensure((size_t)tab * 4)); CKS(ws->tab_first.ensure((size_t)tab * 4));
+        CKS(ws->dirty.ensure((size_t)dwords * 4));
+        CK(cudaMemsetAsync(ws->tab_sim.p, 0, (size_t)tab * 4, s));
+        CK(cudaMemsetAsync(ws->tab_cmin.p, 0xFF, (size_t)tab * 4, s));
+        CK(cudaMemsetAsync(ws->tab_cmax.p, 0, (size_t)tab * 4, s));
+        CK(cudaMemsetAsync(ws->tab_first.p, 0xFF, (size_t)tab * 4, s));
+        CK(cudaMemsetAsync(ws->dirty.p, 0, (size_t)dwords * 4, s));
+        FBestParams F;
+        F.B = B; F.tab_sim = ws->tab_sim.as<uint32_t>(); F.tab_cmin = ws->tab_cmin.as<uint32_t>(); F.tab_cmax = ws->tab_cmax.as<uint32_t>();
+        F.tab_first = ws->tab_first.as<uint32_t>(); F.dirty = ws->dirty.as<uint32_t>(); F.dirty_base = R.seg_begin;
+        const uint32_t gb = cdiv(n_cand, 256);
+        k_fbest_max<<<gb, 256, 0, s>>>(F);
+        k_fbest_minmax<<<gb, 256, 0, s>>>(F);
+        k_fbest_mark<<<gb, 256, 0, s>>>(F);
+        k_fbest_emit<<<gb, 256, 0, s>>>(F);
+        CKS(ws->tiles.ensure((size_t)n_win * sizeof(uint4) / 8 + 4096));  // dirty windows are rare; overflow is re-run below
+        const uint32_t dcap = (uint32_t)(ws->tiles.cap / sizeof(uint4));
+        CK(cudaMemsetAsync((uint8_t *)ws->counters.p + 40, 0, 8, s));
+        k_dirty_tiles<<<cdiv(dwords, 256), 256, 0, s>>>(ws->dirty.as<uint32_t>(), dwords, R.seg_begin, R.text_end, ws->tiles.as<uint4>(), dcap,
+                                                        ws->counters.as<unsigned long long>() + 5);
         CK(cudaGetLastError());
-        stats.launches += 2;
+        stats.launches += 5;
         CK(cudaMemcpyAsync(ws->h_counters, ws->counters.p, 8 * 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         *n_matches += ws->h_counters[4];
+        uint64_t n_dirty = ws->h_counters[5];
+        if (n_dirty) {
+            if (n_dirty > dcap) {  // enlarge and list again
+                CKS(ws->tiles.ensure((size_t)n_dirty * sizeof(uint4)));
+                CK(cudaMemsetAsync((uint8_t *)ws->counters.p + 40, 0, 8, s));
+                k_dirty_tiles<<<cdiv(dwords, 256), 256, 0, s>>>(ws->dirty.as<uint32_t>(), dwords, R.seg_begin, R.text_end, ws->tiles.as<uint4>(),
+                                                                (uint32_t)n_dirty, ws->counters.as<unsigned long long>() + 5);
+                CK(cudaStreamSynchronize(s));
+            }
+            ExpandRun R2;
+            R2.tv = R.tv; R2.text_end = R.text_end; R2.d_windows = R.d_windows; R2.thr = R.thr; R2.fast = false; R2.count_states = false;
+            R2.tiles.resize(n_dirty);
+            CK(cudaMemcpy(R2.tiles.data(), ws->tiles.p, n_dirty * sizeof(uint4), cudaMemcpyDeviceToHost));
+            stats.dirty_windows += n_dirty;
+            CKS(expand_and_reduce(E, ws, R2, 1, n_matches, stats, nullptr));
+        }
         return FAC_OK;
     }
     set_err("candidate buffer kept overflowing");
@@ -709,7 +766,7 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
         if (!calibrated) seg = std::min<uint64_t>(seg, 1 << 16);  // small calibration segment decides the tile size
         ExpandRun R;
         R.tv = tv; R.seg_begin = (uint32_t)pos; R.seg_end = (uint32_t)(pos + seg); R.text_end = (uint32_t)n;
-        R.d_windows = ws->windows.as<FacWindow>(); R.thr = thr;
+        R.d_windows = ws->windows.as<FacWindow>(); R.thr = thr; R.fast = E->fast_ok;
         double spw = 0;
         // keep what is already in m_a: grow by copy before the reduction writes
         CKS(grow_keep(ws->m_a, n_matches * sizeof(WMatch), (n_matches + (1u << 20)) * sizeof(WMatch), s));
@@ -806,6 +863,7 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
     E->smem_tab = (uint32_t)env_int("FAC_SMEM_TAB", 4096);
     E->ctas_per_sm = env_int("FAC_CTAS_PER_SM", 4);
     E->use_tma = env_int("FAC_USE_TMA", 1);
+    E->fast_ok = H.mef != 255 && H.beam_width == 0 && !H.has_auto_beam && env_int("FAC_FAITHFUL", 0) == 0;
     *out = E;
     return FAC_OK;
 }

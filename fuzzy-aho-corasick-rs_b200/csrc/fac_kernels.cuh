@@ -161,7 +161,7 @@ struct ExpandParams {
     // outputs
     FacCand *cands;
     uint32_t cand_cap;
-    unsigned long long *counters;  // [0] next tile, [1] candidates, [2] states pushed, [3] failed tiles
+    unsigned long long *counters;  // [0] next tile, [1] candidates, [2] states pushed, [3] failed tiles, [4] matches, [5] dirty, [6] queued states
     uint32_t *failed_tiles;
     uint32_t failed_cap;
     uint32_t *failed_bitmap;  // one bit per tile of the main pass
@@ -199,7 +199,50 @@ __device__ __forceinline__ uint32_t fac_hash3(uint32_t a, uint32_t b, uint32_t c
     return h;
 }
 
-template <bool ASCII, bool MAPP>
+// Append one raw candidate (a `best.entry(key)` visit, search.rs:705-735) to the global list.
+__device__ __forceinline__ void fac_emit_cand(const ExpandParams &P, uint32_t sg, uint32_t eg, uint32_t pat, float sim, uint32_t cnt,
+                                              uint32_t seq, uint32_t tile, uint32_t tag) {
+    const unsigned long long ci = atomicAdd(&P.counters[1], 1ull);
+    if (ci < P.cand_cap) {
+        FacCand cd;
+        cd.sg = sg; cd.eg = eg; cd.pat = pat; cd.sim = sim; cd.cnt = cnt; cd.seq = seq; cd.tile = tile; cd.tag = tag;
+        uint4 *dst = reinterpret_cast<uint4 *>(&P.cands[ci]);
+        dst[0] = reinterpret_cast<uint4 *>(&cd)[0];
+        dst[1] = reinterpret_cast<uint4 *>(&cd)[1];
+    }
+}
+
+// FAST mode: a child that has spent its whole edit budget can only follow exact transitions
+// (sub / swap / ins / del all need `edits < MAX_EDITS_FAST`, search.rs:810, 937, 1003, 1043), so its
+// entire future is one chain of exact steps.  Instead of materialising that chain state by state
+// it is walked here, with the same per-pop checks (node ceiling :638-642, outputs :659-737, exact
+// transition :776-798).  Returns the number of chain states visited.
+template <class Text>
+__device__ __forceinline__ uint32_t fac_walk_exhausted(const ExpandParams &P, const Text &T, uint32_t start, uint32_t text_end,
+                                                       const FacState &child, uint32_t tile, uint32_t tag) {
+    const AutomatonView &A = P.A;
+    uint32_t node = child.node;
+    uint32_t jr = (child.pos >> FAC_POS_J_SHIFT) & FAC_POS_MASK, mr = child.pos & FAC_POS_MASK;
+    uint32_t steps = 0;
+    for (;;) {
+        steps++;
+        if (fac_over_ceiling(A, node, child.pen, P.thr)) break;
+        const uint32_t o1 = A.node_out_off[node + 1];
+        for (uint32_t o = A.node_out_off[node]; o < o1; o++) {
+            const uint32_t pat = A.out_pat[o];
+            float sim;
+            if (fac_eval_output(A, P.thr, pat, child.pen, child.cnt, sim)) fac_emit_cand(P, start, start + mr, pat, sim, child.cnt, 0u, tile, tag);
+        }
+        const uint32_t j = start + jr;
+        if (j >= text_end) break;
+        const uint32_t nx = A.has_mappings ? fac_lookup(A, node, T.gid(j)) : fac_lookup(A, node, T.first(j));
+        if (nx == FAC_NONE) break;
+        node = nx; jr++; mr = jr;
+    }
+    return steps;
+}
+
+template <bool ASCII, bool MAPP, bool FAST>
 __global__ void __launch_bounds__(FAC_BLOCK) k_expand(const __grid_constant__ ExpandParams P) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -291,6 +334,7 @@ __global__ void __launch_bounds__(FAC_BLOCK) k_expand(const __grid_constant__ Ex
 
         // ---- level 0: one root state per (non-skipped) start window, in window order ----
         uint32_t qlen = 0;
+        uint32_t tail_steps = 0;  // FAST: chain states walked in place instead of being queued
         bool failed = false;
         for (uint32_t w0 = 0; w0 < count; w0 += FAC_BLOCK) {
             const uint32_t w = w0 + tid;
@@ -370,17 +414,8 @@ __global__ void __launch_bounds__(FAC_BLOCK) k_expand(const __grid_constant__ Ex
                         for (uint32_t o = A.node_out_off[S.node]; o < o1; o++) {
                             const uint32_t pat = A.out_pat[o];
                             float sim;
-                            if (fac_eval_output(A, P.thr, pat, S.pen, S.cnt, sim)) {
-                                const unsigned long long ci = atomicAdd(&P.counters[1], 1ull);
-                                if (ci < P.cand_cap) {
-                                    FacCand cd;
-                                    cd.sg = start; cd.eg = start + (S.pos & FAC_POS_MASK); cd.pat = pat; cd.sim = sim;
-                                    cd.cnt = S.cnt; cd.seq = i; cd.tile = t; cd.tag = win_tag;
-                                    uint4 *dst = reinterpret_cast<uint4 *>(&P.cands[ci]);
-                                    dst[0] = reinterpret_cast<uint4 *>(&cd)[0];
-                                    dst[1] = reinterpret_cast<uint4 *>(&cd)[1];
-                                }
-                            }
+                            if (fac_eval_output(A, P.thr, pat, S.pen, S.cnt, sim))
+                                fac_emit_cand(P, start, start + (S.pos & FAC_POS_MASK), pat, sim, S.cnt, i, t, win_tag);
                         }
                         FacCtx Cx;
                         fac_make_ctx(A, T, P.maxpen, start, text_end, S, Cx);
@@ -410,6 +445,10 @@ __global__ void __launch_bounds__(FAC_BLOCK) k_expand(const __grid_constant__ Ex
                         Cx.exact = c_exact[lo]; Cx.flags = c_flags[lo]; Cx.nslots = 0;
                         const uint32_t start = tile_start + (Cx.pos >> FAC_POS_W_SHIFT);
                         push = fac_eval_slot(A, T, P.maxpen, start, text_end, Cx, k - s_off[lo], child);
+                        if (FAST && push && (int)fac_edits_of(child.cnt) >= A.mef) {
+                            tail_steps += fac_walk_exhausted(P, T, start, text_end, child, t, win_tag);
+                            push = false;
+                        }
                     }
                     uint32_t total;
                     const uint32_t r = fac_block_rank(push, s_scan, parity, total);
@@ -450,6 +489,10 @@ __global__ void __launch_bounds__(FAC_BLOCK) k_expand(const __grid_constant__ Ex
                 g_rep[h] = FAC_EMPTY; g_head[h] = FAC_EMPTY; g_min[h] = __int_as_float(0x7F800000);
             }
         }
+        if (FAST && !failed) {
+            tail_steps = __reduce_add_sync(0xFFFFFFFFu, tail_steps);
+            if (fac_lane() == 0 && tail_steps) atomicAdd(&P.counters[2], (unsigned long long)tail_steps);
+        }
         if (tid == 0) {
             if (failed) {
                 const unsigned long long fi = atomicAdd(&P.counters[3], 1ull);
@@ -457,6 +500,7 @@ __global__ void __launch_bounds__(FAC_BLOCK) k_expand(const __grid_constant__ Ex
                 if (P.failed_bitmap) atomicOr(&P.failed_bitmap[t >> 5], 1u << (t & 31u));
             } else {
                 atomicAdd(&P.counters[2], (unsigned long long)le);
+                atomicAdd(&P.counters[6], (unsigned long long)le);  // queued states only (tile sizing)
             }
         }
         __syncthreads();
