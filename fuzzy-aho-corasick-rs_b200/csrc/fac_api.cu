@@ -824,7 +824,7 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
 #define UP(field, vec) do { fac_status s_ = upload(E, vec, &V.field); if (s_ != FAC_OK) return fail(s_); } while (0)
     UP(node_edge_off, H.node_edge_off); UP(node_prune_len, H.node_prune_len); UP(node_prune_low, H.node_prune_low);
     UP(node_out_off, H.node_out_off); UP(node_bitmap, H.node_bitmap); UP(node_lim, H.node_lim); UP(node_map_off, H.node_map_off);
-    UP(edge_char, H.edge_char); UP(edge_next, H.edge_next); UP(trans, H.trans); UP(out_pat, H.out_pat);
+    UP(edge_char, H.edge_char); UP(edge_next, H.edge_next); UP(edge_sym, H.edge_sym); UP(trans, H.trans); UP(out_pat, H.out_pat);
     UP(pat_glen, H.pat_glen); UP(pat_weight, H.pat_weight); UP(pat_lim, H.pat_lim); UP(lim, H.lim);
     UP(sim_ascii, H.sim_ascii); UP(sim_keys, H.sim_keys); UP(sim_vals, H.sim_vals);
     UP(map_hay_off, H.map_hay_off); UP(map_hay_gid, H.map_hay_gid); UP(map_next, H.map_next); UP(map_pen, H.map_pen);

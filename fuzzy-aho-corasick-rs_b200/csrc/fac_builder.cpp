@@ -327,7 +327,7 @@ fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_
     // ---- flatten nodes / edges ----
     A.node_edge_off.assign(N + 1, 0); A.node_out_off.assign(N + 1, 0); A.node_map_off.assign(N + 1, 0);
     A.node_bitmap.assign(N * 4, 0); A.node_lim.assign(N, FAC_NONE);
-    A.edge_char.clear(); A.edge_next.clear(); A.out_pat.clear();
+    A.edge_char.clear(); A.edge_next.clear(); A.edge_sym.clear(); A.out_pat.clear();
     A.map_hay_off.assign(1, 0); A.map_hay_gid.clear(); A.map_next.clear(); A.map_pen.clear();
     size_t n_trans = 0;
     for (size_t i = 0; i < N; i++) {
@@ -338,6 +338,7 @@ fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_
             const uint32_t fc = first_scalar(kv.first);
             A.edge_char.push_back(fc);
             A.edge_next.push_back(kv.second | (nodes[kv.second].output.empty() ? 0u : 0x80000000u));
+            A.edge_sym.push_back(A.has_mappings ? gid_of[kv.first] : fc);
             if (kv.first.size() == 1 && fc < 128) A.node_bitmap[i * 4 + (fc >> 5)] |= 1u << (fc & 31);
             n_trans++;
         }
@@ -519,7 +520,7 @@ AutomatonView HostAutomaton::host_view() const {
     V.n_nodes = n_nodes(); V.n_edges = (uint32_t)edge_char.size(); V.n_patterns = (uint32_t)patterns.size(); V.n_outputs = (uint32_t)out_pat.size();
     V.node_edge_off = node_edge_off.data(); V.node_prune_len = node_prune_len.data(); V.node_prune_low = node_prune_low.data();
     V.node_out_off = node_out_off.data(); V.node_bitmap = node_bitmap.data(); V.node_lim = node_lim.data(); V.node_map_off = node_map_off.data();
-    V.edge_char = edge_char.data(); V.edge_next = edge_next.data();
+    V.edge_char = edge_char.data(); V.edge_next = edge_next.data(); V.edge_sym = edge_sym.data();
     V.trans = trans.data(); V.trans_mask = (uint32_t)trans.size() - 1;
     V.out_pat = out_pat.data(); V.pat_glen = pat_glen.data(); V.pat_weight = pat_weight.data(); V.pat_lim = pat_lim.data(); V.lim = lim.data();
     V.sim_ascii = sim_ascii.data(); V.sim_keys = sim_keys.data(); V.sim_vals = sim_vals.data(); V.n_sim = (uint32_t)sim_keys.size();

@@ -60,7 +60,7 @@ struct HostAutomaton {
     // flattened arrays, exactly the members of AutomatonView
     std::vector<uint32_t> node_edge_off, node_out_off, node_bitmap, node_lim, node_map_off;
     std::vector<float> node_prune_len, node_prune_low;
-    std::vector<uint32_t> edge_char, edge_next;
+    std::vector<uint32_t> edge_char, edge_next, edge_sym;
     std::vector<FacTrans> trans;
     std::vector<uint32_t> out_pat;
     std::vector<float> pat_glen, pat_weight;

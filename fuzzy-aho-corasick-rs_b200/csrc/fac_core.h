@@ -81,8 +81,11 @@ FAC_HD uint32_t fac_hash2(uint32_t a, uint32_t b) {
 
 // Exact transition (Node::find_transition*, src/structs.rs:452-519).  `sym` is the text first char
 // for engines without mappings (first edge in build order with that first char wins), else the
-// grapheme id of the folded haystack grapheme (full-string identity).
-FAC_HD uint32_t fac_lookup(const AutomatonView &A, uint32_t node, uint32_t sym) {
+// grapheme id of the folded haystack grapheme (full-string identity).  Low-degree nodes (the bulk
+// of a trie) are resolved by scanning their edge symbols, which are contiguous; high-degree nodes
+// go through the open-addressing table.
+#define FAC_SCAN_DEG 4u
+FAC_HD uint32_t fac_lookup_hash(const AutomatonView &A, uint32_t node, uint32_t sym) {
     uint32_t h = fac_hash2(node, sym) & A.trans_mask;
     for (;;) {
         const FacTrans t = A.trans[h];
@@ -90,6 +93,18 @@ FAC_HD uint32_t fac_lookup(const AutomatonView &A, uint32_t node, uint32_t sym) 
         if (t.node == node && t.sym == sym) return t.next;
         h = (h + 1) & A.trans_mask;
     }
+}
+FAC_HD uint32_t fac_find_edge(const AutomatonView &A, uint32_t node, uint32_t eoff, uint32_t deg, uint32_t sym) {
+    if (deg <= FAC_SCAN_DEG) {
+        for (uint32_t e = 0; e < deg; e++)
+            if (A.edge_sym[eoff + e] == sym) return A.edge_next[eoff + e] & 0x7FFFFFFFu;
+        return FAC_NONE;
+    }
+    return fac_lookup_hash(A, node, sym);
+}
+FAC_HD uint32_t fac_lookup(const AutomatonView &A, uint32_t node, uint32_t sym) {
+    const uint32_t eoff = A.node_edge_off[node];
+    return fac_find_edge(A, node, eoff, A.node_edge_off[node + 1] - eoff, sym);
 }
 
 // Node::has_matching_edge_char (src/structs.rs:471-475): a single-ASCII-byte edge equal to `ch`.

@@ -42,6 +42,7 @@ struct AutomatonView {
     // ---- edges ----
     const uint32_t *edge_char;  // [E] Edge::first_char
     const uint32_t *edge_next;  // [E] bit31 = child has a non-empty output; low 31 bits = Edge::next()
+    const uint32_t *edge_sym;   // [E] exact-match symbol of the edge: first char (no mappings) or grapheme id (mappings)
     // ---- exact transition lookup ----
     const FacTrans *trans;  // [trans_mask+1]
     uint32_t trans_mask;
