@@ -23,6 +23,7 @@
 #include "fac_beam.cuh"
 #include "fac_fastreduce.cuh"
 #include "fac_segment.cuh"
+#include "fac_succinct.cuh"
 
 #define FAC_TABLE_QUAL static const
 #include "unicode_tables.h"
@@ -81,7 +82,7 @@ struct SearchStats {
 struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, evk0 = nullptr, evk1 = nullptr;
-    DBuf hay, mark, gidx, first, gid, off, pfsym;
+    DBuf hay, mark, gidx, first, gid, off, pfsym, srec;
     DBuf queue, nxt, hslot, gtab_rep, gtab_head, gtab_min;
     uint32_t grid = 0, qcap = 0, gtab_size = 0;
     DBuf cands, counters, failed_tiles, failed_bitmap, tiles;
@@ -97,7 +98,7 @@ struct Workspace {
         return FAC_OK;
     }
     void destroy() {
-        for (DBuf *b : {&hay, &mark, &gidx, &first, &gid, &off, &pfsym, &queue, &nxt, &hslot, &gtab_rep, &gtab_head, &gtab_min, &cands, &counters,
+        for (DBuf *b : {&hay, &mark, &gidx, &first, &gid, &off, &pfsym, &srec, &queue, &nxt, &hslot, &gtab_rep, &gtab_head, &gtab_min, &cands, &counters,
                         &failed_tiles, &failed_bitmap, &tiles, &best_rep, &best_val, &cslot, &tab_sim, &tab_cmin, &tab_cmax, &tab_first, &dirty, &m_a, &m_b, &idx_a, &idx_b, &winend, &st_a, &st_b,
                         &flags8, &sel, &nsel, &outm, &keep8, &windows, &misc, &cubtmp, &used})
             b->release();
@@ -132,6 +133,13 @@ struct fac_engine {
     uint32_t smem_tab = 4096;
     int ctas_per_sm = 2;
     int use_tma = 1;
+    // succinct-trie fast kernel (fac_succinct.cuh)
+    bool succ_ok = false;
+    const uint32_t *d_s_bm = nullptr, *d_s_fc = nullptr, *d_s_out_idx = nullptr, *d_s_out2 = nullptr;
+    const float *d_s_plen = nullptr, *d_s_plow = nullptr, *d_s_subpen = nullptr;
+    const uint8_t *d_s_symof = nullptr;
+    uint32_t succ_nt = 768, succ_tile = 1024, succ_stack = 0;
+    int smem_optin = 0;
     bool fast_ok = false;  // FAST kernel allowed (fast-path edit ceiling, no beam); FAC_FAITHFUL=1 forces the order-faithful kernel
     mutable std::mutex mu;
     mutable std::vector<Workspace *> pool;
@@ -197,6 +205,51 @@ fac_status launch_expand_f(const ExpandParams &P, uint32_t grid, size_t smem, cu
 }
 fac_status launch_expand(const ExpandParams &P, uint32_t grid, size_t smem, cudaStream_t s, bool fast) {
     return fast ? launch_expand_f<true>(P, grid, smem, s) : launch_expand_f<false>(P, grid, smem, s);
+}
+
+// ---- succinct fast kernel launch (fac_succinct.cuh) ----
+template <int NT>
+fac_status launch_succ_t(const SuccParams &P, uint32_t grid, size_t smem, cudaStream_t s) {
+    CK(cudaFuncSetAttribute(k_expand_succinct<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_expand_succinct<NT><<<grid, NT, smem, s>>>(P);
+    CK(cudaGetLastError());
+    return FAC_OK;
+}
+fac_status launch_succinct(const fac_engine *E, Workspace *ws, const uint8_t *d_text, float thr, uint32_t seg_begin, uint32_t seg_end,
+                           uint32_t text_end, FacCand *cands, uint32_t cand_cap, cudaStream_t s) {
+    const fac::HostSuccinct &S = E->host.succ;
+    const uint32_t N = (uint32_t)S.bm.size();
+    CKS(ws->srec.ensure((size_t)N * 16));
+    k_succ_prepare<<<cdiv(N, 256), 256, 0, s>>>(E->d_s_bm, E->d_s_fc, E->d_s_plen, E->d_s_plow, E->d_s_out_idx, thr, N, ws->srec.as<uint4>());
+    CK(cudaGetLastError());
+    SuccParams P;
+    memset(&P, 0, sizeof(P));
+    P.rec = ws->srec.as<uint4>(); P.out2 = (const uint4 *)E->d_s_out2; P.sub_pen = E->d_s_subpen; P.sym_of = E->d_s_symof; P.text = d_text;
+    P.n_nodes = N;
+    P.K.thr = thr;
+    P.K.maxpen = S.prune_len[0] - S.prune_low[0] * thr;  // search.rs:487 (host compiled without contraction)
+    P.K.pen_ins = E->host.pen_ins; P.K.pen_del = E->host.pen_del; P.K.pen_swap = E->host.pen_swap; P.K.mef = E->host.mef;
+    P.ci = E->host.ci; P.wskip = E->host.wskip; P.first_mask = S.first_mask; P.second_mask = S.second_mask;
+    P.seg_begin = seg_begin; P.seg_end = seg_end; P.text_end = text_end;
+    P.tile = E->succ_tile; P.n_tiles = cdiv((uint64_t)seg_end - seg_begin, P.tile); P.lookahead = E->lookahead;
+    const uint32_t nw = E->succ_nt / 32;
+    P.stack_cap = E->succ_stack ? E->succ_stack : (E->host.mef <= 2 ? 128u : 384u);
+    P.text_cap = (P.tile + P.lookahead + 16u + 15u) & ~15u;
+    const size_t fixed = (size_t)nw * P.stack_cap * 16 + 32 * 128 * 4 + (size_t)P.text_cap * 3 + 256;
+    const size_t budget = (size_t)E->smem_optin - 1024;  // static shared + reserve
+    if (fixed + 16 * 64 > budget) { set_err("succinct kernel: shared-memory budget too small for the configured stack / tile"); return FAC_UNSUPPORTED; }
+    P.n_smem_nodes = (uint32_t)std::min<size_t>(N, (budget - fixed) / 16);
+    P.cands = cands; P.cand_cap = cand_cap;
+    P.counters = ws->counters.as<unsigned long long>();
+    P.dirty = ws->dirty.as<uint32_t>();
+    const size_t smem = fixed + (size_t)P.n_smem_nodes * 16;
+    const uint32_t grid = std::min<uint32_t>((uint32_t)E->sm_count, P.n_tiles);
+    switch (E->succ_nt) {
+        case 1024: return launch_succ_t<1024>(P, grid, smem, s);
+        case 512: return launch_succ_t<512>(P, grid, smem, s);
+        case 256: return launch_succ_t<256>(P, grid, smem, s);
+        default: return launch_succ_t<768>(P, grid, smem, s);
+    }
 }
 
 size_t expand_smem_bytes(const fac_engine *E, bool ascii, uint32_t text_cap) {
@@ -299,15 +352,23 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
     P.per_window = R.d_per_window;
     P.use_tma = E->use_tma;
     const size_t smem = expand_smem_bytes(E, ascii, P.smem_text_cap);
+    const bool use_succ = R.fast && E->succ_ok && ascii && !explicit_tiles && !R.beam && !R.d_per_window;
+    const uint32_t n_win_seg = explicit_tiles ? 0 : (R.seg_end - R.seg_begin);
+    const uint32_t dirty_words = n_win_seg / 32 + 1;
+    if (R.fast) CKS(ws->dirty.ensure((size_t)dirty_words * 4));
 
     for (int attempt = 0; attempt < 3; attempt++) {
         CK(cudaMemsetAsync(ws->counters.p, 0, 16 * 8, s));
+        if (R.fast) CK(cudaMemsetAsync(ws->dirty.p, 0, (size_t)dirty_words * 4, s));
         CK(cudaMemsetAsync(ws->failed_bitmap.p, 0, (size_t)4 * (n_tiles / 32 + 1), s));
         P.pass = 0; P.cand_cap = cand_cap; P.cands = ws->cands.as<FacCand>();
         CK(cudaEventRecord(ws->evk0, s));
         if (R.beam) {
             k_expand_beam<<<grid, FAC_BLOCK, 0, s>>>(P, R.bw);
             CK(cudaGetLastError());
+        } else if (use_succ) {
+            CKS(launch_succinct(E, ws, R.tv.bytes, R.thr, R.seg_begin, R.seg_end, R.text_end, ws->cands.as<FacCand>(), cand_cap, s));
+            stats.launches++;
         } else CKS(launch_expand(P, grid, smem, s, R.fast));
         CK(cudaEventRecord(ws->evk1, s));
         stats.launches++;
@@ -382,7 +443,8 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
         if (R.limit_after_expand) sg_end = R.limit_after_expand(states);
         else if (R.count_states) stats.states += states;
         if (states_per_window_out && n_windows_total) *states_per_window_out = (double)ws->h_counters[6] / (double)n_windows_total;
-        if (n_cand == 0) return FAC_OK;
+        const uint64_t n_overflowed = use_succ ? ws->h_counters[7] : 0;
+        if (n_cand == 0 && n_overflowed == 0) return FAC_OK;
 
         // ---- best-per-span reduction ----
         const uint32_t tab = next_pow2(n_cand * 2 + 16);
@@ -418,20 +480,20 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
         const uint32_t dwords = n_win / 32 + 1;
         CKS(ws->tab_sim.ensure((size_t)tab * 4)); CKS(ws->tab_cmin.ensure((size_t)tab * 4));
         CKS(ws->tab_cmax.ensure((size_t)tab * 4)); CKS(ws->tab_first.ensure((size_t)tab * 4));
-        CKS(ws->dirty.ensure((size_t)dwords * 4));
         CK(cudaMemsetAsync(ws->tab_sim.p, 0, (size_t)tab * 4, s));
         CK(cudaMemsetAsync(ws->tab_cmin.p, 0xFF, (size_t)tab * 4, s));
         CK(cudaMemsetAsync(ws->tab_cmax.p, 0, (size_t)tab * 4, s));
         CK(cudaMemsetAsync(ws->tab_first.p, 0xFF, (size_t)tab * 4, s));
-        CK(cudaMemsetAsync(ws->dirty.p, 0, (size_t)dwords * 4, s));
         FBestParams F;
         F.B = B; F.tab_sim = ws->tab_sim.as<uint32_t>(); F.tab_cmin = ws->tab_cmin.as<uint32_t>(); F.tab_cmax = ws->tab_cmax.as<uint32_t>();
         F.tab_first = ws->tab_first.as<uint32_t>(); F.dirty = ws->dirty.as<uint32_t>(); F.dirty_base = R.seg_begin;
         const uint32_t gb = cdiv(n_cand, 256);
-        k_fbest_max<<<gb, 256, 0, s>>>(F);
-        k_fbest_minmax<<<gb, 256, 0, s>>>(F);
-        k_fbest_mark<<<gb, 256, 0, s>>>(F);
-        k_fbest_emit<<<gb, 256, 0, s>>>(F);
+        if (gb) {
+            k_fbest_max<<<gb, 256, 0, s>>>(F);
+            k_fbest_minmax<<<gb, 256, 0, s>>>(F);
+            k_fbest_mark<<<gb, 256, 0, s>>>(F);
+            k_fbest_emit<<<gb, 256, 0, s>>>(F);
+        }
         CKS(ws->tiles.ensure((size_t)n_win * sizeof(uint4) / 8 + 4096));  // dirty windows are rare; overflow is re-run below
         const uint32_t dcap = (uint32_t)(ws->tiles.cap / sizeof(uint4));
         CK(cudaMemsetAsync((uint8_t *)ws->counters.p + 40, 0, 8, s));
@@ -759,6 +821,7 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
     const uint64_t SEG = (uint64_t)env_int("FAC_SEGMENT_WINDOWS", 1 << 25);
     uint32_t tile = E->default_tile;
     bool calibrated = tile != 0;
+    if (E->succ_ok && ascii) { calibrated = true; if (!tile) tile = 8; }  // the succinct kernel tiles by itself
     if (!calibrated) tile = 4;
     uint64_t pos = g_begin;
     while (pos < g_end) {
@@ -854,8 +917,21 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
         if ((st = upload(E, H.symbol_pool, &pool)) != FAC_OK) return fail(st);
         E->d_symbols = (FacSymbol *)sy; E->sym_mask = (uint32_t)H.symbols.size() - 1; E->d_pool = (uint8_t *)pool;
     }
+    if (H.succ.ok) {
+        const fac::HostSuccinct &S = H.succ;
+        std::vector<uint8_t> symof(S.sym_of, S.sym_of + 256);
+        if ((st = upload(E, S.bm, &E->d_s_bm)) != FAC_OK) return fail(st);
+        if ((st = upload(E, S.fc_sym, &E->d_s_fc)) != FAC_OK) return fail(st);
+        if ((st = upload(E, S.out_idx, &E->d_s_out_idx)) != FAC_OK) return fail(st);
+        if ((st = upload(E, S.out2, &E->d_s_out2)) != FAC_OK) return fail(st);
+        if ((st = upload(E, S.prune_len, &E->d_s_plen)) != FAC_OK) return fail(st);
+        if ((st = upload(E, S.prune_low, &E->d_s_plow)) != FAC_OK) return fail(st);
+        if ((st = upload(E, S.sub_pen, &E->d_s_subpen)) != FAC_OK) return fail(st);
+        if ((st = upload(E, symof, &E->d_s_symof)) != FAC_OK) return fail(st);
+    }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
+    CK(cudaDeviceGetAttribute(&E->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     E->sm_count = prop.multiProcessorCount;
     E->lookahead = (uint32_t)H.max_match_graphemes + H.max_map_hay + 3;
     E->default_tile = (uint32_t)env_int("FAC_TILE", 0);
@@ -864,6 +940,10 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
     E->ctas_per_sm = env_int("FAC_CTAS_PER_SM", 4);
     E->use_tma = env_int("FAC_USE_TMA", 1);
     E->fast_ok = H.mef != 255 && H.beam_width == 0 && !H.has_auto_beam && env_int("FAC_FAITHFUL", 0) == 0;
+    E->succ_ok = E->fast_ok && H.succ.ok && env_int("FAC_SUCCINCT", 1) != 0;
+    E->succ_nt = (uint32_t)env_int("FAC_SUCC_THREADS", 768);
+    E->succ_tile = (uint32_t)std::max(32, env_int("FAC_SUCC_TILE", 1024));
+    E->succ_stack = (uint32_t)env_int("FAC_SUCC_STACK", 0);
     *out = E;
     return FAC_OK;
 }

@@ -1,5 +1,8 @@
 // fac_builder.cpp -- host-side construction of the flattened automaton (see fac_builder.h).
 #include "fac_builder.h"
+#include "fac_succinct.h"
+#include <limits>
+#define FAC_POPC_HOST(x) __builtin_popcount(x)
 #include "fac_core.h"
 
 #include <algorithm>
@@ -437,6 +440,77 @@ fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_
             if (!nodes[kv.second].output.empty()) child_output = true;
         }
         if (!child_output) { A.wskip = true; for (int k = 0; k < 4; k++) { A.ws_first[k] = first[k]; A.ws_second[k] = second[k]; } }
+    }
+
+    // ---- succinct BFS-ordered trie for the fast kernel (fac_succinct.h) ----
+    {
+        HostSuccinct &S = A.succ;
+        S = HostSuccinct();
+        memset(S.sym_of, 31, sizeof(S.sym_of));
+        bool ok = !A.has_mappings && A.mef != 255 && N <= SUCC_MAX_NODES;
+        std::vector<int> sym_of_char(128, -1);
+        std::vector<uint32_t> chars;
+        for (size_t i = 0; i < N && ok; i++)
+            for (auto &kv : nodes[i].order) {
+                if (kv.first.size() != 1 || (uint8_t)kv.first[0] >= 128) { ok = false; break; }
+                chars.push_back((uint8_t)kv.first[0]);
+            }
+        if (ok) {
+            std::sort(chars.begin(), chars.end());
+            chars.erase(std::unique(chars.begin(), chars.end()), chars.end());
+            if (chars.size() > 31) ok = false;
+        }
+        if (ok) {
+            S.n_syms = (uint32_t)chars.size();
+            for (size_t k = 0; k < chars.size(); k++) { sym_of_char[chars[k]] = (int)k; S.sym_of[chars[k]] = (uint8_t)k; }
+            // BFS numbering: children of a node contiguous, sorted by symbol
+            std::vector<uint32_t> new_of(N, 0);
+            S.old_of.assign(1, 0);
+            S.bm.assign(N, 0); S.fc_sym.assign(N, 0);
+            for (size_t h = 0; h < S.old_of.size(); h++) {
+                const uint32_t old = S.old_of[h];
+                std::vector<std::pair<uint32_t, uint32_t>> ch;  // (sym, old child)
+                for (auto &kv : nodes[old].order) ch.emplace_back((uint32_t)sym_of_char[(uint8_t)kv.first[0]], kv.second);
+                std::sort(ch.begin(), ch.end());
+                S.fc_sym[h] |= (uint32_t)S.old_of.size();
+                for (auto &c : ch) {
+                    S.bm[h] |= 1u << c.first;
+                    new_of[c.second] = (uint32_t)S.old_of.size();
+                    S.fc_sym[S.old_of.size()] = c.first << 27;
+                    S.old_of.push_back(c.second);
+                }
+            }
+            S.prune_len.resize(N); S.prune_low.resize(N); S.out_idx.assign(N, FAC_NONE);
+            for (size_t h = 0; h < N; h++) {
+                const uint32_t old = S.old_of[h];
+                S.prune_len[h] = A.node_prune_len[old]; S.prune_low[h] = A.node_prune_low[old];
+                const auto &o = nodes[old].output;
+                if (!o.empty()) {
+                    S.out_idx[h] = (uint32_t)(S.out2.size() / 4);
+                    for (size_t k = 0; k < o.size(); k++) {
+                        union { float f; uint32_t u; } g, w;
+                        g.f = A.pat_glen[o[k]]; w.f = A.pat_weight[o[k]];
+                        S.out2.push_back(o[k] | (k + 1 == o.size() ? 0x80000000u : 0u));
+                        S.out2.push_back(g.u); S.out2.push_back(w.u); S.out2.push_back(0);
+                    }
+                }
+            }
+            if (S.out2.empty()) S.out2.assign(4, 0x80000000u);
+            const float inf = std::numeric_limits<float>::infinity();
+            S.sub_pen.assign(32 * 128, inf);
+            for (size_t k = 0; k < chars.size(); k++)
+                for (uint32_t b = 0; b < 128; b++) {
+                    const float sm = chars[k] == b ? 1.0f : A.sim_ascii[chars[k] * 128 + b];  // get_similarity, search.rs:76-82
+                    if (sm < A.min_sym) continue;                                              // search.rs:822-825
+                    volatile float one_minus = 1.0f - sm;
+                    volatile float pp = A.pen_sub * one_minus;                                 // search.rs:829
+                    S.sub_pen[k * 128 + b] = pp;
+                }
+            S.first_mask = S.bm[0];
+            for (uint32_t c = 0; c < (uint32_t)FAC_POPC_HOST(S.bm[0]); c++) S.second_mask |= S.bm[(S.fc_sym[0] & SUCC_FC_MASK) + c];
+            S.first_mask |= S.second_mask;
+            S.ok = true;
+        }
     }
 
     // ---- max_match_graphemes (src/stream.rs:213-253) ----

@@ -56,6 +56,21 @@ struct HostBitap {
     std::vector<uint64_t> masks;           // [P * (alphabet+1)]
 };
 
+// Succinct BFS-ordered trie for the fast expansion kernel (fac_succinct.h).  `ok` is false when the
+// engine is outside that kernel's domain (mappings, per-type limits, multi-byte edges, > 31 symbols).
+struct HostSuccinct {
+    bool ok = false;
+    uint32_t n_syms = 0;
+    uint8_t sym_of[256];                 // folded text byte -> dense symbol, 31 = not in the alphabet
+    std::vector<uint32_t> bm, fc_sym;    // [N] child bitmap; first_child | in-symbol << 27
+    std::vector<float> prune_len, prune_low;  // [N] in BFS numbering
+    std::vector<uint32_t> out_idx;       // [N] first entry in out2 or FAC_NONE
+    std::vector<uint32_t> out2;          // 4 words per entry: pat | last << 31, glen f32 bits, weight f32 bits, 0
+    std::vector<float> sub_pen;          // [32 * 128] pen_sub * (1 - sim(edge char, text byte)), +inf below min_symbol_similarity
+    std::vector<uint32_t> old_of;        // [N] reference node index of BFS node i
+    uint32_t first_mask = 0, second_mask = 0;  // 2-gram window skip (search.rs:504-521) in symbol space
+};
+
 struct HostAutomaton {
     // flattened arrays, exactly the members of AutomatonView
     std::vector<uint32_t> node_edge_off, node_out_off, node_bitmap, node_lim, node_map_off;
@@ -89,6 +104,7 @@ struct HostAutomaton {
     uint32_t max_map_hay = 1;
     std::vector<HostPattern> patterns;
     HostBitap bitap;
+    HostSuccinct succ;
 
     uint32_t n_nodes() const { return (uint32_t)node_prune_len.size(); }
     // View over the host vectors (used by the CPU-side emulator in tests).

@@ -1,0 +1,170 @@
+// fac_succinct.h -- per-state logic of the succinct-trie expansion (K3 fast kernel), shared by the
+// CUDA kernel (fac_succinct.cuh) and the CPU-side emulator the tests use.
+//
+// Applies to engines the reference dispatches to its fast monomorphisations
+// `search_unsorted_impl<MAPPINGS=false, _, MAX_EDITS_FAST=1..6>` (src/search.rs:204-393) when, in
+// addition, every trie edge is one ASCII byte and the pattern alphabet has at most 31 symbols.
+//
+// Layout.  Nodes are renumbered in BFS order with the children of a node contiguous and sorted by
+// symbol, so the whole node is one 16-byte record
+//     x = child bitmap over the dense symbol alphabet (bit 31 never set)
+//     y = first_child | (symbol of the edge that leads INTO this node) << 27
+//     z = f32 bits of the node ceiling  prune_len - prune_len_over_weight * threshold  (search.rs:638-642)
+//     w = index of the node's first output entry, or FAC_NONE
+// and  child(n, sym) = first_child + popc(x & below(sym)).  There is no edge array and no hash
+// table: the exact transition (Node::find_transition_char_no_mappings, src/structs.rs:512-519) is a
+// bit test + popcount, and the last-edit dead-end filter (search.rs:839-847, 1005-1007, 1057-1063:
+// "child has an output or a single-byte edge equal to the next text char") reads only the child's
+// record.
+//
+// The expansion is order-independent: candidates are reduced by maximum similarity and ties
+// between different edit-count vectors are detected and redone by the order-faithful kernel
+// (fac_fastreduce.cuh), so the reference's FIFO order does not have to be kept here.  The dedup
+// map (search.rs:608-628) is result-neutral and is not applied.
+#pragma once
+#include "fac_core.h"
+#include "fac_types.h"
+
+#define SUCC_FC_MASK 0x07FFFFFFu
+#define SUCC_NOSYM 31u
+#define SUCC_MAX_NODES 0x07FFFFFFu
+
+#if defined(__CUDA_ARCH__)
+#define FAC_POPC(x) __popc(x)
+#define FAC_AS_FLOAT(u) __uint_as_float(u)
+#else
+#define FAC_POPC(x) ((uint32_t)__builtin_popcount(x))
+static inline float fac_as_float_host(uint32_t u) { union { uint32_t u; float f; } v; v.u = u; return v.f; }
+#define FAC_AS_FLOAT(u) fac_as_float_host(u)
+#endif
+
+struct SuccRec { uint32_t x, y, z, w; };   // same bytes as uint4
+struct SuccOut { uint32_t pat_last; uint32_t glen_bits; uint32_t weight_bits; uint32_t pad; };  // pat | last<<31
+
+struct SuccConsts {
+    float thr, maxpen, pen_ins, pen_del, pen_swap;
+    int32_t mef;
+};
+
+FAC_HD uint32_t succ_child(const SuccRec &r, uint32_t sym) { return (r.y & SUCC_FC_MASK) + FAC_POPC(r.x & ((1u << sym) - 1u)); }
+FAC_HD bool succ_has_edge(const SuccRec &r, uint32_t sym) { return (r.x >> sym) & 1u; }
+FAC_HD uint32_t succ_make_pos(uint32_t jr, uint32_t mr) { return (jr << 10) | mr; }
+
+// Outputs of one node visit (search.rs:659-737): fast-path limit check is `edits > MAX_EDITS_FAST`,
+// never true here because no state exceeds the budget.
+template <class Emit>
+FAC_HD void succ_outputs(const SuccConsts &K, const SuccOut *out2, Emit &emit, uint32_t idx, float pen, uint32_t cnt, uint32_t sg, uint32_t eg) {
+    for (;;) {
+        const SuccOut o = out2[idx++];
+        const float total = FAC_AS_FLOAT(o.glen_bits);
+        const float sim = FAC_MUL(FAC_DIV(FAC_SUB(total, pen), total), FAC_AS_FLOAT(o.weight_bits));  // search.rs:698-699
+        if (!(sim < K.thr)) emit(sg, eg, o.pat_last & 0x7FFFFFFFu, sim, cnt);
+        if (o.pat_last >> 31) break;
+    }
+}
+
+// A state that has spent its whole edit budget follows exact transitions only (sub / swap / ins /
+// del all need edits < MAX_EDITS_FAST, search.rs:810, 937, 1003, 1043): walk the chain with the
+// per-pop checks (ceiling :638-642, outputs :659-737, exact :776-798).  Returns the nodes visited.
+template <class Recs, class Text, class Emit>
+FAC_HD uint32_t succ_walk(const SuccConsts &K, const Recs &R, const SuccOut *out2, const Text &T, Emit &emit, uint32_t start, uint32_t text_end,
+                          SuccRec rec, float pen, uint32_t cnt, uint32_t jr, uint32_t mr) {
+    uint32_t steps = 0;
+    for (;;) {
+        steps++;
+        if (pen > FAC_AS_FLOAT(rec.z)) break;
+        if (rec.w != FAC_NONE) succ_outputs(K, out2, emit, rec.w, pen, cnt, start, start + mr);
+        const uint32_t j = start + jr;
+        if (j >= text_end) break;
+        const uint32_t s = T.sym(j);
+        if (!succ_has_edge(rec, s)) break;
+        rec = R(succ_child(rec, s));
+        jr++; mr = jr;
+    }
+    return steps;
+}
+
+// What the edge-independent part of a popped state needs (search.rs:742-770, 994-1008, 1035-1045).
+enum : uint32_t { SUCC_F_IN_TEXT = 1u, SUCC_F_LAST = 2u, SUCC_F_DEL = 4u, SUCC_F_HAS_NXT = 8u };
+struct SuccCtx {
+    uint32_t fc;       // rec.y (first child | in-symbol)
+    float pen;
+    uint32_t cnt, pos;
+    uint32_t packed;   // cur byte | cur sym << 8 | next sym << 16 | exact child rank << 24 (0xFF = none)
+    uint32_t flags;
+};
+
+template <class Text>
+FAC_HD void succ_make_ctx(const SuccConsts &K, const Text &T, uint32_t start, uint32_t text_end, const SuccRec &rec, float pen, uint32_t cnt,
+                          uint32_t pos, SuccCtx &C) {
+    const uint32_t jr = pos >> 10;
+    const uint32_t j = start + jr;
+    const int edits = (int)fac_edits_of(cnt);
+    const bool last = edits + 1 >= K.mef;
+    const bool in_text = j < text_end;
+    uint32_t cur_b = 0, cur_s = SUCC_NOSYM, nxt_s = SUCC_NOSYM, ex = 0xFFu, flags = 0;
+    if (last) flags |= SUCC_F_LAST;
+    if (in_text) {
+        flags |= SUCC_F_IN_TEXT;
+        cur_b = T.byte(j); cur_s = T.sym(j);
+        if (j + 1 < text_end) { nxt_s = T.sym(j + 1); flags |= SUCC_F_HAS_NXT; }
+        if (succ_has_edge(rec, cur_s)) ex = FAC_POPC(rec.x & ((1u << cur_s) - 1u));
+    }
+    if (K.pen_del <= FAC_SUB(K.maxpen, pen)) flags |= SUCC_F_DEL;  // search.rs:1035 (edits < MEF holds for every popped state)
+    C.fc = rec.y; C.pen = pen; C.cnt = cnt; C.pos = pos;
+    C.packed = cur_b | (cur_s << 8) | (nxt_s << 16) | (ex << 24);
+    C.flags = flags;
+}
+
+// Swap (search.rs:935-989): node -text[j+1]-> x -text[j]-> n2; matched_start unchanged.
+template <class Recs>
+FAC_HD bool succ_swap(const SuccConsts &K, const Recs &R, const SuccRec &rec, const SuccCtx &C, SuccRec &rec2, FacState &out) {
+    if ((C.flags & (SUCC_F_IN_TEXT | SUCC_F_HAS_NXT)) != (SUCC_F_IN_TEXT | SUCC_F_HAS_NXT)) return false;
+    if (!(K.pen_swap <= FAC_SUB(K.maxpen, C.pen))) return false;
+    const uint32_t cur_s = (C.packed >> 8) & 0xFFu, nxt_s = (C.packed >> 16) & 0xFFu;
+    if (!succ_has_edge(rec, nxt_s)) return false;
+    const SuccRec rx = R(succ_child(rec, nxt_s));
+    if (!succ_has_edge(rx, cur_s)) return false;
+    const uint32_t n2 = succ_child(rx, cur_s);
+    rec2 = R(n2);
+    const uint32_t jr = C.pos >> 10;
+    out.node = n2; out.pen = FAC_ADD(C.pen, K.pen_swap); out.cnt = C.cnt + 0x1000000u; out.pos = succ_make_pos(jr + 2, jr + 2);
+    return true;
+}
+
+// Insertion (search.rs:994-1029): forbidden before anything is consumed; matched_end unchanged.
+FAC_HD bool succ_ins(const SuccConsts &K, const SuccRec &rec, const SuccCtx &C, uint32_t node, FacState &out) {
+    if (!(C.flags & SUCC_F_IN_TEXT)) return false;
+    const uint32_t jr = C.pos >> 10, mr = C.pos & 1023u;
+    if (mr == 0 && jr == 0) return false;
+    if (!(K.pen_ins <= FAC_SUB(K.maxpen, C.pen))) return false;
+    if ((C.flags & SUCC_F_LAST) && rec.w == FAC_NONE) {  // dead-end filter on the current node
+        if (!(C.flags & SUCC_F_HAS_NXT) || !succ_has_edge(rec, (C.packed >> 16) & 0xFFu)) return false;
+    }
+    out.node = node; out.pen = FAC_ADD(C.pen, K.pen_ins); out.cnt = C.cnt + 1u; out.pos = succ_make_pos(jr + 1, mr);
+    return true;
+}
+
+// Substitution through child rank k (search.rs:814-874).  `crec` is the child's record.
+FAC_HD bool succ_sub(const SuccConsts &K, const float *sub_pen, const SuccCtx &C, uint32_t k, const SuccRec &crec, FacState &out) {
+    if (!(C.flags & SUCC_F_IN_TEXT)) return false;
+    if (k == (C.packed >> 24)) return false;  // the exact edge
+    const float pp = sub_pen[(crec.y >> 27) * 128u + (C.packed & 0x7Fu)];  // +inf when similarity < min_symbol_similarity
+    if (pp > FAC_SUB(K.maxpen, C.pen)) return false;
+    if (C.flags & SUCC_F_LAST) {
+        if (crec.w == FAC_NONE && (!(C.flags & SUCC_F_HAS_NXT) || !succ_has_edge(crec, (C.packed >> 16) & 0xFFu))) return false;
+    }
+    const uint32_t jr = C.pos >> 10;
+    out.node = (C.fc & SUCC_FC_MASK) + k; out.pen = FAC_ADD(C.pen, pp); out.cnt = C.cnt + 0x10000u; out.pos = succ_make_pos(jr + 1, jr + 1);
+    return true;
+}
+
+// Deletion through child rank k (search.rs:1035-1089); allowed at j == text_end.
+FAC_HD bool succ_del(const SuccConsts &K, const SuccCtx &C, uint32_t k, const SuccRec &crec, FacState &out) {
+    if (!(C.flags & SUCC_F_DEL)) return false;
+    if (C.flags & SUCC_F_LAST) {
+        if (crec.w == FAC_NONE && (!(C.flags & SUCC_F_IN_TEXT) || !succ_has_edge(crec, (C.packed >> 8) & 0xFFu))) return false;
+    }
+    out.node = (C.fc & SUCC_FC_MASK) + k; out.pen = FAC_ADD(C.pen, K.pen_del); out.cnt = C.cnt + 0x100u; out.pos = C.pos;
+    return true;
+}

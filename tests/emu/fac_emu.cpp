@@ -15,6 +15,7 @@
 
 #include "../../fuzzy-aho-corasick-rs_b200/csrc/fac_builder.h"
 #include "../../fuzzy-aho-corasick-rs_b200/csrc/fac_core.h"
+#include "../../fuzzy-aho-corasick-rs_b200/csrc/fac_succinct.h"
 #include "../../fuzzy-aho-corasick-rs_b200/csrc/fac_unicode.h"
 
 using namespace fac;
@@ -168,6 +169,122 @@ int emu_search(const fac_config *cfg, const fac_pattern *pats, size_t np, const 
     *out = (fac_match *)malloc(sizeof(fac_match) * (res.size() ? res.size() : 1));
     if (!res.empty()) memcpy(*out, res.data(), sizeof(fac_match) * res.size());
     if (states_out) *states_out = states;
+    return 0;
+}
+
+// ---- succinct-trie fast path (csrc/fac_succinct.h) run sequentially: same per-state helpers as the
+// kernel, a plain LIFO stack instead of the warp stack machine, the order-independent reduction with
+// tie detection, and the faithful emulation above for tied ("dirty") windows. ----
+struct EmuRecs { const SuccRec *r; SuccRec operator()(uint32_t n) const { return r[n]; } };
+struct EmuSText {
+    const uint8_t *b; const uint8_t *symof; bool ci;
+    uint32_t byte(uint32_t j) const { const uint32_t c = b[j]; return (ci && c >= 'A' && c <= 'Z') ? c + 32u : c; }
+    uint32_t sym(uint32_t j) const { return symof[byte(j)]; }
+};
+struct EmuEmit {
+    std::vector<FacCand> *v;
+    void operator()(uint32_t sg, uint32_t eg, uint32_t pat, float sim, uint32_t cnt) { v->push_back(FacCand{sg, eg, pat, sim, cnt, 0, 0, 0}); }
+};
+
+// returns 0 ok, -3 engine/haystack outside the fast kernel's domain.  info[0] = dirty windows, info[1] = states visited
+int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t np, const uint8_t *hay, size_t len, float thr,
+                        fac_match **out, size_t *n_out, uint64_t *info) {
+    HostAutomaton HA; std::string err;
+    fac_status st = build_automaton(cfg, pats, np, HA, err);
+    if (st != FAC_OK) return (int)st;
+    const HostSuccinct &S = HA.succ;
+    for (size_t i = 0; i < len; i++) if (hay[i] >= 0x80) return -3;
+    if (!S.ok || HA.beam_width != 0 || HA.has_auto_beam) return -3;
+    const uint32_t N = (uint32_t)S.bm.size(), n = (uint32_t)len, text_end = n;
+    std::vector<SuccRec> recs(N);
+    for (uint32_t i = 0; i < N; i++) {
+        union { float f; uint32_t u; } c;
+        c.f = FAC_SUB(S.prune_len[i], FAC_MUL(S.prune_low[i], thr));
+        recs[i] = SuccRec{S.bm[i], S.fc_sym[i], c.u, S.out_idx[i]};
+    }
+    SuccConsts K;
+    K.thr = thr; K.maxpen = FAC_AS_FLOAT(recs[0].z); K.pen_ins = HA.pen_ins; K.pen_del = HA.pen_del; K.pen_swap = HA.pen_swap; K.mef = HA.mef;
+    const EmuRecs R{recs.data()};
+    const EmuSText T{hay, S.sym_of, HA.ci};
+    const SuccOut *out2 = (const SuccOut *)S.out2.data();
+    std::vector<FacCand> cands;
+    EmuEmit emit{&cands};
+    uint64_t states = 0;
+    for (uint32_t start = 0; start < n; start++) {
+        if (HA.wskip) {
+            if (!((S.first_mask >> T.sym(start)) & 1u)) {
+                if (start + 1 >= n) continue;
+                if (!((S.second_mask >> T.sym(start + 1)) & 1u)) continue;
+            }
+        }
+        std::vector<FacState> stack;
+        stack.push_back(FacState{0, 0.f, 0, 0});
+        while (!stack.empty()) {
+            const FacState s = stack.back();
+            stack.pop_back();
+            states++;
+            const SuccRec rec = R(s.node);
+            if (s.pen > FAC_AS_FLOAT(rec.z)) continue;
+            if (rec.w != FAC_NONE) succ_outputs(K, out2, emit, rec.w, s.pen, s.cnt, start, start + (s.pos & 1023u));
+            SuccCtx C;
+            succ_make_ctx(K, T, start, text_end, rec, s.pen, s.cnt, s.pos, C);
+            const bool last = (C.flags & SUCC_F_LAST) != 0;
+            const uint32_t jr = s.pos >> 10;
+            auto child = [&](const FacState &c, const SuccRec &crec) {
+                if (last) states += succ_walk(K, R, out2, T, emit, start, text_end, crec, c.pen, c.cnt, c.pos >> 10, c.pos & 1023u);
+                else stack.push_back(c);
+            };
+            if ((C.packed >> 24) != 0xFFu) stack.push_back(FacState{(rec.y & SUCC_FC_MASK) + (C.packed >> 24), s.pen, s.cnt, succ_make_pos(jr + 1, jr + 1)});
+            FacState c; SuccRec r2;
+            if (succ_swap(K, R, rec, C, r2, c)) child(c, r2);
+            if (succ_ins(K, rec, C, s.node, c)) child(c, rec);
+            const uint32_t deg = FAC_POPC(rec.x);
+            for (uint32_t k = 0; k < deg; k++) {
+                const SuccRec crec = R((rec.y & SUCC_FC_MASK) + k);
+                if (succ_sub(K, S.sub_pen.data(), C, k, crec, c)) child(c, crec);
+                if (succ_del(K, C, k, crec, c)) child(c, crec);
+            }
+        }
+    }
+    typedef std::tuple<uint32_t, uint32_t, uint32_t> Key;
+    struct Best { float sim; uint32_t cmin, cmax; };
+    std::map<Key, Best> best;
+    for (const FacCand &c : cands) {
+        const Key k(c.sg, c.eg, c.pat);
+        auto it = best.find(k);
+        if (it == best.end()) best.emplace(k, Best{c.sim, c.cnt, c.cnt});
+        else if (c.sim > it->second.sim) it->second = Best{c.sim, c.cnt, c.cnt};
+        else if (c.sim == it->second.sim) { it->second.cmin = std::min(it->second.cmin, c.cnt); it->second.cmax = std::max(it->second.cmax, c.cnt); }
+    }
+    std::vector<uint8_t> dirty(n + 1, 0);
+    uint64_t n_dirty = 0;
+    for (auto &kv : best) if (kv.second.cmin != kv.second.cmax && !dirty[std::get<0>(kv.first)]) { dirty[std::get<0>(kv.first)] = 1; n_dirty++; }
+    std::vector<fac_match> res;
+    for (auto &kv : best) {
+        if (dirty[std::get<0>(kv.first)]) continue;
+        fac_match m; memset(&m, 0, sizeof(m));
+        const uint32_t cnt = kv.second.cmin;
+        m.start = std::get<0>(kv.first); m.end = std::get<1>(kv.first); m.pattern_index = std::get<2>(kv.first); m.similarity = kv.second.sim;
+        m.insertions = cnt & 0xFF; m.deletions = (cnt >> 8) & 0xFF; m.substitutions = (cnt >> 16) & 0xFF; m.swaps = cnt >> 24;
+        m.edits = (uint8_t)fac_edits_of(cnt);
+        res.push_back(m);
+    }
+    if (n_dirty) {
+        fac_match *fm = nullptr; size_t fn = 0; uint64_t fs = 0;
+        const int rc = emu_search(cfg, pats, np, hay, len, thr, 16, &fm, &fn, &fs, nullptr);
+        if (rc != 0) return rc;
+        for (size_t i = 0; i < fn; i++) if (dirty[fm[i].start]) res.push_back(fm[i]);
+        free(fm);
+    }
+    std::sort(res.begin(), res.end(), [](const fac_match &a, const fac_match &b) {
+        if (a.start != b.start) return a.start < b.start;
+        if (a.end != b.end) return a.end < b.end;
+        return a.pattern_index < b.pattern_index;
+    });
+    *n_out = res.size();
+    *out = (fac_match *)malloc(sizeof(fac_match) * (res.size() ? res.size() : 1));
+    if (!res.empty()) memcpy(*out, res.data(), sizeof(fac_match) * res.size());
+    if (info) { info[0] = n_dirty; info[1] = states; }
     return 0;
 }
 

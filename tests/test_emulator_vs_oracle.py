@@ -44,3 +44,34 @@ def test_emu_tile_size_independent(oracle):
         b, _, _, _ = rand_case(random.Random(seed), e2, t % 2 == 1)
         o = SearchOptions.new().threshold(thr)
         assert a.search(hay, o).tuples() == b.search(hay, o).tuples(), desc
+
+
+def test_succinct_fast_path_matches_oracle(oracle):
+    """The succinct-trie formulation of the fast kernel (csrc/fac_succinct.h): order-independent
+    enumeration + tie detection + faithful redo must equal the oracle wherever it applies."""
+    emu = EmuBackend(tile=16)
+    emu.succinct = True
+    r1, r2 = random.Random(31), random.Random(31)
+    for t in range(2500):
+        eo, hay, thr, desc = rand_case(r1, oracle, False)
+        ee, _, _, _ = rand_case(r2, emu, False)
+        o = eo.search(hay, SearchOptions.new().threshold(thr))
+        e = ee.search(hay, SearchOptions.new().threshold(thr))
+        assert o.tuples() == e.tuples(), (t, desc)
+    assert emu.succinct_used > 300, emu.succinct_used
+
+
+def test_succinct_ties(oracle):
+    emu = EmuBackend(tile=16)
+    emu.succinct = True
+    r = random.Random(99)
+    from fac_b200 import FuzzyAhoCorasickBuilder, FuzzyLimits
+    for t in range(400):
+        pats = ["".join(r.choice("ab") for _ in range(r.randrange(3, 7))) for _ in range(r.randrange(1, 5))]
+        hay = "".join(r.choice("ab ") for _ in range(r.randrange(0, 50)))
+        edits = r.choice([1, 2, 2, 3])
+        mk = lambda b: FuzzyAhoCorasickBuilder.new(b).fuzzy(FuzzyLimits.new().edits(edits)).build(pats)
+        o = mk(oracle).search(hay, SearchOptions.new().threshold(0.3))
+        e = mk(emu).search(hay, SearchOptions.new().threshold(0.3))
+        assert o.tuples() == e.tuples(), (t, pats, hay, edits)
+    assert emu.succinct_dirty > 0
