@@ -138,7 +138,8 @@ struct fac_engine {
     const uint32_t *d_s_bm = nullptr, *d_s_fc = nullptr, *d_s_out_idx = nullptr, *d_s_out2 = nullptr;
     const float *d_s_plen = nullptr, *d_s_plow = nullptr, *d_s_subpen = nullptr;
     const uint8_t *d_s_symof = nullptr;
-    uint32_t succ_nt = 768, succ_tile = 1024, succ_stack = 0;
+    const uint32_t *d_s_gm = nullptr;
+    uint32_t succ_nt = 1024, succ_tile = 1024, succ_stack = 0;
     int smem_optin = 0;
     bool fast_ok = false;  // FAST kernel allowed (fast-path edit ceiling, no beam); FAC_FAITHFUL=1 forces the order-faithful kernel
     mutable std::mutex mu;
@@ -235,7 +236,8 @@ fac_status launch_succinct(const fac_engine *E, Workspace *ws, const uint8_t *d_
     const uint32_t nw = E->succ_nt / 32;
     P.stack_cap = E->succ_stack ? E->succ_stack : (E->host.mef <= 2 ? 128u : 384u);
     P.text_cap = (P.tile + P.lookahead + 16u + 15u) & ~15u;
-    const size_t fixed = (size_t)nw * P.stack_cap * 16 + 32 * 128 * 4 + (size_t)P.text_cap * 3 + 256;
+    P.gm = E->d_s_gm; P.gm_nodes = S.gm_nodes;
+    const size_t fixed = (size_t)nw * (P.stack_cap + SUCC_WQ_CAP) * 16 + 32 * 128 * 4 + (size_t)P.text_cap * 3 + 256;
     const size_t budget = (size_t)E->smem_optin - 1024;  // static shared + reserve
     if (fixed + 16 * 64 > budget) { set_err("succinct kernel: shared-memory budget too small for the configured stack / tile"); return FAC_UNSUPPORTED; }
     P.n_smem_nodes = (uint32_t)std::min<size_t>(N, (budget - fixed) / 16);
@@ -928,6 +930,7 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
         if ((st = upload(E, S.prune_low, &E->d_s_plow)) != FAC_OK) return fail(st);
         if ((st = upload(E, S.sub_pen, &E->d_s_subpen)) != FAC_OK) return fail(st);
         if ((st = upload(E, symof, &E->d_s_symof)) != FAC_OK) return fail(st);
+        if ((st = upload(E, S.gmask, &E->d_s_gm)) != FAC_OK) return fail(st);
     }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -941,7 +944,7 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
     E->use_tma = env_int("FAC_USE_TMA", 1);
     E->fast_ok = H.mef != 255 && H.beam_width == 0 && !H.has_auto_beam && env_int("FAC_FAITHFUL", 0) == 0;
     E->succ_ok = E->fast_ok && H.succ.ok && env_int("FAC_SUCCINCT", 1) != 0;
-    E->succ_nt = (uint32_t)env_int("FAC_SUCC_THREADS", 768);
+    E->succ_nt = (uint32_t)env_int("FAC_SUCC_THREADS", 1024);
     E->succ_tile = (uint32_t)std::max(32, env_int("FAC_SUCC_TILE", 1024));
     E->succ_stack = (uint32_t)env_int("FAC_SUCC_STACK", 0);
     *out = E;

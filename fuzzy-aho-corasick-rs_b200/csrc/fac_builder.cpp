@@ -2,6 +2,7 @@
 #include "fac_builder.h"
 #include "fac_succinct.h"
 #include <limits>
+#include <cstdlib>
 #define FAC_POPC_HOST(x) __builtin_popcount(x)
 #include "fac_core.h"
 
@@ -509,6 +510,23 @@ fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_
             S.first_mask = S.bm[0];
             for (uint32_t c = 0; c < (uint32_t)FAC_POPC_HOST(S.bm[0]); c++) S.second_mask |= S.bm[(S.fc_sym[0] & SUCC_FC_MASK) + c];
             S.first_mask |= S.second_mask;
+            {   // grandchild masks: gm[n][y] = symbols s with child(n, s) having edge y; gm[n][31] = children with an output
+                const char *ev = getenv("FAC_GM_NODES");
+                const size_t lim = ev && *ev ? (size_t)atoll(ev) : 65536;
+                S.gm_nodes = (uint32_t)std::min<size_t>(N, lim);
+                S.gmask.assign((size_t)std::max<uint32_t>(S.gm_nodes, 1) * 32, 0);
+                for (uint32_t h = 0; h < S.gm_nodes; h++) {
+                    uint32_t bmv = S.bm[h], k = 0;
+                    while (bmv) {
+                        const uint32_t sy = (uint32_t)__builtin_ctz(bmv);
+                        bmv &= bmv - 1;
+                        const uint32_t c = (S.fc_sym[h] & SUCC_FC_MASK) + k++;
+                        uint32_t cb = S.bm[c];
+                        while (cb) { S.gmask[(size_t)h * 32 + (uint32_t)__builtin_ctz(cb)] |= 1u << sy; cb &= cb - 1; }
+                        if (S.out_idx[c] != FAC_NONE) S.gmask[(size_t)h * 32 + 31] |= 1u << sy;
+                    }
+                }
+            }
             S.ok = true;
         }
     }

@@ -69,6 +69,9 @@ struct HostSuccinct {
     std::vector<float> sub_pen;          // [32 * 128] pen_sub * (1 - sim(edge char, text byte)), +inf below min_symbol_similarity
     std::vector<uint32_t> old_of;        // [N] reference node index of BFS node i
     uint32_t first_mask = 0, second_mask = 0;  // 2-gram window skip (search.rs:504-521) in symbol space
+    // grandchild masks of the first gm_nodes BFS nodes (fac_succinct.h): [gm_nodes * 32]
+    std::vector<uint32_t> gmask;
+    uint32_t gm_nodes = 0;
 };
 
 struct HostAutomaton {

@@ -11,9 +11,12 @@
 //     land) copied to shared memory once per CTA; deeper records come through L1/L2 as 128-bit loads;
 //   * each warp owns one start window at a time and runs a depth-first stack machine in shared
 //     memory: pop <= 32 states (one per lane), push exact/swap/insertion children by ballot/popc
-//     compaction, flatten the (state, child edge) pairs of the popped states with a warp prefix sum
-//     and evaluate substitution + deletion through 32 edges per round; children that exhausted the
-//     edit budget are walked in place (exact transitions only).
+//     compaction; the children that survive the last-edit dead-end filter are read off the
+//     precomputed grandchild masks (two 4-byte loads per state instead of one record per child),
+//     flattened over the warp with a prefix sum and turned into child states 32 per round;
+//   * children that exhausted the edit budget can only follow exact transitions: they are queued in
+//     a per-warp shared-memory walk queue and walked 32 at a time, so the divergent chain walk runs
+//     with (nearly) full warps.
 //
 // No global-memory frontier: DRAM traffic is the haystack once plus the emitted candidates.
 #pragma once
@@ -34,6 +37,8 @@ struct SuccParams {
     int32_t ci, wskip;
     uint32_t first_mask, second_mask;
     uint32_t seg_begin, seg_end, text_end, tile, n_tiles, lookahead;
+    const uint32_t *gm;      // [gm_nodes * 32] grandchild masks (fac_succinct.h)
+    uint32_t gm_nodes;
     uint32_t stack_cap;      // states per warp stack
     uint32_t text_cap;       // bytes of the shared text tile (multiple of 16)
     FacCand *cands;
@@ -59,6 +64,24 @@ struct SuccRecsDev {
         const uint4 v = n < ns ? s[n] : __ldg(&g[n]);
         SuccRec r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
         return r;
+    }
+};
+struct SuccGMDev {
+    const uint32_t *gm;
+    uint32_t gm_nodes;
+    SuccRecsDev R;
+    __device__ __forceinline__ uint32_t operator()(uint32_t node, uint32_t y) const {
+        if (node < gm_nodes) return __ldg(&gm[(size_t)node * 32u + y]);
+        // beyond the table: recompute the row entry from the children's records
+        const SuccRec r = R(node);
+        uint32_t bmv = r.x, k = 0, m = 0;
+        while (bmv) {
+            const uint32_t sy = __ffs(bmv) - 1u;
+            bmv &= bmv - 1u;
+            const SuccRec c = R((r.y & SUCC_FC_MASK) + k++);
+            if (y == SUCC_NOSYM ? c.w != FAC_NONE : ((c.x >> y) & 1u)) m |= 1u << sy;
+        }
+        return m;
     }
 };
 struct SuccTextDev {
@@ -89,6 +112,8 @@ __device__ __forceinline__ void succ_warp_push(uint4 *stk, uint32_t &top, bool p
     top += __popc(bal);
 }
 
+#define SUCC_WQ_CAP 96u
+
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant__ SuccParams P) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
@@ -97,10 +122,11 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
     constexpr int NW = NT / 32;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
-    // carve-up: [node records][warp stacks][sub_pen][raw tile][folded bytes][symbols][sym_of]
+    // carve-up: [node records][warp stacks][walk queues][sub_pen][raw tile][folded bytes][symbols][sym_of]
     uint4 *s_rec = reinterpret_cast<uint4 *>(dyn_smem);
     uint4 *s_stack = s_rec + P.n_smem_nodes;
-    float *s_subpen = reinterpret_cast<float *>(s_stack + (size_t)NW * P.stack_cap);
+    uint4 *s_wq = s_stack + (size_t)NW * P.stack_cap;
+    float *s_subpen = reinterpret_cast<float *>(s_wq + (size_t)NW * SUCC_WQ_CAP);
     uint8_t *s_raw = reinterpret_cast<uint8_t *>(s_subpen + 32 * 128);
     uint8_t *s_byte = s_raw + P.text_cap;
     uint8_t *s_sym = s_byte + P.text_cap;
@@ -114,9 +140,11 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
 
     const SuccConsts K = P.K;
     const SuccRecsDev R{s_rec, P.rec, P.n_smem_nodes};
+    const SuccGMDev G{P.gm, P.gm_nodes, R};
     const SuccOut *out2 = reinterpret_cast<const SuccOut *>(P.out2);
     SuccEmitDev emit{P.cands, P.cand_cap, &P.counters[1]};
     uint4 *const stk = s_stack + (size_t)warp * P.stack_cap;
+    uint4 *const wq = s_wq + (size_t)warp * SUCC_WQ_CAP;
     const uint32_t cap = P.stack_cap;
     uint32_t mbar_phase = 0;
     uint32_t n_states = 0;  // per-lane count of visited states (summed at the end)
@@ -171,10 +199,57 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                     if (!((P.second_mask >> T.sym(start + 1)) & 1u)) continue;
                 }
             }
-            uint32_t top = 1;
+            uint32_t top = 1, wn = 0;      // stack height, walk-queue length (warp-uniform)
+            uint32_t b0 = 0, total = 0;    // item rounds of the current pop
+            uint32_t off = 0;              // exclusive prefix of the lanes' item counts
+            SuccCtx2 C;
+            C.bm = C.fc = C.cnt = C.pos = C.packed = C.flags = C.sub_m = C.del_m = 0; C.pen = 0.f;
             if (lane == 0) stk[0] = make_uint4(0u, 0u, 0u, 0u);
-            while (top) {
+            for (;;) {
                 __syncwarp();
+                // (1) exhausted children: exact transitions only, walked 32 at a time
+                if (wn >= 32u || (wn && b0 >= total && top == 0)) {
+                    const uint32_t n = min(wn, 32u);
+                    if (lane < n) {
+                        const uint4 q = wq[wn - n + lane];
+                        n_states += succ_walk(K, R, out2, T, emit, start, text_end, R(q.x), __uint_as_float(q.y), q.z, q.w >> 10, q.w & 1023u);
+                    }
+                    wn -= n;
+                    continue;
+                }
+                // (2) surviving (state, child) pairs of the last pop, 32 per round
+                if (b0 < total) {
+                    const uint32_t it = b0 + lane;
+                    b0 += 32u;
+                    uint32_t lo = 0;
+#pragma unroll
+                    for (int step = 16; step; step >>= 1) {
+                        const uint32_t cand = lo + step;
+                        const uint32_t v = __shfl_sync(0xFFFFFFFFu, off, cand & 31u);
+                        if (cand < 32u && v <= it) lo = cand;
+                    }
+                    SuccCtx2 O;
+                    O.bm = __shfl_sync(0xFFFFFFFFu, C.bm, lo);
+                    O.fc = __shfl_sync(0xFFFFFFFFu, C.fc, lo);
+                    O.pen = __shfl_sync(0xFFFFFFFFu, C.pen, lo);
+                    O.cnt = __shfl_sync(0xFFFFFFFFu, C.cnt, lo);
+                    O.pos = __shfl_sync(0xFFFFFFFFu, C.pos, lo);
+                    O.packed = __shfl_sync(0xFFFFFFFFu, C.packed, lo);
+                    O.flags = __shfl_sync(0xFFFFFFFFu, C.flags, lo);
+                    O.sub_m = __shfl_sync(0xFFFFFFFFu, C.sub_m, lo);
+                    O.del_m = __shfl_sync(0xFFFFFFFFu, C.del_m, lo);
+                    const uint32_t r = it - __shfl_sync(0xFFFFFFFFu, off, lo);
+                    FacState c;
+                    c.node = 0; c.pen = 0.f; c.cnt = 0; c.pos = 0;
+                    const bool ok = it < total && succ_item2(K, s_subpen, O, r, c);
+                    const bool to_walk = ok && (O.flags & SUCC_F_LAST);
+                    const bool to_stack = ok && !(O.flags & SUCC_F_LAST);
+                    if (__any_sync(0xFFFFFFFFu, to_walk)) succ_warp_push(wq, wn, to_walk, c);
+                    if (__any_sync(0xFFFFFFFFu, to_stack)) succ_warp_push(stk, top, to_stack, c);
+                    continue;
+                }
+                if (top == 0) break;
+                // (3) pop up to 32 states
                 const uint32_t navail = min(top, 32u);
                 const bool has = lane < navail;
                 uint4 sv = make_uint4(0, 0, 0, 0);
@@ -183,9 +258,8 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                 const float pen = __uint_as_float(sv.y);
                 const bool dead = !has || pen > __uint_as_float(rec.z);   // node ceiling, search.rs:638-642
                 const bool last = (int)fac_edits_of(sv.z) + 1 >= K.mef;
-                const uint32_t deg = __popc(rec.x);
-                // worst-case pushes of this state: exact only when its edit-children are exhausted
-                const uint32_t ub = dead ? 0u : (last ? 1u : 2u * deg + 3u);
+                // worst-case stack pushes of this state: only the exact child when its edit-children are exhausted
+                const uint32_t ub = dead ? 0u : (last ? 1u : 2u * (uint32_t)__popc(rec.x) + 3u);
                 uint32_t incl = ub;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -205,76 +279,42 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                 top -= n_pop;
                 __syncwarp();
 
-                SuccCtx C;
-                C.fc = 0; C.pen = 0.f; C.cnt = 0; C.pos = 0; C.packed = 0xFF000000u; C.flags = 0;
-                uint32_t n_items = 0;
                 bool p_ex = false, p_sw = false, p_in = false;
                 FacState c_ex, c_sw, c_in;
-                SuccRec r_sw; r_sw.x = r_sw.y = r_sw.z = 0; r_sw.w = FAC_NONE;
+                c_ex.node = c_sw.node = c_in.node = 0; c_ex.pen = c_sw.pen = c_in.pen = 0.f;
+                c_ex.cnt = c_sw.cnt = c_in.cnt = 0; c_ex.pos = c_sw.pos = c_in.pos = 0;
+                C.sub_m = C.del_m = 0;
                 if (active) {
                     n_states++;
                     if (rec.w != FAC_NONE) succ_outputs(K, out2, emit, rec.w, pen, sv.z, start, start + (sv.w & 1023u));
-                    succ_make_ctx(K, T, start, text_end, rec, pen, sv.z, sv.w, C);
+                    succ_make_ctx2(K, T, G, start, text_end, sv.x, rec, pen, sv.z, sv.w, C);
                     const uint32_t jr = sv.w >> 10;
-                    if ((C.packed >> 24) != 0xFFu) {
+                    const uint32_t cur_s = (C.packed >> 8) & 0xFFu;
+                    if (succ_has_edge(rec, cur_s)) {   // exact transition, search.rs:776-798
                         p_ex = true;
-                        c_ex.node = (rec.y & SUCC_FC_MASK) + (C.packed >> 24); c_ex.pen = pen; c_ex.cnt = sv.z; c_ex.pos = succ_make_pos(jr + 1, jr + 1);
+                        c_ex.node = succ_child(rec, cur_s); c_ex.pen = pen; c_ex.cnt = sv.z; c_ex.pos = succ_make_pos(jr + 1, jr + 1);
                     }
-                    p_sw = succ_swap(K, R, rec, C, r_sw, c_sw);
-                    p_in = succ_ins(K, rec, C, sv.x, c_in);
-                    if ((C.flags & (SUCC_F_IN_TEXT | SUCC_F_DEL)) != 0) n_items = deg;
-                    if (last) {  // edit-children are exhausted: walk them in place
-                        if (p_sw) n_states += succ_walk(K, R, out2, T, emit, start, text_end, r_sw, c_sw.pen, c_sw.cnt, c_sw.pos >> 10, c_sw.pos & 1023u);
-                        if (p_in) n_states += succ_walk(K, R, out2, T, emit, start, text_end, rec, c_in.pen, c_in.cnt, c_in.pos >> 10, c_in.pos & 1023u);
-                        p_sw = p_in = false;
-                    }
+                    p_sw = succ_swap2(K, R, C, c_sw);
+                    p_in = succ_ins2(K, C, sv.x, rec.w != FAC_NONE, c_in);
                 }
                 succ_warp_push(stk, top, p_ex, c_ex);
-                if (__any_sync(0xFFFFFFFFu, p_sw)) succ_warp_push(stk, top, p_sw, c_sw);
-                if (__any_sync(0xFFFFFFFFu, p_in)) succ_warp_push(stk, top, p_in, c_in);
-
-                // ---- (state, child edge) pairs, 32 per round ----
-                uint32_t off = n_items;
+                {
+                    const bool lw = active && last;
+                    if (__any_sync(0xFFFFFFFFu, p_sw && lw)) succ_warp_push(wq, wn, p_sw && lw, c_sw);
+                    if (__any_sync(0xFFFFFFFFu, p_sw && !lw)) succ_warp_push(stk, top, p_sw && !lw, c_sw);
+                    if (__any_sync(0xFFFFFFFFu, p_in && lw)) succ_warp_push(wq, wn, p_in && lw, c_in);
+                    if (__any_sync(0xFFFFFFFFu, p_in && !lw)) succ_warp_push(stk, top, p_in && !lw, c_in);
+                }
+                const uint32_t n_items = (uint32_t)__popc(C.sub_m) + (uint32_t)__popc(C.del_m);
+                off = n_items;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, off, d);
                     if (lane >= (uint32_t)d) off += v;
                 }
-                const uint32_t total = __shfl_sync(0xFFFFFFFFu, off, 31);
+                total = __shfl_sync(0xFFFFFFFFu, off, 31);
                 off -= n_items;  // exclusive
-                for (uint32_t b0 = 0; b0 < total; b0 += 32u) {
-                    const uint32_t it = b0 + lane;
-                    const bool valid = it < total;
-                    uint32_t lo = 0;
-#pragma unroll
-                    for (int step = 16; step; step >>= 1) {
-                        const uint32_t cand = lo + step;
-                        const uint32_t v = __shfl_sync(0xFFFFFFFFu, off, cand & 31u);
-                        if (cand < 32u && v <= it) lo = cand;
-                    }
-                    SuccCtx O;
-                    O.fc = __shfl_sync(0xFFFFFFFFu, C.fc, lo);
-                    O.pen = __shfl_sync(0xFFFFFFFFu, C.pen, lo);
-                    O.cnt = __shfl_sync(0xFFFFFFFFu, C.cnt, lo);
-                    O.pos = __shfl_sync(0xFFFFFFFFu, C.pos, lo);
-                    O.packed = __shfl_sync(0xFFFFFFFFu, C.packed, lo);
-                    O.flags = __shfl_sync(0xFFFFFFFFu, C.flags, lo);
-                    const uint32_t k = it - __shfl_sync(0xFFFFFFFFu, off, lo);
-                    bool p_sub = false, p_del = false;
-                    FacState c_sub, c_del;
-                    if (valid) {
-                        const SuccRec crec = R((O.fc & SUCC_FC_MASK) + k);
-                        p_sub = succ_sub(K, s_subpen, O, k, crec, c_sub);
-                        p_del = succ_del(K, O, k, crec, c_del);
-                        if (O.flags & SUCC_F_LAST) {
-                            if (p_sub) n_states += succ_walk(K, R, out2, T, emit, start, text_end, crec, c_sub.pen, c_sub.cnt, c_sub.pos >> 10, c_sub.pos & 1023u);
-                            if (p_del) n_states += succ_walk(K, R, out2, T, emit, start, text_end, crec, c_del.pen, c_del.cnt, c_del.pos >> 10, c_del.pos & 1023u);
-                            p_sub = p_del = false;
-                        }
-                    }
-                    if (__any_sync(0xFFFFFFFFu, p_sub)) succ_warp_push(stk, top, p_sub, c_sub);
-                    if (__any_sync(0xFFFFFFFFu, p_del)) succ_warp_push(stk, top, p_del, c_del);
-                }
+                b0 = 0;
             }
         }
         __syncthreads();  // every warp is done with the tile before it is restaged

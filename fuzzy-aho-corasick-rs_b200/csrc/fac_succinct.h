@@ -168,3 +168,111 @@ FAC_HD bool succ_del(const SuccConsts &K, const SuccCtx &C, uint32_t k, const Su
     out.node = (C.fc & SUCC_FC_MASK) + k; out.pen = FAC_ADD(C.pen, K.pen_del); out.cnt = C.cnt + 0x100u; out.pos = C.pos;
     return true;
 }
+
+// ---- survivor masks -------------------------------------------------------------------------------
+// For a state on its last edit the dead-end filter keeps a child c iff
+//     c has an output  ||  c has a single-byte edge for the look-ahead symbol
+// (substitution: look-ahead = text[j+1], search.rs:839-847; deletion: text[j], :1057-1063).  Per node
+// and symbol the builder precomputes  gm[node][y] = { symbols s : child(node, s) has edge y }  and
+// gm[node][31] = { s : child(node, s) has an output }  ("grandchild masks", symbol space), so the
+// children that survive are known from two 4-byte loads instead of one record load per child.
+// States that are not on their last edit keep every child.  `GM(node, y)` returns the row entry.
+struct SuccCtx2 {
+    uint32_t bm, fc;
+    float pen;
+    uint32_t cnt, pos;
+    uint32_t packed;   // cur byte | cur sym << 8 | next sym << 16
+    uint32_t flags;
+    uint32_t sub_m, del_m;
+};
+
+template <class Text, class GM>
+FAC_HD void succ_make_ctx2(const SuccConsts &K, const Text &T, const GM &G, uint32_t start, uint32_t text_end, uint32_t node, const SuccRec &rec,
+                           float pen, uint32_t cnt, uint32_t pos, SuccCtx2 &C) {
+    const uint32_t jr = pos >> 10;
+    const uint32_t j = start + jr;
+    const bool last = (int)fac_edits_of(cnt) + 1 >= K.mef;
+    const bool in_text = j < text_end;
+    uint32_t cur_b = 0, cur_s = SUCC_NOSYM, nxt_s = SUCC_NOSYM, flags = 0;
+    if (last) flags |= SUCC_F_LAST;
+    if (in_text) {
+        flags |= SUCC_F_IN_TEXT;
+        cur_b = T.byte(j); cur_s = T.sym(j);
+        if (j + 1 < text_end) { nxt_s = T.sym(j + 1); flags |= SUCC_F_HAS_NXT; }
+    }
+    const bool del_ok = K.pen_del <= FAC_SUB(K.maxpen, pen);  // search.rs:1035
+    if (del_ok) flags |= SUCC_F_DEL;
+    uint32_t sub_m = 0, del_m = 0;
+    if (last) {
+        if (rec.x && (in_text || del_ok)) {
+            const uint32_t outm = G(node, SUCC_NOSYM);
+            if (in_text) sub_m = (outm | (nxt_s != SUCC_NOSYM ? G(node, nxt_s) : 0u)) & rec.x & ~(1u << cur_s);
+            if (del_ok) del_m = (outm | (cur_s != SUCC_NOSYM ? G(node, cur_s) : 0u)) & rec.x;
+        }
+    } else {
+        if (in_text) sub_m = rec.x & ~(1u << cur_s);
+        if (del_ok) del_m = rec.x;
+    }
+    C.bm = rec.x; C.fc = rec.y; C.pen = pen; C.cnt = cnt; C.pos = pos;
+    C.packed = cur_b | (cur_s << 8) | (nxt_s << 16);
+    C.flags = flags; C.sub_m = sub_m; C.del_m = del_m;
+}
+
+// position of the n-th (0-based) set bit of m; m must have more than n bits set
+FAC_HD uint32_t succ_nth_bit(uint32_t m, uint32_t n) {
+    uint32_t pos = 0;
+    uint32_t c = FAC_POPC(m & 0xFFFFu);
+    if (n >= c) { n -= c; pos = 16; m >>= 16; }
+    c = FAC_POPC(m & 0xFFu);
+    if (n >= c) { n -= c; pos += 8; m >>= 8; }
+    c = FAC_POPC(m & 0xFu);
+    if (n >= c) { n -= c; pos += 4; m >>= 4; }
+    c = FAC_POPC(m & 0x3u);
+    if (n >= c) { n -= c; pos += 2; m >>= 2; }
+    if (n >= (m & 1u)) pos += 1;
+    return pos;
+}
+
+// Item r of a state's survivors: r < popc(sub_m) is a substitution, the rest are deletions.
+// Returns false when the substitution penalty exceeds the remaining budget (search.rs:829-834).
+FAC_HD bool succ_item2(const SuccConsts &K, const float *sub_pen, const SuccCtx2 &C, uint32_t r, FacState &out) {
+    const uint32_t ns = FAC_POPC(C.sub_m);
+    const uint32_t jr = C.pos >> 10;
+    if (r < ns) {
+        const uint32_t s = succ_nth_bit(C.sub_m, r);
+        const float pp = sub_pen[s * 128u + (C.packed & 0x7Fu)];  // +inf when similarity < min_symbol_similarity
+        if (pp > FAC_SUB(K.maxpen, C.pen)) return false;
+        out.node = (C.fc & SUCC_FC_MASK) + FAC_POPC(C.bm & ((1u << s) - 1u));
+        out.pen = FAC_ADD(C.pen, pp); out.cnt = C.cnt + 0x10000u; out.pos = succ_make_pos(jr + 1, jr + 1);
+        return true;
+    }
+    const uint32_t s = succ_nth_bit(C.del_m, r - ns);
+    out.node = (C.fc & SUCC_FC_MASK) + FAC_POPC(C.bm & ((1u << s) - 1u));
+    out.pen = FAC_ADD(C.pen, K.pen_del); out.cnt = C.cnt + 0x100u; out.pos = C.pos;
+    return true;
+}
+
+// Swap / insertion with the SuccCtx2 layout (same rules as succ_swap / succ_ins above).
+template <class Recs>
+FAC_HD bool succ_swap2(const SuccConsts &K, const Recs &R, const SuccCtx2 &C, FacState &out) {
+    if ((C.flags & (SUCC_F_IN_TEXT | SUCC_F_HAS_NXT)) != (SUCC_F_IN_TEXT | SUCC_F_HAS_NXT)) return false;
+    if (!(K.pen_swap <= FAC_SUB(K.maxpen, C.pen))) return false;
+    const uint32_t cur_s = (C.packed >> 8) & 0xFFu, nxt_s = (C.packed >> 16) & 0xFFu;
+    if (!((C.bm >> nxt_s) & 1u)) return false;
+    const SuccRec rx = R((C.fc & SUCC_FC_MASK) + FAC_POPC(C.bm & ((1u << nxt_s) - 1u)));
+    if (!succ_has_edge(rx, cur_s)) return false;
+    const uint32_t jr = C.pos >> 10;
+    out.node = succ_child(rx, cur_s); out.pen = FAC_ADD(C.pen, K.pen_swap); out.cnt = C.cnt + 0x1000000u; out.pos = succ_make_pos(jr + 2, jr + 2);
+    return true;
+}
+FAC_HD bool succ_ins2(const SuccConsts &K, const SuccCtx2 &C, uint32_t node, bool has_out, FacState &out) {
+    if (!(C.flags & SUCC_F_IN_TEXT)) return false;
+    const uint32_t jr = C.pos >> 10, mr = C.pos & 1023u;
+    if (mr == 0 && jr == 0) return false;
+    if (!(K.pen_ins <= FAC_SUB(K.maxpen, C.pen))) return false;
+    if ((C.flags & SUCC_F_LAST) && !has_out) {
+        if (!(C.flags & SUCC_F_HAS_NXT) || !((C.bm >> ((C.packed >> 16) & 0xFFu)) & 1u)) return false;
+    }
+    out.node = node; out.pen = FAC_ADD(C.pen, K.pen_ins); out.cnt = C.cnt + 1u; out.pos = succ_make_pos(jr + 1, mr);
+    return true;
+}

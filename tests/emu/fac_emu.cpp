@@ -181,6 +181,20 @@ struct EmuSText {
     uint32_t byte(uint32_t j) const { const uint32_t c = b[j]; return (ci && c >= 'A' && c <= 'Z') ? c + 32u : c; }
     uint32_t sym(uint32_t j) const { return symof[byte(j)]; }
 };
+struct EmuGM {   // grandchild-mask rows: table for the first gm_nodes nodes, recomputed from the children beyond
+    const uint32_t *gm; uint32_t gm_nodes; const SuccRec *r;
+    uint32_t operator()(uint32_t node, uint32_t y) const {
+        if (node < gm_nodes) return gm[(size_t)node * 32 + y];
+        uint32_t bmv = r[node].x, k = 0, m = 0;
+        while (bmv) {
+            const uint32_t sy = (uint32_t)__builtin_ctz(bmv);
+            bmv &= bmv - 1;
+            const SuccRec &c = r[(r[node].y & SUCC_FC_MASK) + k++];
+            if (y == SUCC_NOSYM ? c.w != FAC_NONE : ((c.x >> y) & 1u)) m |= 1u << sy;
+        }
+        return m;
+    }
+};
 struct EmuEmit {
     std::vector<FacCand> *v;
     void operator()(uint32_t sg, uint32_t eg, uint32_t pat, float sim, uint32_t cnt) { v->push_back(FacCand{sg, eg, pat, sim, cnt, 0, 0, 0}); }
@@ -205,11 +219,13 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
     SuccConsts K;
     K.thr = thr; K.maxpen = FAC_AS_FLOAT(recs[0].z); K.pen_ins = HA.pen_ins; K.pen_del = HA.pen_del; K.pen_swap = HA.pen_swap; K.mef = HA.mef;
     const EmuRecs R{recs.data()};
+    const EmuGM G{S.gmask.data(), S.gm_nodes, recs.data()};
     const EmuSText T{hay, S.sym_of, HA.ci};
     const SuccOut *out2 = (const SuccOut *)S.out2.data();
     std::vector<FacCand> cands;
     EmuEmit emit{&cands};
     uint64_t states = 0;
+    uint64_t st_pop = 0, st_items = 0, st_surv = 0, st_walk = 0, st_deg_hist[33] = {0};
     for (uint32_t start = 0; start < n; start++) {
         if (HA.wskip) {
             if (!((S.first_mask >> T.sym(start)) & 1u)) {
@@ -226,24 +242,23 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
             const SuccRec rec = R(s.node);
             if (s.pen > FAC_AS_FLOAT(rec.z)) continue;
             if (rec.w != FAC_NONE) succ_outputs(K, out2, emit, rec.w, s.pen, s.cnt, start, start + (s.pos & 1023u));
-            SuccCtx C;
-            succ_make_ctx(K, T, start, text_end, rec, s.pen, s.cnt, s.pos, C);
+            SuccCtx2 C;
+            succ_make_ctx2(K, T, G, start, text_end, s.node, rec, s.pen, s.cnt, s.pos, C);
             const bool last = (C.flags & SUCC_F_LAST) != 0;
             const uint32_t jr = s.pos >> 10;
-            auto child = [&](const FacState &c, const SuccRec &crec) {
-                if (last) states += succ_walk(K, R, out2, T, emit, start, text_end, crec, c.pen, c.cnt, c.pos >> 10, c.pos & 1023u);
+            auto child = [&](const FacState &c) {
+                if (last) { const uint32_t w_ = succ_walk(K, R, out2, T, emit, start, text_end, R(c.node), c.pen, c.cnt, c.pos >> 10, c.pos & 1023u); states += w_; st_walk += w_; st_surv++; }
                 else stack.push_back(c);
             };
-            if ((C.packed >> 24) != 0xFFu) stack.push_back(FacState{(rec.y & SUCC_FC_MASK) + (C.packed >> 24), s.pen, s.cnt, succ_make_pos(jr + 1, jr + 1)});
-            FacState c; SuccRec r2;
-            if (succ_swap(K, R, rec, C, r2, c)) child(c, r2);
-            if (succ_ins(K, rec, C, s.node, c)) child(c, rec);
-            const uint32_t deg = FAC_POPC(rec.x);
-            for (uint32_t k = 0; k < deg; k++) {
-                const SuccRec crec = R((rec.y & SUCC_FC_MASK) + k);
-                if (succ_sub(K, S.sub_pen.data(), C, k, crec, c)) child(c, crec);
-                if (succ_del(K, C, k, crec, c)) child(c, crec);
-            }
+            const uint32_t cur_s = (C.packed >> 8) & 0xFFu;
+            if (succ_has_edge(rec, cur_s)) stack.push_back(FacState{succ_child(rec, cur_s), s.pen, s.cnt, succ_make_pos(jr + 1, jr + 1)});
+            FacState c;
+            if (succ_swap2(K, R, C, c)) child(c);
+            if (succ_ins2(K, C, s.node, rec.w != FAC_NONE, c)) child(c);
+            const uint32_t n_items = FAC_POPC(C.sub_m) + FAC_POPC(C.del_m);
+            st_pop++; st_items += n_items; st_deg_hist[std::min<uint32_t>(n_items, 32)]++;
+            for (uint32_t r = 0; r < n_items; r++)
+                if (succ_item2(K, S.sub_pen.data(), C, r, c)) child(c);
         }
     }
     typedef std::tuple<uint32_t, uint32_t, uint32_t> Key;
@@ -284,7 +299,8 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
     *n_out = res.size();
     *out = (fac_match *)malloc(sizeof(fac_match) * (res.size() ? res.size() : 1));
     if (!res.empty()) memcpy(*out, res.data(), sizeof(fac_match) * res.size());
-    if (info) { info[0] = n_dirty; info[1] = states; }
+    if (getenv("EMU_STATS")) { fprintf(stderr, "windows %u popped %llu items %llu survivors %llu walk_steps %llu\n deg hist:", n, (unsigned long long)st_pop, (unsigned long long)st_items, (unsigned long long)st_surv, (unsigned long long)st_walk); for (int d = 0; d < 33; d++) fprintf(stderr, " %llu", (unsigned long long)st_deg_hist[d]); fprintf(stderr, "\n"); }
+    if (info) { info[0] = n_dirty; info[1] = states; info[2] = cands.size(); info[3] = best.size(); }
     return 0;
 }
 

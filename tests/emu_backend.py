@@ -79,7 +79,7 @@ class EmuBackend:
         cnt = C.c_size_t(0)
         states = C.c_uint64(0)
         if self.succinct:
-            info = (C.c_uint64 * 2)()
+            info = (C.c_uint64 * 4)()
             st = self.lib.emu_search_succinct(C.byref(cfg), pats, n, data, len(data), thr, C.byref(out), C.byref(cnt), info)
             if st == 0:
                 self.succinct_used += 1
@@ -88,7 +88,7 @@ class EmuBackend:
                 if cnt.value:
                     C.memmove(arr, out, cnt.value * C.sizeof(fac_match))
                 self.lib.emu_free(out)
-                return arr, {"states_pushed": info[1], "dirty_windows": info[0]}
+                return arr, {"states_pushed": info[1], "dirty_windows": info[0], "candidates": info[2], "keys": info[3]}
             if st != -3:
                 raise RuntimeError("emu succinct status %d" % st)
         pw = (C.c_uint32 * max(1, len(data)))() if per_window else None

@@ -167,6 +167,35 @@ def test_tile_failure_retry_path(oracle, gpu, monkeypatch):
     assert o.stats["states_pushed"] == g.stats["states_pushed"]
 
 
+def test_succinct_stack_overflow_goes_to_faithful_redo(oracle, gpu, monkeypatch):
+    # edits(3) with a deliberately tiny warp stack: windows whose top state does not fit are marked
+    # dirty by the fast kernel and must come back bit-exact from the order-faithful pass
+    monkeypatch.setenv("FAC_FAITHFUL", "0")
+    monkeypatch.setenv("FAC_SUCC_STACK", "40")
+    cfg = workload.cfg2(1 << 11, n_patterns=1500)
+    from fac_b200 import FuzzyLimits as FL
+    mk = lambda b: FuzzyAhoCorasickBuilder.new(b).fuzzy(FL.new().edits(3)).build(cfg["patterns"])
+    text = bytes(cfg["text"])
+    o = mk(oracle).search(text, SearchOptions.new().threshold(0.75))
+    g = mk(gpu).search(text, SearchOptions.new().threshold(0.75))
+    assert len(o) > 20
+    assert o.tuples() == g.tuples()
+
+
+@pytest.mark.parametrize("edits", [1, 3, 4])
+def test_succinct_other_edit_budgets(oracle, gpu, edits, monkeypatch):
+    monkeypatch.setenv("FAC_FAITHFUL", "0")
+    cfg = workload.cfg2(1 << 11 if edits > 2 else 1 << 14, n_patterns=600)
+    from fac_b200 import FuzzyLimits as FL
+    mk = lambda b: FuzzyAhoCorasickBuilder.new(b).fuzzy(FL.new().edits(edits)).case_insensitive(True).build(cfg["patterns"])
+    text = bytes(cfg["text"])
+    thr = 0.8 if edits < 3 else 0.7
+    o = mk(oracle).search(text, SearchOptions.new().threshold(thr))
+    g = mk(gpu).search(text, SearchOptions.new().threshold(thr))
+    assert len(o) > 10
+    assert o.tuples() == g.tuples()
+
+
 def _beam_cases(seed, trials):
     r = random.Random(seed)
     words = ["saddam", "hussein", "tincidunt", "porta", "vestibulum", "accumsan", "hello", "world", "help", "shell",

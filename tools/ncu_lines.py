@@ -37,14 +37,15 @@ def main():
     base = int(k["rows"][0][ci["Address"]], 16)
     samples = {}
     for r in k["rows"]:
-        samples[int(r[ci["Address"]], 16) - base] = (int(r[ci["# Samples"]]), r[ci["Source"]].strip())
+        samples[int(r[ci["Address"]], 16) - base] = (int(r[ci["# Samples"]]), r[ci["Source"]].strip(), int(r[ci["Instructions Executed"]]),
+                                                    int(r[ci["Thread Instructions Executed"]]))
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
     cubins = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")]
     # mangled name from the demangled one: match template args by the bool list
-    bools = re.findall(r"\(bool\)(\d)", k["name"])
+    targs = re.findall(r"\((bool|int)\)(\d+)", k["name"])
     fn = re.match(r"void (\w+)", k["name"]).group(1)
-    pat = re.compile(r"\.text\._Z\d+%s%s" % (fn, ("I" + "".join("Lb%sE" % b for b in bools) + "E") if bools else ""))
+    pat = re.compile(r"\.text\._Z\d+%s%s" % (fn, ("I" + "".join("L%s%sE" % ("b" if t == "bool" else "i", v) for t, v in targs) + "E") if targs else ""))
     line_of, cur_line, active = {}, None, False
     for cb in cubins:
         dis = subprocess.run(["nvdisasm", "-g", "-c", cb], capture_output=True, text=True).stdout
@@ -62,11 +63,16 @@ def main():
             if m:
                 line_of[int(m.group(1), 16)] = cur_line
     agg = defaultdict(int)
-    tot = 0
-    for off, (s, _) in samples.items():
+    iagg, tagg = defaultdict(int), defaultdict(int)
+    tot = itot = 0
+    for off, (s, _, ni, nt) in samples.items():
         agg[line_of.get(off)] += s
+        iagg[line_of.get(off)] += ni
+        tagg[line_of.get(off)] += nt
         tot += s
-    print("kernel:", k["name"], "total samples", tot)
+        itot += ni
+    print("kernel:", k["name"], "total samples", tot, "warp instructions", itot)
+    print("stall%  inst%  thr/inst  line")
     srcs = {}
     for (key, s) in sorted(agg.items(), key=lambda kv: -kv[1])[:topn]:
         text = ""
@@ -77,7 +83,8 @@ def main():
                 srcs[f] = open(p).read().splitlines() if os.path.exists(p) else []
             if 0 < l <= len(srcs[f]):
                 text = srcs[f][l - 1].strip()[:100]
-        print("%5.2f%%  %-22s %s" % (100.0 * s / max(tot, 1), "%s:%d" % key if key else "?", text))
+        print("%5.2f%% %5.2f%% %5.1f  %-22s %s" % (100.0 * s / max(tot, 1), 100.0 * iagg[key] / max(itot, 1), tagg[key] / max(iagg[key], 1),
+                                             "%s:%d" % key if key else "?", text))
 
 
 if __name__ == "__main__":
