@@ -24,6 +24,7 @@
 #include "fac_fastreduce.cuh"
 #include "fac_segment.cuh"
 #include "fac_succinct.cuh"
+#include "fac_bitap.cuh"
 
 #define FAC_TABLE_QUAL static const
 #include "unicode_tables.h"
@@ -75,6 +76,7 @@ struct U8ToU32 {
 struct SearchStats {
     uint64_t states = 0;
     uint64_t dirty_windows = 0;
+    uint64_t pf_slices = 0, pf_hits = 0;
     double device_ms = 0, expand_ms = 0;
     uint32_t launches = 0;
 };
@@ -82,7 +84,7 @@ struct SearchStats {
 struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, evk0 = nullptr, evk1 = nullptr;
-    DBuf hay, mark, gidx, first, gid, off, pfsym, srec;
+    DBuf hay, mark, gidx, first, gid, off, pfsym, srec, cov, covcnt, covoff, sl_gs, sl_ge, bp_k;
     DBuf queue, nxt, hslot, gtab_rep, gtab_head, gtab_min;
     uint32_t grid = 0, qcap = 0, gtab_size = 0;
     DBuf cands, counters, failed_tiles, failed_bitmap, tiles;
@@ -98,7 +100,7 @@ struct Workspace {
         return FAC_OK;
     }
     void destroy() {
-        for (DBuf *b : {&hay, &mark, &gidx, &first, &gid, &off, &pfsym, &srec, &queue, &nxt, &hslot, &gtab_rep, &gtab_head, &gtab_min, &cands, &counters,
+        for (DBuf *b : {&hay, &mark, &gidx, &first, &gid, &off, &pfsym, &srec, &cov, &covcnt, &covoff, &sl_gs, &sl_ge, &bp_k, &queue, &nxt, &hslot, &gtab_rep, &gtab_head, &gtab_min, &cands, &counters,
                         &failed_tiles, &failed_bitmap, &tiles, &best_rep, &best_val, &cslot, &tab_sim, &tab_cmin, &tab_cmax, &tab_first, &dirty, &m_a, &m_b, &idx_a, &idx_b, &winend, &st_a, &st_b,
                         &flags8, &sel, &nsel, &outm, &keep8, &windows, &misc, &cubtmp, &used})
             b->release();
@@ -133,6 +135,9 @@ struct fac_engine {
     uint32_t smem_tab = 4096;
     int ctas_per_sm = 2;
     int use_tma = 1;
+    // bitap pre-filter (fac_bitap.cuh)
+    const uint64_t *d_bp_mask = nullptr;
+    const uint8_t *d_bp_m = nullptr;
     // succinct-trie fast kernel (fac_succinct.cuh)
     bool succ_ok = false;
     const uint32_t *d_s_bm = nullptr, *d_s_fc = nullptr, *d_s_out_idx = nullptr, *d_s_out2 = nullptr;
@@ -217,7 +222,8 @@ fac_status launch_succ_t(const SuccParams &P, uint32_t grid, size_t smem, cudaSt
     return FAC_OK;
 }
 fac_status launch_succinct(const fac_engine *E, Workspace *ws, const uint8_t *d_text, float thr, uint32_t seg_begin, uint32_t seg_end,
-                           uint32_t text_end, FacCand *cands, uint32_t cand_cap, cudaStream_t s) {
+                           uint32_t text_end, FacCand *cands, uint32_t cand_cap, cudaStream_t s, const uint4 *d_tiles = nullptr,
+                           uint32_t n_explicit = 0) {
     const fac::HostSuccinct &S = E->host.succ;
     const uint32_t N = (uint32_t)S.bm.size();
     CKS(ws->srec.ensure((size_t)N * 16));
@@ -233,7 +239,10 @@ fac_status launch_succinct(const fac_engine *E, Workspace *ws, const uint8_t *d_
     P.ci = E->host.ci; P.wskip = E->host.wskip; P.first_mask = S.first_mask; P.second_mask = S.second_mask;
     P.seg_begin = seg_begin; P.seg_end = seg_end; P.text_end = text_end;
     P.tile = E->succ_tile; P.n_tiles = cdiv((uint64_t)seg_end - seg_begin, P.tile); P.lookahead = E->lookahead;
-    const uint32_t nw = E->succ_nt / 32;
+    if (d_tiles) { P.tiles = d_tiles; P.n_tiles = n_explicit; }
+    // deeper edit budgets push whole sibling sets of non-final states: fewer warps, deeper stacks
+    const uint32_t nt = E->host.mef <= 2 ? E->succ_nt : std::min<uint32_t>(E->succ_nt, 512u);
+    const uint32_t nw = nt / 32;
     P.stack_cap = E->succ_stack ? E->succ_stack : (E->host.mef <= 2 ? 128u : 384u);
     P.text_cap = (P.tile + P.lookahead + 16u + 15u) & ~15u;
     P.gm = E->d_s_gm; P.gm_nodes = S.gm_nodes;
@@ -246,7 +255,7 @@ fac_status launch_succinct(const fac_engine *E, Workspace *ws, const uint8_t *d_
     P.dirty = ws->dirty.as<uint32_t>();
     const size_t smem = fixed + (size_t)P.n_smem_nodes * 16;
     const uint32_t grid = std::min<uint32_t>((uint32_t)E->sm_count, P.n_tiles);
-    switch (E->succ_nt) {
+    switch (nt) {
         case 1024: return launch_succ_t<1024>(P, grid, smem, s);
         case 512: return launch_succ_t<512>(P, grid, smem, s);
         case 256: return launch_succ_t<256>(P, grid, smem, s);
@@ -307,6 +316,9 @@ struct ExpandRun {
     // called after the expansion has completed (stream synchronised) and before the reduction;
     // returns the exclusive upper bound of the start windows whose candidates count (auto_beam), default: all
     std::function<uint32_t(uint64_t states)> limit_after_expand;
+    // pre-filter mode: the merged slices (gs, ge) the explicit tiles were cut from; a start window's
+    // text_end is the end of its slice (each slice is searched as its own haystack, prefilter.rs:346-350)
+    const std::vector<std::pair<uint32_t, uint32_t>> *slices = nullptr;
 };
 
 // Run K3 (+ retry of failed tiles) and the best-per-span reduction; appends WMatch records to
@@ -354,8 +366,9 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
     P.per_window = R.d_per_window;
     P.use_tma = E->use_tma;
     const size_t smem = expand_smem_bytes(E, ascii, P.smem_text_cap);
-    const bool use_succ = R.fast && E->succ_ok && ascii && !explicit_tiles && !R.beam && !R.d_per_window;
-    const uint32_t n_win_seg = explicit_tiles ? 0 : (R.seg_end - R.seg_begin);
+    const bool use_succ = R.fast && E->succ_ok && ascii && (!explicit_tiles || R.slices) && !R.beam && !R.d_per_window;
+    if (use_succ && explicit_tiles && max_count > E->succ_tile) { set_err("internal: slice tile larger than the succinct tile"); return FAC_INVALID_ARGUMENT; }
+    const uint32_t n_win_seg = R.seg_end - R.seg_begin;
     const uint32_t dirty_words = n_win_seg / 32 + 1;
     if (R.fast) CKS(ws->dirty.ensure((size_t)dirty_words * 4));
 
@@ -369,7 +382,8 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
             k_expand_beam<<<grid, FAC_BLOCK, 0, s>>>(P, R.bw);
             CK(cudaGetLastError());
         } else if (use_succ) {
-            CKS(launch_succinct(E, ws, R.tv.bytes, R.thr, R.seg_begin, R.seg_end, R.text_end, ws->cands.as<FacCand>(), cand_cap, s));
+            CKS(launch_succinct(E, ws, R.tv.bytes, R.thr, R.seg_begin, R.seg_end, R.text_end, ws->cands.as<FacCand>(), cand_cap, s,
+                                explicit_tiles ? ws->tiles.as<uint4>() : nullptr, n_tiles));
             stats.launches++;
         } else CKS(launch_expand(P, grid, smem, s, R.fast));
         CK(cudaEventRecord(ws->evk1, s));
@@ -519,6 +533,11 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
             R2.tv = R.tv; R2.text_end = R.text_end; R2.d_windows = R.d_windows; R2.thr = R.thr; R2.fast = false; R2.count_states = false;
             R2.tiles.resize(n_dirty);
             CK(cudaMemcpy(R2.tiles.data(), ws->tiles.p, n_dirty * sizeof(uint4), cudaMemcpyDeviceToHost));
+            if (R.slices)
+                for (uint4 &t4 : R2.tiles) {  // the window's haystack ends where its slice ends
+                    auto it = std::upper_bound(R.slices->begin(), R.slices->end(), std::make_pair(t4.x, 0xFFFFFFFFu));
+                    t4.z = (--it)->second;
+                }
             stats.dirty_windows += n_dirty;
             CKS(expand_and_reduce(E, ws, R2, 1, n_matches, stats, nullptr));
         }
@@ -764,10 +783,100 @@ fac_status search_beamed(const fac_engine *E, Workspace *ws, const TextView &tv,
     return FAC_OK;
 }
 
+// ---- K2: bitap pre-filter (src/prefilter.rs:285-343) on an ASCII haystack -----------------------------
+// k_for (prefilter.rs:285-302): false => the call falls back to the plain search.
+bool bitap_k_for(const fac::HostBitap &B, size_t p, float thr, uint32_t &k_out) {
+    const float n = (float)B.m[p];
+    const float p_max = n * (1.0f - thr / B.weight[p]);
+    uint64_t k_pen;
+    if (p_max <= 0.0f) k_pen = 0;
+    else {
+        const float v = std::floor(p_max * B.edit_cost_mult);
+        if (std::isnan(v)) k_pen = 0; else if (v >= 1.8e19f) k_pen = ~0ull; else k_pen = (uint64_t)v;  // Rust `as usize` saturates
+    }
+    const uint64_t k = B.k_limit[p] >= 0 ? std::min<uint64_t>(k_pen, (uint64_t)B.k_limit[p]) : k_pen;
+    if (k > 24) return false;
+    k_out = (uint32_t)k;
+    return true;
+}
+
+template <int KMAX>
+void launch_bitap_t(const BitapParams &P, dim3 grid, cudaStream_t s) { k_bitap_scan<KMAX><<<grid, BITAP_WARPS * 32, 0, s>>>(P); }
+
+// Scans, merges and returns the slices (gs, ge) in ascending order.  *fallback = true when a pattern's
+// budget exceeds MAX_USEFUL_K (the reference then runs the plain search).
+fac_status prefilter_slices(const fac_engine *E, Workspace *ws, const uint8_t *d_text, uint32_t n, float thr,
+                            std::vector<std::pair<uint32_t, uint32_t>> &slices, bool *fallback, SearchStats &stats) {
+    cudaStream_t s = ws->stream;
+    const fac::HostBitap &B = E->host.bitap;
+    const size_t P = B.m.size();
+    std::vector<uint8_t> ks(P);
+    uint32_t kmax = 0, warm = 0;
+    *fallback = false;
+    for (size_t p = 0; p < P; p++) {
+        uint32_t k;
+        if (!bitap_k_for(B, p, thr, k)) { *fallback = true; return FAC_OK; }
+        ks[p] = (uint8_t)k; kmax = std::max(kmax, k); warm = std::max(warm, B.m[p] + k);
+    }
+    const uint32_t n_words = n / 32 + 1;
+    CKS(ws->bp_k.ensure(P + 16));
+    CKS(ws->cov.ensure((size_t)(n_words + 2) * 4));
+    CKS(ws->covcnt.ensure((size_t)n_words * 4));
+    CKS(ws->covoff.ensure((size_t)(n_words + 1) * 8));
+    CKS(ws->misc.ensure(64));
+    CK(cudaMemcpyAsync(ws->bp_k.p, ks.data(), P, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ws->cov.p, 0, (size_t)(n_words + 2) * 4, s));
+    CK(cudaMemsetAsync(ws->misc.p, 0, 16, s));
+    BitapParams BP;
+    BP.text = d_text; BP.n = n; BP.bytemask = E->d_bp_mask; BP.m = E->d_bp_m; BP.k = ws->bp_k.as<uint8_t>();
+    BP.n_patterns = (uint32_t)P; BP.warm = warm; BP.cov = ws->cov.as<uint32_t>(); BP.hits = ws->misc.as<unsigned long long>();
+    const dim3 grid(cdiv(n, (uint64_t)BITAP_SUB * BITAP_WARPS), cdiv(P, 32));
+    if (kmax <= 2) launch_bitap_t<2>(BP, grid, s);
+    else if (kmax <= 4) launch_bitap_t<4>(BP, grid, s);
+    else if (kmax <= 8) launch_bitap_t<8>(BP, grid, s);
+    else launch_bitap_t<24>(BP, grid, s);
+    CK(cudaGetLastError());
+    k_cov_edges<<<cdiv(n_words, 256), 256, 0, s>>>(ws->cov.as<uint32_t>(), n_words, ws->covcnt.as<uint32_t>());
+    {
+        size_t tb = 0;
+        cub::TransformInputIterator<unsigned long long, CovCountToU64, const uint32_t *> it(ws->covcnt.as<uint32_t>(), CovCountToU64());
+        CK(cub::DeviceScan::ExclusiveSum((void *)nullptr, tb, it, ws->covoff.as<unsigned long long>(), (int64_t)n_words + 1, s));
+        CKS(ws->cubtmp.ensure(tb));
+        CK(cudaMemsetAsync(ws->covcnt.as<uint32_t>() + n_words - 0, 0, 0, s));
+        CK(cub::DeviceScan::ExclusiveSum(ws->cubtmp.p, tb, it, ws->covoff.as<unsigned long long>(), (int64_t)n_words, s));
+    }
+    // total = off[last] + cnt[last]
+    unsigned long long last_off = 0; uint32_t last_cnt = 0;
+    CK(cudaMemcpyAsync(&last_off, ws->covoff.as<unsigned long long>() + (n_words - 1), 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&last_cnt, ws->covcnt.as<uint32_t>() + (n_words - 1), 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ws->h_counters, ws->misc.p, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    stats.launches += 3;
+    stats.pf_hits = ws->h_counters[0];
+    const uint32_t n_runs = (uint32_t)(last_off & 0xFFFFFFFFull) + (last_cnt & 0xFFFFu);
+    slices.clear();
+    if (n_runs == 0) return FAC_OK;
+    CKS(ws->sl_gs.ensure((size_t)n_runs * 4));
+    CKS(ws->sl_ge.ensure((size_t)n_runs * 4));
+    k_cov_emit<<<cdiv(n_words, 256), 256, 0, s>>>(ws->cov.as<uint32_t>(), n_words, ws->covoff.as<unsigned long long>(), ws->sl_gs.as<uint32_t>(),
+                                                  ws->sl_ge.as<uint32_t>());
+    CK(cudaGetLastError());
+    std::vector<uint32_t> gs(n_runs), ge(n_runs);
+    CK(cudaMemcpyAsync(gs.data(), ws->sl_gs.p, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ge.data(), ws->sl_ge.p, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    stats.launches++;
+    slices.resize(n_runs);
+    for (uint32_t i = 0; i < n_runs; i++) slices[i] = {gs[i], std::min(ge[i], n)};  // ge.min(n), prefilter.rs:348
+    stats.pf_slices = n_runs;
+    return FAC_OK;
+}
+
 // The whole-haystack search on device-resident text: classification, (K1), K3 over segments of
 // start windows, reduction, apply.  Restricts start windows to the byte range [own_begin, own_end).
 fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_text, uint64_t len, float thr, int order, int overlap,
-                           uint64_t own_begin, uint64_t own_end, uint64_t base, uint64_t commit, bool apply, std::vector<fac_match> &out, SearchStats &stats) {
+                           uint64_t own_begin, uint64_t own_end, uint64_t base, uint64_t commit, bool apply, std::vector<fac_match> &out, SearchStats &stats,
+                           bool use_prefilter = false) {
     cudaStream_t s = ws->stream;
     if (len == 0) return FAC_OK;
     CKS(ws->misc.ensure(64));
@@ -819,6 +928,37 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
         if (apply) CKS(apply_device(E, ws, (uint32_t)n_matches, order, overlap, 1, &n_fin, stats));
         CKS(finalize_and_fetch(ws, n_fin, ws->windows.as<FacWindow>(), commit != ~0ull, out, stats));
         return FAC_OK;
+    }
+    // Prefiltered::search (src/prefilter.rs:135-155, 304-374): bitap scan -> merged slices -> the engine on every
+    // slice as its own haystack.  Device path for ASCII haystacks of beam-less engines; elsewhere the plain
+    // search below answers (result-neutral by the reference's contract, prefilter.rs:1-21).
+    if (use_prefilter && E->host.bitap.active && ascii && own_begin == 0 && own_end >= len) {
+        std::vector<std::pair<uint32_t, uint32_t>> slices;
+        bool fallback = false;
+        CKS(prefilter_slices(E, ws, d_text, (uint32_t)n, thr, slices, &fallback, stats));
+        if (!fallback) {
+            const uint32_t tile_w = E->succ_ok ? E->succ_tile : 64u;
+            size_t si = 0;
+            while (si < slices.size()) {
+                // batches of slices bounded by a window budget so the candidate buffers stay modest
+                ExpandRun R;
+                R.tv = tv; R.d_windows = ws->windows.as<FacWindow>(); R.thr = thr; R.fast = E->fast_ok; R.slices = &slices;
+                uint64_t wins = 0;
+                const size_t s0 = si;
+                for (; si < slices.size() && wins < (1u << 25); si++) {
+                    const uint32_t gs = slices[si].first, ge = slices[si].second;
+                    for (uint32_t a = gs; a < ge; a += tile_w) R.tiles.push_back(make_uint4(a, std::min(tile_w, ge - a), ge, 0u));
+                    wins += ge - gs;
+                }
+                R.seg_begin = slices[s0].first; R.seg_end = slices[si - 1].second; R.text_end = (uint32_t)n;
+                CKS(grow_keep(ws->m_a, n_matches * sizeof(WMatch), (n_matches + (1u << 20)) * sizeof(WMatch), s));
+                CKS(expand_and_reduce(E, ws, R, tile_w, &n_matches, stats, nullptr));
+            }
+            uint32_t n_final = (uint32_t)n_matches;
+            if (apply) CKS(apply_device(E, ws, (uint32_t)n_matches, order, overlap, 1, &n_final, stats));
+            CKS(finalize_and_fetch(ws, n_final, ws->windows.as<FacWindow>(), commit != ~0ull, out, stats));
+            return FAC_OK;
+        }
     }
     const uint64_t SEG = (uint64_t)env_int("FAC_SEGMENT_WINDOWS", 1 << 25);
     uint32_t tile = E->default_tile;
@@ -919,6 +1059,18 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
         if ((st = upload(E, H.symbol_pool, &pool)) != FAC_OK) return fail(st);
         E->d_symbols = (FacSymbol *)sy; E->sym_mask = (uint32_t)H.symbols.size() - 1; E->d_pool = (uint8_t *)pool;
     }
+    if (H.bitap.active) {
+        const fac::HostBitap &B = H.bitap;
+        const size_t P = B.m.size();
+        std::vector<uint64_t> bm(P * 128, 0);
+        std::vector<uint8_t> mm(P);
+        for (size_t pi = 0; pi < P; pi++) {
+            mm[pi] = (uint8_t)B.m[pi];
+            for (int b = 0; b < 128; b++) bm[pi * 128 + b] = B.masks[pi * (size_t)(B.alphabet + 1) + B.ascii_id[b]];
+        }
+        if ((st = upload(E, bm, &E->d_bp_mask)) != FAC_OK) return fail(st);
+        if ((st = upload(E, mm, &E->d_bp_m)) != FAC_OK) return fail(st);
+    }
     if (H.succ.ok) {
         const fac::HostSuccinct &S = H.succ;
         std::vector<uint8_t> symof(S.sym_of, S.sym_of + 256);
@@ -987,8 +1139,7 @@ static fac_status search_common(const fac_engine *E, const uint8_t *hay, size_t 
             CK(cudaMemsetAsync((uint8_t *)ws->hay.p + len, 0, 64, ws->stream));
             d_text = ws->hay.as<uint8_t>();
         }
-        (void)use_prefilter;  // the pre-filter is result-neutral (src/prefilter.rs:1-21); wired in a later step
-        CKS(search_resident(E, ws, d_text, len, thr, order, overlap, own_begin, own_end, base, ~0ull, apply, M->v, M->stats));
+        CKS(search_resident(E, ws, d_text, len, thr, order, overlap, own_begin, own_end, base, ~0ull, apply, M->v, M->stats, use_prefilter != 0));
         CK(cudaEventRecord(ws->ev_end, ws->stream));
         CK(cudaEventSynchronize(ws->ev_end));
         float ms = 0;

@@ -37,6 +37,7 @@ struct SuccParams {
     int32_t ci, wskip;
     uint32_t first_mask, second_mask;
     uint32_t seg_begin, seg_end, text_end, tile, n_tiles, lookahead;
+    const uint4 *tiles;      // optional explicit tiles {start, count (<= tile), text_end, _} (pre-filter slices); null = uniform tiling
     const uint32_t *gm;      // [gm_nodes * 32] grandchild masks (fac_succinct.h)
     uint32_t gm_nodes;
     uint32_t stack_cap;      // states per warp stack
@@ -154,9 +155,9 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
         __syncthreads();
         const uint32_t t = s_tile_idx;
         if (t >= P.n_tiles) break;
-        const uint32_t tile_start = P.seg_begin + t * P.tile;
-        const uint32_t count = min(P.tile, P.seg_end - tile_start);
-        const uint32_t text_end = P.text_end;
+        uint32_t tile_start, count, text_end;
+        if (P.tiles) { const uint4 d = P.tiles[t]; tile_start = d.x; count = d.y; text_end = d.z; }
+        else { tile_start = P.seg_begin + t * P.tile; count = min(P.tile, P.seg_end - tile_start); text_end = P.text_end; }
 
         // ---- stage the tile: TMA bulk copy of the 16-byte aligned body, plain loads for the tail ----
         uint32_t lead = (uint32_t)(((uintptr_t)(P.text + tile_start)) & 15u);

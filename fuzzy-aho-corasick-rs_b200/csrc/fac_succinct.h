@@ -235,21 +235,20 @@ FAC_HD uint32_t succ_nth_bit(uint32_t m, uint32_t n) {
 
 // Item r of a state's survivors: r < popc(sub_m) is a substitution, the rest are deletions.
 // Returns false when the substitution penalty exceeds the remaining budget (search.rs:829-834).
+// Written branch-free so substitution and deletion lanes of a warp stay converged.
 FAC_HD bool succ_item2(const SuccConsts &K, const float *sub_pen, const SuccCtx2 &C, uint32_t r, FacState &out) {
     const uint32_t ns = FAC_POPC(C.sub_m);
     const uint32_t jr = C.pos >> 10;
-    if (r < ns) {
-        const uint32_t s = succ_nth_bit(C.sub_m, r);
-        const float pp = sub_pen[s * 128u + (C.packed & 0x7Fu)];  // +inf when similarity < min_symbol_similarity
-        if (pp > FAC_SUB(K.maxpen, C.pen)) return false;
-        out.node = (C.fc & SUCC_FC_MASK) + FAC_POPC(C.bm & ((1u << s) - 1u));
-        out.pen = FAC_ADD(C.pen, pp); out.cnt = C.cnt + 0x10000u; out.pos = succ_make_pos(jr + 1, jr + 1);
-        return true;
-    }
-    const uint32_t s = succ_nth_bit(C.del_m, r - ns);
+    const bool is_sub = r < ns;
+    const uint32_t s = succ_nth_bit(is_sub ? C.sub_m : C.del_m, is_sub ? r : r - ns);
+    // +inf in the table when similarity < min_symbol_similarity; deletions read a valid slot and ignore it
+    const float tp = sub_pen[s * 128u + (C.packed & 0x7Fu)];
+    const float pp = is_sub ? tp : K.pen_del;
     out.node = (C.fc & SUCC_FC_MASK) + FAC_POPC(C.bm & ((1u << s) - 1u));
-    out.pen = FAC_ADD(C.pen, K.pen_del); out.cnt = C.cnt + 0x100u; out.pos = C.pos;
-    return true;
+    out.pen = FAC_ADD(C.pen, pp);
+    out.cnt = C.cnt + (is_sub ? 0x10000u : 0x100u);
+    out.pos = is_sub ? succ_make_pos(jr + 1, jr + 1) : C.pos;
+    return !(is_sub && pp > FAC_SUB(K.maxpen, C.pen));
 }
 
 // Swap / insertion with the SuccCtx2 layout (same rules as succ_swap / succ_ins above).

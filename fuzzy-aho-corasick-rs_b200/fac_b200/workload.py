@@ -154,10 +154,41 @@ def cfg2(nbytes=1 << 30, n_patterns=10000, seed=0xFAC00002):
             "text": text, "name": "cfg2: %d ASCII patterns, edits(2), thr 0.8" % n_patterns}
 
 
+def cfg4(nbytes=4_000_000_000, n_patterns=100, seed=0xFAC00004, plant_every=1 << 20):
+    """Sparse haystack for the bitap pre-filter: 100 random patterns (len 8-20) that do not occur in the
+    text vocabulary, per-pattern weights {0.5, 1, 1.5, 2} and per-pattern limits (edits(1), edits(2),
+    edits(2).swaps(0), substitutions(1).deletions(1)), one planted fuzzy hit every ~`plant_every` bytes,
+    threshold 0.85, sorted().non_overlapping().  Per-pattern limits put the engine on the reference's
+    generic MAX_EDITS_FAST=255 path (src/search.rs:205-247)."""
+    vocab = make_vocab(seed)
+    pats = random_words(seed, n_patterns, 8, 20)
+    text = make_text(seed, nbytes, vocab, mixed_case=False)
+    text = plant(text, pats, seed, every=plant_every)
+    weights = [(0.5, 1.0, 1.5, 2.0)[i % 4] for i in range(n_patterns)]
+    limits = [("edits1", "edits2", "edits2_noswap", "sub1_del1")[(i // 4) % 4] for i in range(n_patterns)]
+    return {"patterns": [p.decode() for p in pats], "weights": weights, "limit_kinds": limits, "case_insensitive": False,
+            "threshold": 0.85, "text": text, "name": "cfg4: %d weighted patterns with per-pattern limits, sparse text" % n_patterns}
+
+
+def _limits_of(kind):
+    from .api import FuzzyLimits
+    if kind == "edits1":
+        return FuzzyLimits.new().edits(1)
+    if kind == "edits2":
+        return FuzzyLimits.new().edits(2)
+    if kind == "edits2_noswap":
+        return FuzzyLimits.new().edits(2).swaps(0)
+    return FuzzyLimits.new().substitutions(1).deletions(1)
+
+
 def build_engine(cfg, backend=None, device=None):
-    from .api import FuzzyAhoCorasickBuilder, FuzzyLimits
-    b = FuzzyAhoCorasickBuilder.new(backend).fuzzy(FuzzyLimits.new().edits(cfg["edits"])).case_insensitive(
-        cfg["case_insensitive"])
+    from .api import FuzzyAhoCorasickBuilder, FuzzyLimits, Pattern
+    b = FuzzyAhoCorasickBuilder.new(backend).case_insensitive(cfg["case_insensitive"])
+    if "edits" in cfg:
+        b = b.fuzzy(FuzzyLimits.new().edits(cfg["edits"]))
     if device is not None:
         b = b.device(device)
+    if "limit_kinds" in cfg:
+        pats = [Pattern(p, w, _limits_of(k)) for p, w, k in zip(cfg["patterns"], cfg["weights"], cfg["limit_kinds"])]
+        return b.build(pats)
     return b.build(cfg["patterns"])

@@ -225,6 +225,8 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
     std::vector<FacCand> cands;
     EmuEmit emit{&cands};
     uint64_t states = 0;
+    const bool warpsim = getenv("EMU_WARPSIM") != nullptr;
+    uint64_t sim_rounds = 0, sim_max = 0, sim_sum = 0;
     uint64_t st_pop = 0, st_items = 0, st_surv = 0, st_walk = 0, st_deg_hist[33] = {0};
     for (uint32_t start = 0; start < n; start++) {
         if (HA.wskip) {
@@ -236,18 +238,23 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
         std::vector<FacState> stack;
         stack.push_back(FacState{0, 0.f, 0, 0});
         while (!stack.empty()) {
-            const FacState s = stack.back();
-            stack.pop_back();
+          const size_t npop = warpsim ? std::min<size_t>(32, stack.size()) : 1;
+          std::vector<FacState> popped(stack.end() - npop, stack.end());
+          std::reverse(popped.begin(), popped.end());
+          stack.resize(stack.size() - npop);
+          uint64_t lane_max = 0, lane_sum = 0;
+          for (const FacState &s : popped) {
+            uint64_t lane_work = 0;
             states++;
             const SuccRec rec = R(s.node);
-            if (s.pen > FAC_AS_FLOAT(rec.z)) continue;
+            if (s.pen > FAC_AS_FLOAT(rec.z)) continue;  /*dead*/
             if (rec.w != FAC_NONE) succ_outputs(K, out2, emit, rec.w, s.pen, s.cnt, start, start + (s.pos & 1023u));
             SuccCtx2 C;
             succ_make_ctx2(K, T, G, start, text_end, s.node, rec, s.pen, s.cnt, s.pos, C);
             const bool last = (C.flags & SUCC_F_LAST) != 0;
             const uint32_t jr = s.pos >> 10;
             auto child = [&](const FacState &c) {
-                if (last) { const uint32_t w_ = succ_walk(K, R, out2, T, emit, start, text_end, R(c.node), c.pen, c.cnt, c.pos >> 10, c.pos & 1023u); states += w_; st_walk += w_; st_surv++; }
+                if (last) { const uint32_t w_ = succ_walk(K, R, out2, T, emit, start, text_end, R(c.node), c.pen, c.cnt, c.pos >> 10, c.pos & 1023u); states += w_; st_walk += w_; st_surv++; lane_work += w_; }
                 else stack.push_back(c);
             };
             const uint32_t cur_s = (C.packed >> 8) & 0xFFu;
@@ -259,6 +266,9 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
             st_pop++; st_items += n_items; st_deg_hist[std::min<uint32_t>(n_items, 32)]++;
             for (uint32_t r = 0; r < n_items; r++)
                 if (succ_item2(K, S.sub_pen.data(), C, r, c)) child(c);
+            lane_max = std::max(lane_max, lane_work); lane_sum += lane_work;
+          }
+          sim_rounds++; sim_max += lane_max; sim_sum += lane_sum;
         }
     }
     typedef std::tuple<uint32_t, uint32_t, uint32_t> Key;
@@ -299,7 +309,7 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
     *n_out = res.size();
     *out = (fac_match *)malloc(sizeof(fac_match) * (res.size() ? res.size() : 1));
     if (!res.empty()) memcpy(*out, res.data(), sizeof(fac_match) * res.size());
-    if (getenv("EMU_STATS")) { fprintf(stderr, "windows %u popped %llu items %llu survivors %llu walk_steps %llu\n deg hist:", n, (unsigned long long)st_pop, (unsigned long long)st_items, (unsigned long long)st_surv, (unsigned long long)st_walk); for (int d = 0; d < 33; d++) fprintf(stderr, " %llu", (unsigned long long)st_deg_hist[d]); fprintf(stderr, "\n"); }
+    if (getenv("EMU_STATS")) { fprintf(stderr, "windows %u popped %llu items %llu survivors %llu walk_steps %llu\n deg hist:", n, (unsigned long long)st_pop, (unsigned long long)st_items, (unsigned long long)st_surv, (unsigned long long)st_walk); for (int d = 0; d < 33; d++) fprintf(stderr, " %llu", (unsigned long long)st_deg_hist[d]); fprintf(stderr, "\n warpsim rounds %llu sum(max steps) %llu sum(steps) %llu\n", (unsigned long long)sim_rounds, (unsigned long long)sim_max, (unsigned long long)sim_sum); }
     if (info) { info[0] = n_dirty; info[1] = states; info[2] = cands.size(); info[3] = best.size(); }
     return 0;
 }

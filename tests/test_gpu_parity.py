@@ -196,6 +196,52 @@ def test_succinct_other_edit_budgets(oracle, gpu, edits, monkeypatch):
     assert o.tuples() == g.tuples()
 
 
+def test_prefilter_fuzz_ascii(oracle, gpu, monkeypatch):
+    # Prefiltered::search (prefilter.rs:135): GPU bitap scan + slices vs the oracle's restatement
+    r1, r2 = random.Random(41), random.Random(41)
+    ropt = random.Random(48)
+    used = 0
+    for t in range(400):
+        eo, hay, thr, desc = rand_case(r1, oracle, False)
+        eg, _, _, _ = rand_case(r2, gpu, False)
+        order, overlap = ropt.choice(ALL_OPTS)
+        opts = SearchOptions(thr, order, overlap)
+        assert eo.with_prefilter().is_active() == eg.with_prefilter().is_active(), (t, desc)
+        used += eo.with_prefilter().is_active()
+        o = eo.with_prefilter().search(hay, opts)
+        g = eg.with_prefilter().search(hay, opts)
+        assert o.tuples() == g.tuples(), (t, order, overlap, desc)
+    assert used > 50
+
+
+@pytest.mark.parametrize("faithful", [True, False])
+def test_cfg1_prefilter_parity(oracle, gpu, faithful, monkeypatch):
+    monkeypatch.setenv("FAC_FAITHFUL", "1" if faithful else "0")
+    cfg = workload.cfg1(1 << 17)
+    eo, eg = _engines(oracle, gpu, cfg)
+    text = bytes(cfg["text"])
+    for opts in (SearchOptions.new().threshold(0.8), SearchOptions.new().threshold(0.8).sorted().non_overlapping()):
+        o, g = eo.with_prefilter().search(text, opts), eg.with_prefilter().search(text, opts)
+        assert len(o) > 50
+        assert o.tuples() == g.tuples()
+        assert g.tuples() == eg.search(text, opts).tuples()   # the reference's own differential (prefilter.rs:465-546)
+
+
+def test_cfg4_sparse_prefilter_parity(oracle, gpu):
+    cfg = workload.cfg4(1 << 20, plant_every=1 << 13)
+    eo, eg = _engines(oracle, gpu, cfg)
+    assert eg.with_prefilter().is_active()
+    text = bytes(cfg["text"])
+    opts = SearchOptions.new().threshold(0.85).sorted().non_overlapping()
+    o = eo.with_prefilter().search(text, opts)
+    g = eg.with_prefilter().search(text, opts)
+    assert len(o) > 20
+    assert o.tuples() == g.tuples()
+    raw_o = eo.with_prefilter().search(text, SearchOptions.new().threshold(0.85))
+    raw_g = eg.with_prefilter().search(text, SearchOptions.new().threshold(0.85))
+    assert raw_o.tuples() == raw_g.tuples()
+
+
 def _beam_cases(seed, trials):
     r = random.Random(seed)
     words = ["saddam", "hussein", "tincidunt", "porta", "vestibulum", "accumsan", "hello", "world", "help", "shell",
