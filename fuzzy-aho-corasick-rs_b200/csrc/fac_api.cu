@@ -143,7 +143,7 @@ struct fac_engine {
     const uint32_t *d_s_bm = nullptr, *d_s_fc = nullptr, *d_s_out_idx = nullptr, *d_s_out2 = nullptr;
     const float *d_s_plen = nullptr, *d_s_plow = nullptr, *d_s_subpen = nullptr;
     const uint8_t *d_s_symof = nullptr;
-    const uint32_t *d_s_gm = nullptr;
+    const uint32_t *d_s_gm = nullptr, *d_s_gm2 = nullptr;
     uint32_t succ_nt = 1024, succ_tile = 1024, succ_stack = 0;
     int smem_optin = 0;
     bool fast_ok = false;  // FAST kernel allowed (fast-path edit ceiling, no beam); FAC_FAITHFUL=1 forces the order-faithful kernel
@@ -245,7 +245,7 @@ fac_status launch_succinct(const fac_engine *E, Workspace *ws, const uint8_t *d_
     const uint32_t nw = nt / 32;
     P.stack_cap = E->succ_stack ? E->succ_stack : (E->host.mef <= 2 ? 128u : 384u);
     P.text_cap = (P.tile + P.lookahead + 16u + 15u) & ~15u;
-    P.gm = E->d_s_gm; P.gm_nodes = S.gm_nodes;
+    P.gm = E->d_s_gm; P.gm_nodes = S.gm_nodes; P.gm2 = E->d_s_gm2; P.gm2_nodes = S.gm2_nodes;
     const size_t fixed = (size_t)nw * (P.stack_cap + SUCC_WQ_CAP) * 16 + 32 * 128 * 4 + (size_t)P.text_cap * 3 + 256;
     const size_t budget = (size_t)E->smem_optin - 1024;  // static shared + reserve
     if (fixed + 16 * 64 > budget) { set_err("succinct kernel: shared-memory budget too small for the configured stack / tile"); return FAC_UNSUPPORTED; }
@@ -1083,6 +1083,7 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
         if ((st = upload(E, S.sub_pen, &E->d_s_subpen)) != FAC_OK) return fail(st);
         if ((st = upload(E, symof, &E->d_s_symof)) != FAC_OK) return fail(st);
         if ((st = upload(E, S.gmask, &E->d_s_gm)) != FAC_OK) return fail(st);
+        if ((st = upload(E, S.gmask2, &E->d_s_gm2)) != FAC_OK) return fail(st);
     }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));

@@ -527,6 +527,30 @@ fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_
                     }
                 }
             }
+            {   // two-deep masks for the shallow nodes (where almost all last-edit expansions happen)
+                const char *ev = getenv("FAC_GM2_NODES");
+                const size_t lim = ev && *ev ? (size_t)atoll(ev) : 2048;
+                S.gm2_nodes = (uint32_t)std::min<size_t>(std::min<size_t>(N, lim), S.gm_nodes);
+                S.gmask2.assign((size_t)std::max<uint32_t>(S.gm2_nodes, 1) * 1024, 0);
+                for (uint32_t h = 0; h < S.gm2_nodes; h++) {
+                    uint32_t bmv = S.bm[h], k = 0;
+                    while (bmv) {
+                        const uint32_t sy = (uint32_t)__builtin_ctz(bmv);
+                        bmv &= bmv - 1;
+                        const uint32_t c = (S.fc_sym[h] & SUCC_FC_MASK) + k++;
+                        uint32_t cb = S.bm[c], kk = 0;
+                        while (cb) {
+                            const uint32_t y1 = (uint32_t)__builtin_ctz(cb);
+                            cb &= cb - 1;
+                            const uint32_t g = (S.fc_sym[c] & SUCC_FC_MASK) + kk++;
+                            uint32_t *row = &S.gmask2[((size_t)h * 32 + y1) * 32];
+                            const bool gout = S.out_idx[g] != FAC_NONE;
+                            if (gout) { for (uint32_t y2 = 0; y2 < 32; y2++) row[y2] |= 1u << sy; }
+                            else { uint32_t gb = S.bm[g]; while (gb) { row[__builtin_ctz(gb)] |= 1u << sy; gb &= gb - 1; } }
+                        }
+                    }
+                }
+            }
             S.ok = true;
         }
     }

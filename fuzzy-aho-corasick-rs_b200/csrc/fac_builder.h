@@ -72,6 +72,9 @@ struct HostSuccinct {
     // grandchild masks of the first gm_nodes BFS nodes (fac_succinct.h): [gm_nodes * 32]
     std::vector<uint32_t> gmask;
     uint32_t gm_nodes = 0;
+    // two-deep masks of the first gm2_nodes BFS nodes: [gm2_nodes * 32 * 32]
+    std::vector<uint32_t> gmask2;
+    uint32_t gm2_nodes = 0;
 };
 
 struct HostAutomaton {

@@ -40,6 +40,8 @@ struct SuccParams {
     const uint4 *tiles;      // optional explicit tiles {start, count (<= tile), text_end, _} (pre-filter slices); null = uniform tiling
     const uint32_t *gm;      // [gm_nodes * 32] grandchild masks (fac_succinct.h)
     uint32_t gm_nodes;
+    const uint32_t *gm2;     // [gm2_nodes * 1024] two-deep masks
+    uint32_t gm2_nodes;
     uint32_t stack_cap;      // states per warp stack
     uint32_t text_cap;       // bytes of the shared text tile (multiple of 16)
     FacCand *cands;
@@ -83,6 +85,15 @@ struct SuccGMDev {
             if (y == SUCC_NOSYM ? c.w != FAC_NONE : ((c.x >> y) & 1u)) m |= 1u << sy;
         }
         return m;
+    }
+};
+struct SuccGM2Dev {
+    const uint32_t *gm2;
+    uint32_t gm2_nodes;
+    SuccGMDev G;
+    __device__ __forceinline__ uint32_t operator()(uint32_t node, uint32_t y1, uint32_t y2) const {
+        if (node < gm2_nodes) return __ldg(&gm2[((size_t)node * 32u + y1) * 32u + y2]);
+        return G(node, y1);
     }
 };
 struct SuccTextDev {
@@ -142,6 +153,7 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
     const SuccConsts K = P.K;
     const SuccRecsDev R{s_rec, P.rec, P.n_smem_nodes};
     const SuccGMDev G{P.gm, P.gm_nodes, R};
+    const SuccGM2Dev G2{P.gm2, P.gm2_nodes, G};
     const SuccOut *out2 = reinterpret_cast<const SuccOut *>(P.out2);
     SuccEmitDev emit{P.cands, P.cand_cap, &P.counters[1]};
     uint4 *const stk = s_stack + (size_t)warp * P.stack_cap;
@@ -288,7 +300,7 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                 if (active) {
                     n_states++;
                     if (rec.w != FAC_NONE) succ_outputs(K, out2, emit, rec.w, pen, sv.z, start, start + (sv.w & 1023u));
-                    succ_make_ctx2(K, T, G, start, text_end, sv.x, rec, pen, sv.z, sv.w, C);
+                    succ_make_ctx2(K, T, G, G2, start, text_end, sv.x, rec, pen, sv.z, sv.w, C);
                     const uint32_t jr = sv.w >> 10;
                     const uint32_t cur_s = (C.packed >> 8) & 0xFFu;
                     if (succ_has_edge(rec, cur_s)) {   // exact transition, search.rs:776-798

@@ -186,9 +186,15 @@ struct SuccCtx2 {
     uint32_t sub_m, del_m;
 };
 
-template <class Text, class GM>
-FAC_HD void succ_make_ctx2(const SuccConsts &K, const Text &T, const GM &G, uint32_t start, uint32_t text_end, uint32_t node, const SuccRec &rec,
-                           float pen, uint32_t cnt, uint32_t pos, SuccCtx2 &C) {
+//
+// Two-deep refinement for the first gm2_nodes nodes:  gm2[node][y1][y2] = { s : c = child(node, s) has edge y1 and
+// g = child(c, y1) has an output or an edge y2 } and gm2[node][y1][31] = { s : ... g has an output }.  A child
+// outside  outm | gm2[node][y1][y2]  walks c -> g and stops there without visiting an output node, i.e. it
+// cannot emit a candidate: dropping it is result-neutral (only the visited-state statistic changes).
+// `G2(node, y1, y2)` returns that set, or the one-deep set gm[node][y1] for nodes beyond the table.
+template <class Text, class GM, class GM2>
+FAC_HD void succ_make_ctx2(const SuccConsts &K, const Text &T, const GM &G, const GM2 &G2, uint32_t start, uint32_t text_end, uint32_t node,
+                           const SuccRec &rec, float pen, uint32_t cnt, uint32_t pos, SuccCtx2 &C) {
     const uint32_t jr = pos >> 10;
     const uint32_t j = start + jr;
     const bool last = (int)fac_edits_of(cnt) + 1 >= K.mef;
@@ -205,9 +211,10 @@ FAC_HD void succ_make_ctx2(const SuccConsts &K, const Text &T, const GM &G, uint
     uint32_t sub_m = 0, del_m = 0;
     if (last) {
         if (rec.x && (in_text || del_ok)) {
+            const uint32_t nxt2_s = (j + 2 < text_end) ? T.sym(j + 2) : SUCC_NOSYM;
             const uint32_t outm = G(node, SUCC_NOSYM);
-            if (in_text) sub_m = (outm | (nxt_s != SUCC_NOSYM ? G(node, nxt_s) : 0u)) & rec.x & ~(1u << cur_s);
-            if (del_ok) del_m = (outm | (cur_s != SUCC_NOSYM ? G(node, cur_s) : 0u)) & rec.x;
+            if (in_text) sub_m = (outm | (nxt_s != SUCC_NOSYM ? G2(node, nxt_s, nxt2_s) : 0u)) & rec.x & ~(1u << cur_s);
+            if (del_ok) del_m = (outm | (cur_s != SUCC_NOSYM ? G2(node, cur_s, nxt_s) : 0u)) & rec.x;
         }
     } else {
         if (in_text) sub_m = rec.x & ~(1u << cur_s);

@@ -195,6 +195,13 @@ struct EmuGM {   // grandchild-mask rows: table for the first gm_nodes nodes, re
         return m;
     }
 };
+struct EmuGM2 {
+    const uint32_t *gm2; uint32_t gm2_nodes; EmuGM G;
+    uint32_t operator()(uint32_t node, uint32_t y1, uint32_t y2) const {
+        if (node < gm2_nodes) return gm2[((size_t)node * 32 + y1) * 32 + y2];
+        return G(node, y1);
+    }
+};
 struct EmuEmit {
     std::vector<FacCand> *v;
     void operator()(uint32_t sg, uint32_t eg, uint32_t pat, float sim, uint32_t cnt) { v->push_back(FacCand{sg, eg, pat, sim, cnt, 0, 0, 0}); }
@@ -220,6 +227,7 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
     K.thr = thr; K.maxpen = FAC_AS_FLOAT(recs[0].z); K.pen_ins = HA.pen_ins; K.pen_del = HA.pen_del; K.pen_swap = HA.pen_swap; K.mef = HA.mef;
     const EmuRecs R{recs.data()};
     const EmuGM G{S.gmask.data(), S.gm_nodes, recs.data()};
+    const EmuGM2 G2{S.gmask2.data(), S.gm2_nodes, G};
     const EmuSText T{hay, S.sym_of, HA.ci};
     const SuccOut *out2 = (const SuccOut *)S.out2.data();
     std::vector<FacCand> cands;
@@ -250,7 +258,7 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
             if (s.pen > FAC_AS_FLOAT(rec.z)) continue;  /*dead*/
             if (rec.w != FAC_NONE) succ_outputs(K, out2, emit, rec.w, s.pen, s.cnt, start, start + (s.pos & 1023u));
             SuccCtx2 C;
-            succ_make_ctx2(K, T, G, start, text_end, s.node, rec, s.pen, s.cnt, s.pos, C);
+            succ_make_ctx2(K, T, G, G2, start, text_end, s.node, rec, s.pen, s.cnt, s.pos, C);
             const bool last = (C.flags & SUCC_F_LAST) != 0;
             const uint32_t jr = s.pos >> 10;
             auto child = [&](const FacState &c) {
