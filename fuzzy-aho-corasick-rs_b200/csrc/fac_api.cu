@@ -12,7 +12,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <mutex>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -114,6 +116,61 @@ struct Workspace {
     }
 };
 
+// ---- pinned result buffers ---------------------------------------------------------------------------
+// Match lists can be hundreds of MB (cfg2: ~0.17 matches per haystack byte).  Copying them into pageable
+// memory runs at a few GB/s; the result vector therefore allocates page-locked memory from a process-wide
+// pool (page-locking is slow, so buffers are recycled) and does not zero-fill on resize.
+struct PinnedPool {
+    std::mutex mu;
+    std::multimap<size_t, void *> free_;
+    std::map<void *, size_t> live_;  // pinned pointers handed out -> class size
+    size_t pooled_bytes = 0;
+    static constexpr size_t kMinPinned = 1u << 20, kMaxPooled = (size_t)6 << 30;
+    void *get(size_t bytes) {
+        if (bytes < kMinPinned) return malloc(bytes ? bytes : 1);
+        size_t cls = kMinPinned;
+        while (cls < bytes) cls <<= 1;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto it = free_.find(cls);
+            if (it != free_.end()) { void *p = it->second; free_.erase(it); pooled_bytes -= cls; live_[p] = cls; return p; }
+        }
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, cls, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return malloc(bytes); }
+        std::lock_guard<std::mutex> g(mu);
+        live_[p] = cls;
+        return p;
+    }
+    void put(void *p) {
+        if (!p) return;
+        size_t cls = 0;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto it = live_.find(p);
+            if (it != live_.end()) {
+                cls = it->second; live_.erase(it);
+                if (pooled_bytes + cls <= kMaxPooled) { free_.emplace(cls, p); pooled_bytes += cls; return; }
+            }
+        }
+        if (cls) cudaFreeHost(p); else free(p);
+    }
+};
+PinnedPool &pinned_pool() { static PinnedPool *p = new PinnedPool(); return *p; }
+
+template <class T>
+struct PinnedAlloc {
+    using value_type = T;
+    PinnedAlloc() = default;
+    template <class U> PinnedAlloc(const PinnedAlloc<U> &) {}
+    T *allocate(size_t n) { T *p = (T *)pinned_pool().get(n * sizeof(T)); if (!p) throw std::bad_alloc(); return p; }
+    void deallocate(T *p, size_t) { pinned_pool().put(p); }
+    template <class U> void construct(U *) {}                                   // resize() without zero-fill
+    template <class U, class... A> void construct(U *p, A &&...a) { ::new ((void *)p) U(std::forward<A>(a)...); }
+    template <class U> bool operator==(const PinnedAlloc<U> &) const { return true; }
+    template <class U> bool operator!=(const PinnedAlloc<U> &) const { return false; }
+};
+using MatchVec = std::vector<fac_match, PinnedAlloc<fac_match>>;
+
 }  // namespace
 
 struct fac_engine {
@@ -152,7 +209,7 @@ struct fac_engine {
 };
 
 struct fac_matches {
-    std::vector<fac_match> v;
+    MatchVec v;
     SearchStats stats;
 };
 
@@ -337,6 +394,8 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
     const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)E->sm_count * E->ctas_per_sm, n_tiles);
     CKS(ensure_scratch(E, ws, (uint32_t)E->sm_count * E->ctas_per_sm, E->qcap));
     uint32_t cand_cap = (uint32_t)std::max<size_t>(ws->cands.cap / sizeof(FacCand), 1u << 20);
+    // dense-match workloads emit ~0.2-0.4 candidates per start window: size the first attempt so it need not be redone
+    if (R.fast && !explicit_tiles) cand_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(cand_cap, n_windows_total / 2 + (1u << 20)), 0x7FFFFFF0u);
     CKS(ws->cands.ensure((size_t)cand_cap * sizeof(FacCand)));
     cand_cap = (uint32_t)std::min<size_t>(ws->cands.cap / sizeof(FacCand), 0x7FFFFFF0u);
     CKS(ws->counters.ensure(16 * 8));
@@ -640,7 +699,7 @@ fac_status apply_device(const fac_engine *E, Workspace *ws, uint32_t n, int orde
 }
 
 // WMatch list -> fac_match on the host (optionally dropping matches a stream window does not own).
-fac_status finalize_and_fetch(Workspace *ws, uint32_t n, const FacWindow *d_windows, bool filter_commit, std::vector<fac_match> &out,
+fac_status finalize_and_fetch(Workspace *ws, uint32_t n, const FacWindow *d_windows, bool filter_commit, MatchVec &out,
                               SearchStats &stats) {
     cudaStream_t s = ws->stream;
     if (n == 0) return FAC_OK;
@@ -875,7 +934,7 @@ fac_status prefilter_slices(const fac_engine *E, Workspace *ws, const uint8_t *d
 // The whole-haystack search on device-resident text: classification, (K1), K3 over segments of
 // start windows, reduction, apply.  Restricts start windows to the byte range [own_begin, own_end).
 fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_text, uint64_t len, float thr, int order, int overlap,
-                           uint64_t own_begin, uint64_t own_end, uint64_t base, uint64_t commit, bool apply, std::vector<fac_match> &out, SearchStats &stats,
+                           uint64_t own_begin, uint64_t own_end, uint64_t base, uint64_t commit, bool apply, MatchVec &out, SearchStats &stats,
                            bool use_prefilter = false) {
     cudaStream_t s = ws->stream;
     if (len == 0) return FAC_OK;

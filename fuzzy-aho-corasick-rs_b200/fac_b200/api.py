@@ -378,6 +378,19 @@ class StreamMatch:
 # ---------------------------------------------------------------------------------------------
 # Backend: the thin layer that talks to the C ABI.  The GPU backend is the only product backend.
 # ---------------------------------------------------------------------------------------------
+class _MatchesOwner:
+    """Keeps a fac_matches handle alive for as long as a zero-copy view of its records exists."""
+
+    def __init__(self, lib, mh):
+        self.lib, self.mh = lib, mh
+
+    def __del__(self):
+        try:
+            self.lib.fac_matches_free(self.mh)
+        except Exception:
+            pass
+
+
 class GpuBackend:
     name = "libfacgpu"
 
@@ -413,15 +426,22 @@ class GpuBackend:
         return self.lib.fac_engine_num_nodes(h)
 
     def _take(self, mh):
+        """fac_matches handle -> (ctypes array of fac_match, stats).  Large results are exposed in place
+        (the array aliases the library's pinned buffer and frees the handle when it is collected), small
+        ones are copied; either way the caller sees an ordinary `fac_match * n` array."""
         n = self.lib.fac_matches_len(mh)
         data = self.lib.fac_matches_data(mh)
-        arr = (fac_match * n)()
-        if n:
-            C.memmove(arr, data, n * C.sizeof(fac_match))
         stats = {"states_pushed": int(self.lib.fac_matches_states_pushed(mh)),
                  "device_ms": float(self.lib.fac_matches_device_ms(mh)),
                  "expand_ms": float(self.lib.fac_matches_expand_ms(mh)),
                  "kernel_launches": int(self.lib.fac_matches_kernel_launches(mh))}
+        if n >= (1 << 15):
+            arr = (fac_match * n).from_address(C.cast(data, C.c_void_p).value)
+            arr._owner = _MatchesOwner(self.lib, mh)
+            return arr, stats
+        arr = (fac_match * n)()
+        if n:
+            C.memmove(arr, data, n * C.sizeof(fac_match))
         self.lib.fac_matches_free(mh)
         return arr, stats
 
