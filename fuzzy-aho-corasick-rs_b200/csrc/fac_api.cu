@@ -125,15 +125,19 @@ struct PinnedPool {
     std::multimap<size_t, void *> free_;
     std::map<void *, size_t> live_;  // pinned pointers handed out -> class size
     size_t pooled_bytes = 0;
-    static constexpr size_t kMinPinned = 1u << 20, kMaxPooled = (size_t)6 << 30;
+    static constexpr size_t kMinPinned = 1u << 20, kMaxPooled = (size_t)24 << 30, kBig = (size_t)256 << 20;
     void *get(size_t bytes) {
         if (bytes < kMinPinned) return malloc(bytes ? bytes : 1);
         size_t cls = kMinPinned;
-        while (cls < bytes) cls <<= 1;
+        if (bytes >= kBig) cls = (bytes + kBig - 1) / kBig * kBig;   // big lists: 256 MiB granularity
+        else while (cls < bytes) cls <<= 1;
         {
             std::lock_guard<std::mutex> g(mu);
-            auto it = free_.find(cls);
-            if (it != free_.end()) { void *p = it->second; free_.erase(it); pooled_bytes -= cls; live_[p] = cls; return p; }
+            auto it = free_.lower_bound(cls);   // any recycled buffer that is large enough (and not wastefully so)
+            if (it != free_.end() && it->first <= cls + cls / 2 + kBig) {
+                void *p = it->second; const size_t got = it->first;
+                free_.erase(it); pooled_bytes -= got; live_[p] = got; return p;
+            }
         }
         void *p = nullptr;
         if (cudaHostAlloc(&p, cls, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return malloc(bytes); }
@@ -273,8 +277,14 @@ fac_status launch_expand(const ExpandParams &P, uint32_t grid, size_t smem, cuda
 // ---- succinct fast kernel launch (fac_succinct.cuh) ----
 template <int NT>
 fac_status launch_succ_t(const SuccParams &P, uint32_t grid, size_t smem, cudaStream_t s) {
-    CK(cudaFuncSetAttribute(k_expand_succinct<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_expand_succinct<NT><<<grid, NT, smem, s>>>(P);
+    static const int inline_walk = env_int("FAC_SUCC_INLINE_WALK", 0);
+    if (inline_walk) {
+        CK(cudaFuncSetAttribute(k_expand_succinct<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_expand_succinct<NT, true><<<grid, NT, smem, s>>>(P);
+    } else {
+        CK(cudaFuncSetAttribute(k_expand_succinct<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_expand_succinct<NT, false><<<grid, NT, smem, s>>>(P);
+    }
     CK(cudaGetLastError());
     return FAC_OK;
 }

@@ -126,7 +126,7 @@ __device__ __forceinline__ void succ_warp_push(uint4 *stk, uint32_t &top, bool p
 
 #define SUCC_WQ_CAP 96u
 
-template <int NT>
+template <int NT, bool INLINE_WALK>
 __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant__ SuccParams P) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -257,7 +257,9 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                     const bool ok = it < total && succ_item2(K, s_subpen, O, r, c);
                     const bool to_walk = ok && (O.flags & SUCC_F_LAST);
                     const bool to_stack = ok && !(O.flags & SUCC_F_LAST);
-                    if (__any_sync(0xFFFFFFFFu, to_walk)) succ_warp_push(wq, wn, to_walk, c);
+                    if (INLINE_WALK) {
+                        if (to_walk) n_states += succ_walk(K, R, out2, T, emit, start, text_end, R(c.node), c.pen, c.cnt, c.pos >> 10, c.pos & 1023u);
+                    } else if (__any_sync(0xFFFFFFFFu, to_walk)) succ_warp_push(wq, wn, to_walk, c);
                     if (__any_sync(0xFFFFFFFFu, to_stack)) succ_warp_push(stk, top, to_stack, c);
                     continue;
                 }
@@ -273,14 +275,17 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                 const bool last = (int)fac_edits_of(sv.z) + 1 >= K.mef;
                 // worst-case stack pushes of this state: only the exact child when its edit-children are exhausted
                 const uint32_t ub = dead ? 0u : (last ? 1u : 2u * (uint32_t)__popc(rec.x) + 3u);
-                uint32_t incl = ub;
+                uint32_t n_pop = navail;
+                if (__any_sync(0xFFFFFFFFu, ub > 1u)) {  // states on their last edit push at most the exact child: always fits
+                    uint32_t incl = ub;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                    if (lane >= (uint32_t)d) incl += v;
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                        if (lane >= (uint32_t)d) incl += v;
+                    }
+                    const uint32_t viol = __ballot_sync(0xFFFFFFFFu, has && (incl > cap - top + lane + 1u));
+                    if (viol) n_pop = (uint32_t)(__ffs(viol) - 1);
                 }
-                const uint32_t viol = __ballot_sync(0xFFFFFFFFu, has && (incl > cap - top + lane + 1u));
-                const uint32_t n_pop = viol ? (uint32_t)(__ffs(viol) - 1) : navail;
                 if (n_pop == 0) {  // the top state alone does not fit: give the window to the faithful kernel
                     if (lane == 0) {
                         atomicOr(&P.dirty[(start - P.seg_begin) >> 5], 1u << ((start - P.seg_begin) & 31u));
@@ -313,6 +318,11 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                 succ_warp_push(stk, top, p_ex, c_ex);
                 {
                     const bool lw = active && last;
+                    if (INLINE_WALK) {
+                        if (p_sw && lw) n_states += succ_walk(K, R, out2, T, emit, start, text_end, R(c_sw.node), c_sw.pen, c_sw.cnt, c_sw.pos >> 10, c_sw.pos & 1023u);
+                        if (p_in && lw) n_states += succ_walk(K, R, out2, T, emit, start, text_end, rec, c_in.pen, c_in.cnt, c_in.pos >> 10, c_in.pos & 1023u);
+                        if (lw) p_sw = p_in = false;
+                    }
                     if (__any_sync(0xFFFFFFFFu, p_sw && lw)) succ_warp_push(wq, wn, p_sw && lw, c_sw);
                     if (__any_sync(0xFFFFFFFFu, p_sw && !lw)) succ_warp_push(stk, top, p_sw && !lw, c_sw);
                     if (__any_sync(0xFFFFFFFFu, p_in && lw)) succ_warp_push(wq, wn, p_in && lw, c_in);

@@ -242,6 +242,46 @@ def test_cfg4_sparse_prefilter_parity(oracle, gpu):
     assert raw_o.tuples() == raw_g.tuples()
 
 
+MATCH_DT = np.dtype([("start", "<u8"), ("end", "<u8"), ("pat", "<u4"), ("simbits", "<u4"), ("ins", "u1"), ("del", "u1"),
+                     ("sub", "u1"), ("swp", "u1"), ("edits", "u1"), ("pad", "u1", (3,))])
+
+
+def test_cfg2_32MiB_properties_and_sampled_parity(oracle, gpu):
+    """BASELINE-size behaviour through size-independent properties plus oracle parity on sampled regions:
+    the oracle needs ~4 s per KiB on this configuration, so it checks 150 random 384-byte regions
+    (region + halo searched as its own haystack, ownership by start -- the reference's own streaming rule,
+    src/stream.rs:262-297) against the GPU's whole-haystack result."""
+    nbytes = 32 << 20
+    cfg = workload.cfg2(nbytes, 10000)
+    eo, eg = _engines(oracle, gpu, cfg)
+    text = cfg["text"]
+    arr, stats = gpu.search_host_ptr(eg._h, text.ctypes.data, nbytes, 0.8, 0, 0, False)
+    m = np.frombuffer(arr, dtype=MATCH_DT)
+    assert len(m) > 4_000_000
+    # properties: keys unique and ascending (Unsorted == ascending (start, end, pattern)), bounds, limits, threshold
+    key_lt = (m["start"][:-1] < m["start"][1:]) | ((m["start"][:-1] == m["start"][1:]) & (
+        (m["end"][:-1] < m["end"][1:]) | ((m["end"][:-1] == m["end"][1:]) & (m["pat"][:-1] < m["pat"][1:]))))
+    assert key_lt.all()
+    assert (m["end"] <= nbytes).all() and (m["start"] <= m["end"]).all()
+    assert (m["end"] - m["start"] <= eg.max_match_graphemes()).all()
+    assert (m["edits"] <= 2).all() and (m["ins"].astype(int) + m["del"] + m["sub"] + m["swp"] == m["edits"]).all()
+    sim = m["simbits"].view("<f4")
+    assert (sim >= np.float32(0.8)).all() and (sim <= np.float32(1.0)).all()
+    # sampled parity
+    rng = np.random.default_rng(7)
+    halo = eg.max_match_graphemes() + 1
+    region = 384
+    for p in [0, nbytes - region] + [int(x) for x in rng.integers(0, nbytes - region, 148)]:
+        end = min(nbytes, p + region + halo)
+        o, _ = oracle.search(eo._h, bytes(text[p:end]), 0.8, 0, 0, False)
+        want = sorted((x.start + p, x.end + p, x.pattern_index, C.c_uint32.from_buffer(C.c_float(x.similarity)).value,
+                       x.insertions, x.deletions, x.substitutions, x.swaps, x.edits) for x in o if x.start < region)
+        lo, hi = np.searchsorted(m["start"], [p, p + region])
+        got = sorted((int(r["start"]), int(r["end"]), int(r["pat"]), int(r["simbits"]), int(r["ins"]), int(r["del"]),
+                      int(r["sub"]), int(r["swp"]), int(r["edits"])) for r in m[lo:hi])
+        assert got == want, p
+
+
 def _beam_cases(seed, trials):
     r = random.Random(seed)
     words = ["saddam", "hussein", "tincidunt", "porta", "vestibulum", "accumsan", "hello", "world", "help", "shell",
