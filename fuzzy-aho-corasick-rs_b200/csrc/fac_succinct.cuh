@@ -64,7 +64,10 @@ struct SuccRecsDev {
     const uint4 *s, *g;
     uint32_t ns;
     __device__ __forceinline__ SuccRec operator()(uint32_t n) const {
-        const uint4 v = n < ns ? s[n] : __ldg(&g[n]);
+        // one generic 128-bit load through a selected pointer: no divergent branch between the shared-memory
+        // copy of the shallow records and the L2-resident rest
+        const uint4 *p = n < ns ? s + n : g + n;
+        const uint4 v = *p;
         SuccRec r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
         return r;
     }

@@ -195,31 +195,24 @@ struct SuccCtx2 {
 template <class Text, class GM, class GM2>
 FAC_HD void succ_make_ctx2(const SuccConsts &K, const Text &T, const GM &G, const GM2 &G2, uint32_t start, uint32_t text_end, uint32_t node,
                            const SuccRec &rec, float pen, uint32_t cnt, uint32_t pos, SuccCtx2 &C) {
+    // Text contract: T.sym(j) == SUCC_NOSYM and T.byte(j) == 0 for text_end <= j <= start + look-ahead, so the
+    // three look-ahead symbols are read unconditionally (few branches: the kernel is issue-bound).
     const uint32_t jr = pos >> 10;
     const uint32_t j = start + jr;
     const bool last = (int)fac_edits_of(cnt) + 1 >= K.mef;
     const bool in_text = j < text_end;
-    uint32_t cur_b = 0, cur_s = SUCC_NOSYM, nxt_s = SUCC_NOSYM, flags = 0;
-    if (last) flags |= SUCC_F_LAST;
-    if (in_text) {
-        flags |= SUCC_F_IN_TEXT;
-        cur_b = T.byte(j); cur_s = T.sym(j);
-        if (j + 1 < text_end) { nxt_s = T.sym(j + 1); flags |= SUCC_F_HAS_NXT; }
-    }
+    const uint32_t cur_b = T.byte(j), cur_s = T.sym(j), nxt_s = T.sym(j + 1), nxt2_s = T.sym(j + 2);
     const bool del_ok = K.pen_del <= FAC_SUB(K.maxpen, pen);  // search.rs:1035
-    if (del_ok) flags |= SUCC_F_DEL;
-    uint32_t sub_m = 0, del_m = 0;
+    const uint32_t flags = (last ? SUCC_F_LAST : 0u) | (in_text ? SUCC_F_IN_TEXT : 0u) | (j + 1 < text_end ? SUCC_F_HAS_NXT : 0u) |
+                           (del_ok ? SUCC_F_DEL : 0u);
+    uint32_t keep_sub = 0xFFFFFFFFu, keep_del = 0xFFFFFFFFu;  // states not on their last edit keep every child
     if (last) {
-        if (rec.x && (in_text || del_ok)) {
-            const uint32_t nxt2_s = (j + 2 < text_end) ? T.sym(j + 2) : SUCC_NOSYM;
-            const uint32_t outm = G(node, SUCC_NOSYM);
-            if (in_text) sub_m = (outm | (nxt_s != SUCC_NOSYM ? G2(node, nxt_s, nxt2_s) : 0u)) & rec.x & ~(1u << cur_s);
-            if (del_ok) del_m = (outm | (cur_s != SUCC_NOSYM ? G2(node, cur_s, nxt_s) : 0u)) & rec.x;
-        }
-    } else {
-        if (in_text) sub_m = rec.x & ~(1u << cur_s);
-        if (del_ok) del_m = rec.x;
+        const uint32_t outm = G(node, SUCC_NOSYM);
+        keep_sub = outm | (nxt_s != SUCC_NOSYM ? G2(node, nxt_s, nxt2_s) : 0u);
+        keep_del = outm | (cur_s != SUCC_NOSYM ? G2(node, cur_s, nxt_s) : 0u);
     }
+    const uint32_t sub_m = in_text ? (rec.x & keep_sub & ~(1u << cur_s)) : 0u;
+    const uint32_t del_m = del_ok ? (rec.x & keep_del) : 0u;
     C.bm = rec.x; C.fc = rec.y; C.pen = pen; C.cnt = cnt; C.pos = pos;
     C.packed = cur_b | (cur_s << 8) | (nxt_s << 16);
     C.flags = flags; C.sub_m = sub_m; C.del_m = del_m;

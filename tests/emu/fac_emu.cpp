@@ -176,10 +176,10 @@ int emu_search(const fac_config *cfg, const fac_pattern *pats, size_t np, const 
 // kernel, a plain LIFO stack instead of the warp stack machine, the order-independent reduction with
 // tie detection, and the faithful emulation above for tied ("dirty") windows. ----
 struct EmuRecs { const SuccRec *r; SuccRec operator()(uint32_t n) const { return r[n]; } };
-struct EmuSText {
-    const uint8_t *b; const uint8_t *symof; bool ci;
-    uint32_t byte(uint32_t j) const { const uint32_t c = b[j]; return (ci && c >= 'A' && c <= 'Z') ? c + 32u : c; }
-    uint32_t sym(uint32_t j) const { return symof[byte(j)]; }
+struct EmuSText {   // bytes / symbols of the haystack; positions past the end read as (0, SUCC_NOSYM) like the kernel's padded tile
+    const uint8_t *b; const uint8_t *symof; bool ci; uint32_t n;
+    uint32_t byte(uint32_t j) const { if (j >= n) return 0; const uint32_t c = b[j]; return (ci && c >= 'A' && c <= 'Z') ? c + 32u : c; }
+    uint32_t sym(uint32_t j) const { return j >= n ? SUCC_NOSYM : symof[byte(j)]; }
 };
 struct EmuGM {   // grandchild-mask rows: table for the first gm_nodes nodes, recomputed from the children beyond
     const uint32_t *gm; uint32_t gm_nodes; const SuccRec *r;
@@ -228,7 +228,7 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
     const EmuRecs R{recs.data()};
     const EmuGM G{S.gmask.data(), S.gm_nodes, recs.data()};
     const EmuGM2 G2{S.gmask2.data(), S.gm2_nodes, G};
-    const EmuSText T{hay, S.sym_of, HA.ci};
+    const EmuSText T{hay, S.sym_of, HA.ci, n};
     const SuccOut *out2 = (const SuccOut *)S.out2.data();
     std::vector<FacCand> cands;
     EmuEmit emit{&cands};

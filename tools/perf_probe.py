@@ -10,7 +10,7 @@ import torch  # noqa: E402
 from fac_b200 import GpuBackend, SearchOptions, workload  # noqa: E402
 
 
-def probe(name, cfg, reps=3):
+def probe(name, cfg, reps=3, prefilter=False, order=0, overlap=0):
     gpu = GpuBackend()
     t0 = time.time()
     eng = workload.build_engine(cfg, gpu)
@@ -19,7 +19,7 @@ def probe(name, cfg, reps=3):
     d = torch.from_numpy(text).cuda()
     best = None
     for _ in range(reps):
-        arr, st = gpu.search_device(eng._h, d.data_ptr(), d.numel(), cfg["threshold"], 0, 0, False)
+        arr, st = gpu.search_device(eng._h, d.data_ptr(), d.numel(), cfg["threshold"], order, overlap, prefilter)
         if best is None or st["device_ms"] < best["device_ms"]:
             best = st
             nm = len(arr)
@@ -35,5 +35,8 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "cfg1"):
         probe("cfg1", workload.cfg1(int(os.environ.get("CFG1_BYTES", 16 << 20))))
+    if which in ("cfg4",):
+        c4 = workload.cfg4(int(os.environ.get("CFG4_BYTES", 256 << 20)))
+        probe("cfg4+prefilter(sorted,non_overlapping)", c4, prefilter=True, order=1, overlap=1)
     if which in ("all", "cfg2"):
         probe("cfg2", workload.cfg2(int(os.environ.get("CFG2_BYTES", 1 << 20)), int(os.environ.get("CFG2_PATTERNS", 10000))))
