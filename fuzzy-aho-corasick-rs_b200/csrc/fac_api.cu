@@ -277,14 +277,8 @@ fac_status launch_expand(const ExpandParams &P, uint32_t grid, size_t smem, cuda
 // ---- succinct fast kernel launch (fac_succinct.cuh) ----
 template <int NT>
 fac_status launch_succ_t(const SuccParams &P, uint32_t grid, size_t smem, cudaStream_t s) {
-    static const int inline_walk = env_int("FAC_SUCC_INLINE_WALK", 0);
-    if (inline_walk) {
-        CK(cudaFuncSetAttribute(k_expand_succinct<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_expand_succinct<NT, true><<<grid, NT, smem, s>>>(P);
-    } else {
-        CK(cudaFuncSetAttribute(k_expand_succinct<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_expand_succinct<NT, false><<<grid, NT, smem, s>>>(P);
-    }
+    CK(cudaFuncSetAttribute(k_expand_succinct<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_expand_succinct<NT><<<grid, NT, smem, s>>>(P);
     CK(cudaGetLastError());
     return FAC_OK;
 }

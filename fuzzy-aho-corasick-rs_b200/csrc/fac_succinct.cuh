@@ -129,7 +129,7 @@ __device__ __forceinline__ void succ_warp_push(uint4 *stk, uint32_t &top, bool p
 
 #define SUCC_WQ_CAP 96u
 
-template <int NT, bool INLINE_WALK>
+template <int NT>
 __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant__ SuccParams P) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -260,9 +260,7 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                     const bool ok = it < total && succ_item2(K, s_subpen, O, r, c);
                     const bool to_walk = ok && (O.flags & SUCC_F_LAST);
                     const bool to_stack = ok && !(O.flags & SUCC_F_LAST);
-                    if (INLINE_WALK) {
-                        if (to_walk) n_states += succ_walk(K, R, out2, T, emit, start, text_end, R(c.node), c.pen, c.cnt, c.pos >> 10, c.pos & 1023u);
-                    } else if (__any_sync(0xFFFFFFFFu, to_walk)) succ_warp_push(wq, wn, to_walk, c);
+                    if (__any_sync(0xFFFFFFFFu, to_walk)) succ_warp_push(wq, wn, to_walk, c);
                     if (__any_sync(0xFFFFFFFFu, to_stack)) succ_warp_push(stk, top, to_stack, c);
                     continue;
                 }
@@ -321,11 +319,6 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                 succ_warp_push(stk, top, p_ex, c_ex);
                 {
                     const bool lw = active && last;
-                    if (INLINE_WALK) {
-                        if (p_sw && lw) n_states += succ_walk(K, R, out2, T, emit, start, text_end, R(c_sw.node), c_sw.pen, c_sw.cnt, c_sw.pos >> 10, c_sw.pos & 1023u);
-                        if (p_in && lw) n_states += succ_walk(K, R, out2, T, emit, start, text_end, rec, c_in.pen, c_in.cnt, c_in.pos >> 10, c_in.pos & 1023u);
-                        if (lw) p_sw = p_in = false;
-                    }
                     if (__any_sync(0xFFFFFFFFu, p_sw && lw)) succ_warp_push(wq, wn, p_sw && lw, c_sw);
                     if (__any_sync(0xFFFFFFFFu, p_sw && !lw)) succ_warp_push(stk, top, p_sw && !lw, c_sw);
                     if (__any_sync(0xFFFFFFFFu, p_in && lw)) succ_warp_push(wq, wn, p_in && lw, c_in);

@@ -14,8 +14,8 @@
 // and  child(n, sym) = first_child + popc(x & below(sym)).  There is no edge array and no hash
 // table: the exact transition (Node::find_transition_char_no_mappings, src/structs.rs:512-519) is a
 // bit test + popcount, and the last-edit dead-end filter (search.rs:839-847, 1005-1007, 1057-1063:
-// "child has an output or a single-byte edge equal to the next text char") reads only the child's
-// record.
+// "child has an output or a single-byte edge equal to the next text char") is answered for all
+// children of a node at once by precomputed masks (below).
 //
 // The expansion is order-independent: candidates are reduced by maximum similarity and ties
 // between different edit-count vectors are detected and redone by the order-faithful kernel
@@ -84,90 +84,7 @@ FAC_HD uint32_t succ_walk(const SuccConsts &K, const Recs &R, const SuccOut *out
     return steps;
 }
 
-// What the edge-independent part of a popped state needs (search.rs:742-770, 994-1008, 1035-1045).
 enum : uint32_t { SUCC_F_IN_TEXT = 1u, SUCC_F_LAST = 2u, SUCC_F_DEL = 4u, SUCC_F_HAS_NXT = 8u };
-struct SuccCtx {
-    uint32_t fc;       // rec.y (first child | in-symbol)
-    float pen;
-    uint32_t cnt, pos;
-    uint32_t packed;   // cur byte | cur sym << 8 | next sym << 16 | exact child rank << 24 (0xFF = none)
-    uint32_t flags;
-};
-
-template <class Text>
-FAC_HD void succ_make_ctx(const SuccConsts &K, const Text &T, uint32_t start, uint32_t text_end, const SuccRec &rec, float pen, uint32_t cnt,
-                          uint32_t pos, SuccCtx &C) {
-    const uint32_t jr = pos >> 10;
-    const uint32_t j = start + jr;
-    const int edits = (int)fac_edits_of(cnt);
-    const bool last = edits + 1 >= K.mef;
-    const bool in_text = j < text_end;
-    uint32_t cur_b = 0, cur_s = SUCC_NOSYM, nxt_s = SUCC_NOSYM, ex = 0xFFu, flags = 0;
-    if (last) flags |= SUCC_F_LAST;
-    if (in_text) {
-        flags |= SUCC_F_IN_TEXT;
-        cur_b = T.byte(j); cur_s = T.sym(j);
-        if (j + 1 < text_end) { nxt_s = T.sym(j + 1); flags |= SUCC_F_HAS_NXT; }
-        if (succ_has_edge(rec, cur_s)) ex = FAC_POPC(rec.x & ((1u << cur_s) - 1u));
-    }
-    if (K.pen_del <= FAC_SUB(K.maxpen, pen)) flags |= SUCC_F_DEL;  // search.rs:1035 (edits < MEF holds for every popped state)
-    C.fc = rec.y; C.pen = pen; C.cnt = cnt; C.pos = pos;
-    C.packed = cur_b | (cur_s << 8) | (nxt_s << 16) | (ex << 24);
-    C.flags = flags;
-}
-
-// Swap (search.rs:935-989): node -text[j+1]-> x -text[j]-> n2; matched_start unchanged.
-template <class Recs>
-FAC_HD bool succ_swap(const SuccConsts &K, const Recs &R, const SuccRec &rec, const SuccCtx &C, SuccRec &rec2, FacState &out) {
-    if ((C.flags & (SUCC_F_IN_TEXT | SUCC_F_HAS_NXT)) != (SUCC_F_IN_TEXT | SUCC_F_HAS_NXT)) return false;
-    if (!(K.pen_swap <= FAC_SUB(K.maxpen, C.pen))) return false;
-    const uint32_t cur_s = (C.packed >> 8) & 0xFFu, nxt_s = (C.packed >> 16) & 0xFFu;
-    if (!succ_has_edge(rec, nxt_s)) return false;
-    const SuccRec rx = R(succ_child(rec, nxt_s));
-    if (!succ_has_edge(rx, cur_s)) return false;
-    const uint32_t n2 = succ_child(rx, cur_s);
-    rec2 = R(n2);
-    const uint32_t jr = C.pos >> 10;
-    out.node = n2; out.pen = FAC_ADD(C.pen, K.pen_swap); out.cnt = C.cnt + 0x1000000u; out.pos = succ_make_pos(jr + 2, jr + 2);
-    return true;
-}
-
-// Insertion (search.rs:994-1029): forbidden before anything is consumed; matched_end unchanged.
-FAC_HD bool succ_ins(const SuccConsts &K, const SuccRec &rec, const SuccCtx &C, uint32_t node, FacState &out) {
-    if (!(C.flags & SUCC_F_IN_TEXT)) return false;
-    const uint32_t jr = C.pos >> 10, mr = C.pos & 1023u;
-    if (mr == 0 && jr == 0) return false;
-    if (!(K.pen_ins <= FAC_SUB(K.maxpen, C.pen))) return false;
-    if ((C.flags & SUCC_F_LAST) && rec.w == FAC_NONE) {  // dead-end filter on the current node
-        if (!(C.flags & SUCC_F_HAS_NXT) || !succ_has_edge(rec, (C.packed >> 16) & 0xFFu)) return false;
-    }
-    out.node = node; out.pen = FAC_ADD(C.pen, K.pen_ins); out.cnt = C.cnt + 1u; out.pos = succ_make_pos(jr + 1, mr);
-    return true;
-}
-
-// Substitution through child rank k (search.rs:814-874).  `crec` is the child's record.
-FAC_HD bool succ_sub(const SuccConsts &K, const float *sub_pen, const SuccCtx &C, uint32_t k, const SuccRec &crec, FacState &out) {
-    if (!(C.flags & SUCC_F_IN_TEXT)) return false;
-    if (k == (C.packed >> 24)) return false;  // the exact edge
-    const float pp = sub_pen[(crec.y >> 27) * 128u + (C.packed & 0x7Fu)];  // +inf when similarity < min_symbol_similarity
-    if (pp > FAC_SUB(K.maxpen, C.pen)) return false;
-    if (C.flags & SUCC_F_LAST) {
-        if (crec.w == FAC_NONE && (!(C.flags & SUCC_F_HAS_NXT) || !succ_has_edge(crec, (C.packed >> 16) & 0xFFu))) return false;
-    }
-    const uint32_t jr = C.pos >> 10;
-    out.node = (C.fc & SUCC_FC_MASK) + k; out.pen = FAC_ADD(C.pen, pp); out.cnt = C.cnt + 0x10000u; out.pos = succ_make_pos(jr + 1, jr + 1);
-    return true;
-}
-
-// Deletion through child rank k (search.rs:1035-1089); allowed at j == text_end.
-FAC_HD bool succ_del(const SuccConsts &K, const SuccCtx &C, uint32_t k, const SuccRec &crec, FacState &out) {
-    if (!(C.flags & SUCC_F_DEL)) return false;
-    if (C.flags & SUCC_F_LAST) {
-        if (crec.w == FAC_NONE && (!(C.flags & SUCC_F_IN_TEXT) || !succ_has_edge(crec, (C.packed >> 8) & 0xFFu))) return false;
-    }
-    out.node = (C.fc & SUCC_FC_MASK) + k; out.pen = FAC_ADD(C.pen, K.pen_del); out.cnt = C.cnt + 0x100u; out.pos = C.pos;
-    return true;
-}
 
 // ---- survivor masks -------------------------------------------------------------------------------
 // For a state on its last edit the dead-end filter keeps a child c iff
@@ -251,7 +168,9 @@ FAC_HD bool succ_item2(const SuccConsts &K, const float *sub_pen, const SuccCtx2
     return !(is_sub && pp > FAC_SUB(K.maxpen, C.pen));
 }
 
-// Swap / insertion with the SuccCtx2 layout (same rules as succ_swap / succ_ins above).
+// Swap (search.rs:935-989: node -text[j+1]-> x -text[j]-> n2, matched_start unchanged) and insertion
+// (search.rs:994-1029: forbidden before anything is consumed, matched_end unchanged, dead-end filter on the
+// current node when this is the last edit).
 template <class Recs>
 FAC_HD bool succ_swap2(const SuccConsts &K, const Recs &R, const SuccCtx2 &C, FacState &out) {
     if ((C.flags & (SUCC_F_IN_TEXT | SUCC_F_HAS_NXT)) != (SUCC_F_IN_TEXT | SUCC_F_HAS_NXT)) return false;
