@@ -193,8 +193,8 @@ struct fac_engine {
     uint32_t lookahead = 0;
     uint32_t default_tile = 0;  // 0 = adaptive
     uint32_t qcap = 1u << 17;
-    uint32_t smem_tab = 4096;
-    int ctas_per_sm = 2;
+    uint32_t smem_tab = 1024;
+    int ctas_per_sm = 6;
     int use_tma = 1;
     // bitap pre-filter (fac_bitap.cuh)
     const uint64_t *d_bp_mask = nullptr;
@@ -1155,8 +1155,8 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
     E->lookahead = (uint32_t)H.max_match_graphemes + H.max_map_hay + 3;
     E->default_tile = (uint32_t)env_int("FAC_TILE", 0);
     E->qcap = (uint32_t)env_int("FAC_QCAP", 1 << 17);
-    E->smem_tab = (uint32_t)env_int("FAC_SMEM_TAB", 4096);
-    E->ctas_per_sm = env_int("FAC_CTAS_PER_SM", 4);
+    E->smem_tab = (uint32_t)env_int("FAC_SMEM_TAB", 1024);
+    E->ctas_per_sm = env_int("FAC_CTAS_PER_SM", 6);
     E->use_tma = env_int("FAC_USE_TMA", 1);
     E->fast_ok = H.mef != 255 && H.beam_width == 0 && !H.has_auto_beam && env_int("FAC_FAITHFUL", 0) == 0;
     E->succ_ok = E->fast_ok && H.succ.ok && env_int("FAC_SUCCINCT", 1) != 0;
