@@ -170,6 +170,97 @@ def cfg4(nbytes=4_000_000_000, n_patterns=100, seed=0xFAC00004, plant_every=1 <<
             "threshold": 0.85, "text": text, "name": "cfg4: %d weighted patterns with per-pattern limits, sparse text" % n_patterns}
 
 
+CYR = "абвгдежзийклмнопрстуфхцчшщыьэюя"
+CJK = "東京都大阪府北海道日本語中国語漢字文書検索機械学習情報処理技術開発研究計算速度性能評価"
+LAT = "abcdefghijklmnopqrstuvwxyz"
+COMB = ["e\u0301", "a\u0300", "o\u0308", "u\u0308", "n\u0303", "c\u0327"]   # NFD: base + combining mark = one grapheme
+NORDIC = ["straße", "cæsar", "smørbrød", "fußball", "größe", "ærlig", "maße", "æble", "taxi", "boks", "fix", "keks"]
+
+
+def _uni_word(rng, kind, lo, hi):
+    n = int(rng.integers(lo, hi + 1))
+    if kind == 0:
+        return "".join(CYR[int(i)] for i in rng.integers(0, len(CYR), n))
+    if kind == 1:
+        return "".join(CJK[int(i)] for i in rng.integers(0, len(CJK), max(2, n // 2)))
+    if kind == 2:  # Latin with combining marks
+        out = []
+        for _ in range(n):
+            out.append(COMB[int(rng.integers(0, len(COMB)))] if rng.random() < 0.2 else LAT[int(rng.integers(0, 26))])
+        return "".join(out)
+    w = NORDIC[int(rng.integers(0, len(NORDIC)))]
+    return w + "".join(LAT[int(i)] for i in rng.integers(0, 26, int(rng.integers(0, 4))))
+
+
+def cfg3(nbytes=256 << 20, n_patterns=1000, seed=0xFAC00003):
+    """Unicode workload: Cyrillic / CJK / Latin+combining marks (NFD) / German-Nordic words, case-insensitive,
+    mappings ae<->ae-ligature, ss<->sharp-s, ks<->x, edits(2), threshold 0.8.  Text = Zipf words over a 20k-word
+    mixed-script vocabulary (some upper-cased), patterns = 1k vocabulary words of 4..12 graphemes; every ~2 KiB a
+    pattern is planted with one of its mapped spellings or a character edit.  Returns UTF-8 bytes (numpy uint8)."""
+    rng = np.random.default_rng([seed, 1])
+    vocab, seen = [], set()
+    while len(vocab) < 20000:
+        w = _uni_word(rng, int(rng.integers(0, 4)), 3, 12)
+        if w not in seen:
+            seen.add(w)
+            vocab.append(w)
+    pats = [w for w in vocab[500:] if 4 <= len(w) <= 14][:n_patterns]
+    p = 1.0 / np.arange(1, len(vocab) + 1)
+    cdf = np.cumsum(p / p.sum())
+    swaps = [("æ", "ae"), ("ß", "ss"), ("x", "ks"), ("ae", "æ"), ("ss", "ß"), ("ks", "x")]
+    parts, size = [], 0
+    while size < nbytes:
+        ids = np.searchsorted(cdf, rng.random(4096)).clip(0, len(vocab) - 1)
+        ups = rng.random(4096) < 0.1
+        for k, i in enumerate(ids):
+            w = vocab[int(i)]
+            if k % 97 == 0:  # planted pattern, respelled or edited
+                w = pats[int(rng.integers(0, len(pats)))]
+                a, b = swaps[int(rng.integers(0, len(swaps)))]
+                w = w.replace(a, b, 1) if a in w else (w[:1] + w[2:] if rng.random() < 0.5 and len(w) > 3 else w)
+            if ups[k]:
+                w = w.upper()
+            b_ = (w + " ").encode("utf-8")
+            parts.append(b_)
+            size += len(b_)
+    raw = b"".join(parts)[:nbytes]
+    while raw and (raw[-1] & 0xC0) == 0x80:   # do not end inside a scalar
+        raw = raw[:-1]
+    if raw and raw[-1] >= 0xC0:
+        raw = raw[:-1]
+    return {"patterns": pats, "edits": 2, "case_insensitive": True, "threshold": 0.8,
+            "mappings": [("æ", "ae"), ("ß", "ss"), ("ks", "x")],
+            "text": np.frombuffer(raw, dtype=np.uint8).copy(), "name": "cfg3: %d Unicode patterns, ci, mappings, edits(2)" % n_patterns}
+
+
+class BlockReader:
+    """io::Read over a repeating block, handing out at most `max_read` bytes per call and a short read at every
+    block end (the contract of examples/streaming.rs:43-82)."""
+
+    def __init__(self, block, total, max_read=64 * 1024):
+        self.block, self.total, self.pos, self.max_read = bytes(block), total, 0, max_read
+
+    def read(self, cap=-1):
+        if self.pos >= self.total:
+            return b""
+        off = self.pos % len(self.block)
+        n = min(len(self.block) - off, self.total - self.pos, self.max_read, cap if cap and cap > 0 else self.max_read)
+        self.pos += n
+        return self.block[off:off + n]
+
+
+def cfg5(total=16 << 30, n_pairs=1000, seed=0xFAC00005, block=1 << 20, auto_beam=(200_000, 100)):
+    """Streaming find-and-replace: a Read source repeating a 1 MiB block, 1000 (pattern, replacement) pairs,
+    edits(2), case-insensitive, auto_beam(budget, width), threshold 0.8, absolute u64 offsets."""
+    vocab = make_vocab(seed)
+    words = vocab_words(vocab)
+    pats = [w for w in words[1000:] if 5 <= len(w) <= 14][:n_pairs]
+    text = plant(make_text(seed, block, vocab, mixed_case=True), pats, seed)
+    pairs = [(p.decode(), "<%d>" % i) for i, p in enumerate(pats)]
+    return {"pairs": pairs, "edits": 2, "case_insensitive": True, "threshold": 0.8, "auto_beam": auto_beam,
+            "block": bytes(text), "total": total, "name": "cfg5: %d-pair replacer, auto_beam%s, streaming" % (n_pairs, auto_beam)}
+
+
 def _limits_of(kind):
     from .api import FuzzyLimits
     if kind == "edits1":
@@ -186,6 +277,12 @@ def build_engine(cfg, backend=None, device=None):
     b = FuzzyAhoCorasickBuilder.new(backend).case_insensitive(cfg["case_insensitive"])
     if "edits" in cfg:
         b = b.fuzzy(FuzzyLimits.new().edits(cfg["edits"]))
+    for a, c in cfg.get("mappings", ()):
+        b = b.mapping(a, c)
+    if cfg.get("auto_beam"):
+        b = b.auto_beam(*cfg["auto_beam"])
+    if "pairs" in cfg:
+        return b.build_replacer(cfg["pairs"])
     if device is not None:
         b = b.device(device)
     if "limit_kinds" in cfg:

@@ -121,15 +121,25 @@ class OracleBackend:
         self.lib.orc_search_stream(h, data, len(data), read_block, thr, threads, C.byref(mh))
         return self._take(mh)
 
+    @staticmethod
+    def _read_all(reader):
+        parts = []
+        while True:
+            b = reader.read()
+            if not b:
+                break
+            parts.append(bytes(b))
+        return b"".join(parts)
+
     def search_stream(self, h, reader, thr, on_match):
-        data = reader.read()
+        data = self._read_all(reader)
         arr, _ = self.search_stream_mem(h, data, thr)
         for c in arr:
             on_match(c)
         return len(data)
 
     def replace_stream(self, h, reader, writer, thr, callback, read_block=0):
-        data = reader.read()
+        data = self._read_all(reader)
         keep = []
 
         def rp(_u, pm, base, text, n, out_p, out_n):

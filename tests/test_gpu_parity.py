@@ -242,6 +242,38 @@ def test_cfg4_sparse_prefilter_parity(oracle, gpu):
     assert raw_o.tuples() == raw_g.tuples()
 
 
+def test_cfg3_unicode_mappings_slice_parity(oracle, gpu):
+    # BASELINE config 3: Cyrillic / CJK / combining marks, case-insensitive, mappings, edits(2)
+    cfg = workload.cfg3(1 << 15, n_patterns=1000)
+    eo, eg = _engines(oracle, gpu, cfg)
+    text = bytes(cfg["text"])
+    for opts in (SearchOptions.new().threshold(0.8), SearchOptions.new().threshold(0.8).sorted().non_overlapping(),
+                 SearchOptions.new().threshold(0.6).greedy().non_overlapping_unique()):
+        o, g = eo.search(text, opts), eg.search(text, opts)
+        assert len(o) > 50
+        assert o.tuples() == g.tuples()
+    assert eo.search(text, SearchOptions.new().threshold(0.8)).stats["states_pushed"] == \
+        eg.search(text, SearchOptions.new().threshold(0.8)).stats["states_pushed"]
+
+
+def test_cfg5_streaming_replacer_parity(oracle, gpu):
+    # BASELINE config 5 in miniature: repeating-block Read source, auto_beam, FuzzyReplacer::replace_stream,
+    # absolute offsets; three 256 KiB windows
+    import io
+    cfg = workload.cfg5(total=700_000, n_pairs=200, block=1 << 18, auto_beam=(20_000, 50))
+    ro, rg = workload.build_engine(cfg, oracle), workload.build_engine(cfg, gpu)
+    out_o, out_g = io.BytesIO(), io.BytesIO()
+    ro.replace_stream(workload.BlockReader(cfg["block"], cfg["total"]), out_o, 0.8)
+    rg.replace_stream(workload.BlockReader(cfg["block"], cfg["total"]), out_g, 0.8)
+    assert out_o.getvalue() == out_g.getvalue()
+    assert b"<" in out_g.getvalue() and len(out_g.getvalue()) != cfg["total"]
+    mo, mg = [], []
+    ro.engine().search_stream(workload.BlockReader(cfg["block"], cfg["total"]), 0.8, lambda m: mo.append(m.as_tuple()))
+    rg.engine().search_stream(workload.BlockReader(cfg["block"], cfg["total"]), 0.8, lambda m: mg.append(m.as_tuple()))
+    assert mo == mg and len(mo) > 100
+    assert max(t[0] for t in mg) > (1 << 18)   # absolute offsets beyond the first window
+
+
 MATCH_DT = np.dtype([("start", "<u8"), ("end", "<u8"), ("pat", "<u4"), ("simbits", "<u4"), ("ins", "u1"), ("del", "u1"),
                      ("sub", "u1"), ("swp", "u1"), ("edits", "u1"), ("pad", "u1", (3,))])
 

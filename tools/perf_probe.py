@@ -40,3 +40,5 @@ if __name__ == "__main__":
         probe("cfg4+prefilter(sorted,non_overlapping)", c4, prefilter=True, order=1, overlap=1)
     if which in ("all", "cfg2"):
         probe("cfg2", workload.cfg2(int(os.environ.get("CFG2_BYTES", 1 << 20)), int(os.environ.get("CFG2_PATTERNS", 10000))))
+    if which in ("cfg3",):
+        probe("cfg3 (unicode, mappings)", workload.cfg3(int(os.environ.get("CFG3_BYTES", 8 << 20))), reps=2)
