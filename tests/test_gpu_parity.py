@@ -242,7 +242,7 @@ def test_cfg4_sparse_prefilter_parity(oracle, gpu):
     assert raw_o.tuples() == raw_g.tuples()
 
 
-def test_cfg3_unicode_mappings_slice_parity(oracle, gpu):
+def test_cfg3_unicode_mappings_slice_parity(oracle, gpu, monkeypatch):
     # BASELINE config 3: Cyrillic / CJK / combining marks, case-insensitive, mappings, edits(2)
     cfg = workload.cfg3(1 << 15, n_patterns=1000)
     eo, eg = _engines(oracle, gpu, cfg)
@@ -252,8 +252,11 @@ def test_cfg3_unicode_mappings_slice_parity(oracle, gpu):
         o, g = eo.search(text, opts), eg.search(text, opts)
         assert len(o) > 50
         assert o.tuples() == g.tuples()
-    assert eo.search(text, SearchOptions.new().threshold(0.8)).stats["states_pushed"] == \
-        eg.search(text, SearchOptions.new().threshold(0.8)).stats["states_pushed"]
+    # the order-faithful kernel also reproduces the reference's queue.len() total
+    monkeypatch.setenv("FAC_FAITHFUL", "1")
+    ef = workload.build_engine(cfg, gpu)
+    fo, fg = eo.search(text, SearchOptions.new().threshold(0.8)), ef.search(text, SearchOptions.new().threshold(0.8))
+    assert fo.tuples() == fg.tuples() and fo.stats["states_pushed"] == fg.stats["states_pushed"]
 
 
 def test_cfg5_streaming_replacer_parity(oracle, gpu):
