@@ -395,8 +395,13 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
     uint32_t max_count = tile;
     if (explicit_tiles) { max_count = 1; for (auto &t : R.tiles) max_count = std::max(max_count, t.y); }
 
-    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)E->sm_count * E->ctas_per_sm, n_tiles);
-    CKS(ensure_scratch(E, ws, (uint32_t)E->sm_count * E->ctas_per_sm, E->qcap));
+    // beamed windows run one per CTA: by default one WARP per window (32 windows in flight per SM, small scratch),
+    // windows that overflow that scratch are redone by 256-thread CTAs with the large queue
+    const uint32_t beam_bs = R.beam ? (uint32_t)(env_int("FAC_BEAM_BLOCK", 32) == 256 ? 256 : 32) : 0;
+    const uint32_t ctas = beam_bs == 32 ? 32u : (uint32_t)E->ctas_per_sm;
+    const uint32_t run_qcap = beam_bs == 32 ? (uint32_t)std::max(4096, env_int("FAC_BEAM_QCAP", 16384)) : E->qcap;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)E->sm_count * ctas, n_tiles);
+    CKS(ensure_scratch(E, ws, (uint32_t)E->sm_count * ctas, run_qcap));
     uint32_t cand_cap = (uint32_t)std::max<size_t>(ws->cands.cap / sizeof(FacCand), 1u << 20);
     // dense-match workloads emit ~0.2-0.4 candidates per start window: size the first attempt so it need not be redone
     if (R.fast && !explicit_tiles) cand_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(cand_cap, n_windows_total / 2 + (1u << 20)), 0x7FFFFFF0u);
@@ -442,7 +447,8 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
         P.pass = 0; P.cand_cap = cand_cap; P.cands = ws->cands.as<FacCand>();
         CK(cudaEventRecord(ws->evk0, s));
         if (R.beam) {
-            k_expand_beam<<<grid, FAC_BLOCK, 0, s>>>(P, R.bw);
+            if (beam_bs == 32) k_expand_beam<32><<<grid, 32, 0, s>>>(P, R.bw);
+            else k_expand_beam<256><<<grid, 256, 0, s>>>(P, R.bw);
             CK(cudaGetLastError());
         } else if (use_succ) {
             CKS(launch_succinct(E, ws, R.tv.bytes, R.thr, R.seg_begin, R.seg_end, R.text_end, ws->cands.as<FacCand>(), cand_cap, s,
@@ -458,7 +464,7 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
         stats.expand_ms += ms;
         uint64_t n_cand = ws->h_counters[1], n_failed = ws->h_counters[3];
         uint64_t states = ws->h_counters[2];
-        if (R.beam && n_failed) {
+        if (R.beam && n_failed && beam_bs != 32) {
             set_err("a beamed start window exceeded the per-window queue capacity (" + std::to_string(ws->qcap / 4) + " states)");
             return FAC_UNSUPPORTED;
         }
@@ -479,8 +485,8 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
                 else { start = R.seg_begin + t * tile; count = std::min(tile, R.seg_end - start); tend = R.text_end; tag = 0; }
                 for (uint32_t w = 0; w < count; w++) rt.push_back(make_uint4(start + w, 1, tend, tag));
             }
-            const uint32_t big_q = 1u << 21;
-            const uint32_t rgrid = (uint32_t)std::min<size_t>(16, rt.size());
+            const uint32_t big_q = R.beam ? std::max<uint32_t>(E->qcap, 1u << 19) : 1u << 21;
+            const uint32_t rgrid = (uint32_t)std::min<size_t>(R.beam ? 128 : 16, rt.size());
             // the retry uses its own scratch sizing; rebuild the regular scratch afterwards
             const uint32_t keep_grid = ws->grid, keep_q = ws->qcap;
             CKS(ensure_scratch(E, ws, rgrid, big_q));
@@ -497,7 +503,8 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
             CK(cudaMemsetAsync(ws->counters.p, 0, 8, s));
             CK(cudaMemsetAsync((uint8_t *)ws->counters.p + 24, 0, 8, s));
             CK(cudaEventRecord(ws->evk0, s));
-            CKS(launch_expand(Q, rgrid, smem, s, R.fast));
+            if (R.beam) { k_expand_beam<256><<<rgrid, 256, 0, s>>>(Q, R.bw); CK(cudaGetLastError()); }
+            else CKS(launch_expand(Q, rgrid, smem, s, R.fast));
             CK(cudaEventRecord(ws->evk1, s));
             stats.launches++;
             CK(cudaMemcpyAsync(ws->h_counters, ws->counters.p, 8 * 8, cudaMemcpyDeviceToHost, s));
@@ -507,7 +514,7 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
             rtiles.release();
             CKS(ensure_scratch(E, ws, keep_grid, keep_q));
             if (ws->h_counters[3]) {
-                set_err("a start window expands more than " + std::to_string(big_q) + " states; lower the edit limits / raise the threshold or use a beam");
+                set_err("a start window expands more than " + std::to_string(R.beam ? big_q / 4 : big_q) + " states; lower the edit limits / raise the threshold or use a beam");
                 return FAC_UNSUPPORTED;
             }
             if (ws->h_counters[1] > cand_cap) {

@@ -19,15 +19,19 @@
 #pragma once
 #include "fac_kernels.cuh"
 
-__global__ void __launch_bounds__(FAC_BLOCK) k_expand_beam(const __grid_constant__ ExpandParams P, const uint32_t bw) {
-    __shared__ uint32_t s_scan[2][FAC_NWARPS + 1];
+// BS = threads per CTA: 32 (one warp per start window: no cross-warp barriers, 32 windows in flight per SM; the
+// default) or 256 (big-queue retry of windows that overflow the small per-warp scratch).
+template <int BS>
+__global__ void __launch_bounds__(BS) k_expand_beam(const __grid_constant__ ExpandParams P, const uint32_t bw) {
+    constexpr int NWB = BS / 32;
+    __shared__ uint32_t s_scan[2][NWB + 1];
     __shared__ uint32_t s_tile_idx, s_cut, s_vcount;
-    __shared__ uint32_t c_node[FAC_BLOCK], c_cnt[FAC_BLOCK], c_pos[FAC_BLOCK], c_exact[FAC_BLOCK], c_flags[FAC_BLOCK];
-    __shared__ float c_pen[FAC_BLOCK];
-    __shared__ uint32_t k_node[FAC_BLOCK], k_cnt[FAC_BLOCK], k_pos[FAC_BLOCK];
-    __shared__ float k_pen[FAC_BLOCK];
-    __shared__ uint8_t k_exp[FAC_BLOCK];
-    __shared__ uint32_t s_off[FAC_BLOCK + 1], s_pc[FAC_BLOCK], s_pb[FAC_BLOCK + 1];
+    __shared__ uint32_t c_node[BS], c_cnt[BS], c_pos[BS], c_exact[BS], c_flags[BS];
+    __shared__ float c_pen[BS];
+    __shared__ uint32_t k_node[BS], k_cnt[BS], k_pos[BS];
+    __shared__ float k_pen[BS];
+    __shared__ uint8_t k_exp[BS];
+    __shared__ uint32_t s_off[BS + 1], s_pc[BS], s_pb[BS + 1];
 
     const AutomatonView &A = P.A;
     const uint32_t tid = threadIdx.x;
@@ -63,7 +67,7 @@ __global__ void __launch_bounds__(FAC_BLOCK) k_expand_beam(const __grid_constant
         }
         __syncthreads();
         while (h < t && !failed) {
-            const uint32_t m = min(t - h, (uint32_t)FAC_BLOCK);
+            const uint32_t m = min(t - h, (uint32_t)BS);
             // ---- load the chunk ----
             FacState S; S.node = 0; S.pen = 0.f; S.cnt = 0; S.pos = 0;
             if (tid < m) {
@@ -100,15 +104,15 @@ __global__ void __launch_bounds__(FAC_BLOCK) k_expand_beam(const __grid_constant
             }
             k_exp[tid] = expanded ? 1 : 0;
             uint32_t W;
-            const uint32_t excl = fac_block_scan(nslots, s_scan, parity, W);
+            const uint32_t excl = fac_block_scan_t<NWB>(nslots, s_scan, parity, W);
             s_off[tid] = excl;
-            if (tid == 0) s_off[FAC_BLOCK] = W;
+            if (tid == 0) s_off[BS] = W;
             __syncthreads();
             // ---- pass 1: push count of every state ----
-            for (uint32_t k0 = 0; k0 < W; k0 += FAC_BLOCK) {
+            for (uint32_t k0 = 0; k0 < W; k0 += BS) {
                 const uint32_t k = k0 + tid;
                 if (k < W) {
-                    uint32_t lo = 0, hi = FAC_BLOCK;
+                    uint32_t lo = 0, hi = BS;
                     while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (s_off[mid] <= k) lo = mid; else hi = mid; }
                     FacCtx Cx;
                     Cx.node = c_node[lo]; Cx.pen = c_pen[lo]; Cx.cnt = c_cnt[lo]; Cx.pos = c_pos[lo];
@@ -119,9 +123,9 @@ __global__ void __launch_bounds__(FAC_BLOCK) k_expand_beam(const __grid_constant
             }
             __syncthreads();
             uint32_t total_push;
-            const uint32_t pb = fac_block_scan(s_pc[tid], s_scan, parity, total_push);  // pushes before state tid
+            const uint32_t pb = fac_block_scan_t<NWB>(s_pc[tid], s_scan, parity, total_push);  // pushes before state tid
             s_pb[tid] = pb;
-            if (tid == 0) s_pb[FAC_BLOCK] = total_push;
+            if (tid == 0) s_pb[BS] = total_push;
             // ---- where does the beam trip?  remaining = queue.len() - q_idx at the pop of state tid ----
             if (bw && tid < m) {
                 const uint32_t remaining = (t + pb) - (h + tid);
@@ -185,14 +189,14 @@ __global__ void __launch_bounds__(FAC_BLOCK) k_expand_beam(const __grid_constant
                     }
                 }
                 // ---- commit: children of the committed prefix, appended in FIFO order at queue[t..] ----
-                const uint32_t Wc = s_off[cm];  // work items of the committed states (s_off[FAC_BLOCK] == W)
+                const uint32_t Wc = s_off[cm];  // work items of the committed states (s_off[BS] == W)
                 uint32_t nbase = t;
-                for (uint32_t k0 = 0; k0 < Wc; k0 += FAC_BLOCK) {
+                for (uint32_t k0 = 0; k0 < Wc; k0 += BS) {
                     const uint32_t k = k0 + tid;
                     bool push = false;
                     FacState child;
                     if (k < Wc) {
-                        uint32_t lo = 0, hi = FAC_BLOCK;
+                        uint32_t lo = 0, hi = BS;
                         while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (s_off[mid] <= k) lo = mid; else hi = mid; }
                         FacCtx Cx;
                         Cx.node = c_node[lo]; Cx.pen = c_pen[lo]; Cx.cnt = c_cnt[lo]; Cx.pos = c_pos[lo];
@@ -200,7 +204,7 @@ __global__ void __launch_bounds__(FAC_BLOCK) k_expand_beam(const __grid_constant
                         push = fac_eval_slot(A, T, P.maxpen, start, text_end, Cx, k - s_off[lo], child);
                     }
                     uint32_t total;
-                    const uint32_t r = fac_block_rank(push, s_scan, parity, total);
+                    const uint32_t r = fac_block_rank_t<NWB>(push, s_scan, parity, total);
                     if (push) *reinterpret_cast<uint4 *>(&queue[nbase + r]) = *reinterpret_cast<uint4 *>(&child);
                     nbase += total;
                 }
@@ -210,27 +214,33 @@ __global__ void __launch_bounds__(FAC_BLOCK) k_expand_beam(const __grid_constant
                     // ---- beam cut over queue[hc, nbase): keep the bw lowest (pen, position), in queue order ----
                     const uint32_t hc = h + cm, ncut = nbase - hc;
                     uint32_t kept = 0;
-                    for (uint32_t e0 = 0; e0 < ncut; e0 += FAC_BLOCK) {
+                    for (uint32_t e0 = 0; e0 < ncut; e0 += BS) {
                         const uint32_t e = e0 + tid;
                         bool keep = false;
                         uint4 me = make_uint4(0, 0, 0, 0);
-                        if (e < ncut) {
-                            me = *reinterpret_cast<const uint4 *>(&queue[hc + e]);
-                            const uint32_t mykey = fac_total_order_u32(__uint_as_float(me.y));
-                            uint32_t rank = 0;
-                            for (uint32_t f = 0; f < ncut; f++) {
-                                const uint32_t ok = fac_total_order_u32(queue[hc + f].pen);
-                                rank += (ok < mykey || (ok == mykey && f < e)) ? 1u : 0u;
+                        if (e < ncut) me = *reinterpret_cast<const uint4 *>(&queue[hc + e]);
+                        const uint32_t mykey = fac_total_order_u32(__uint_as_float(me.y));
+                        // rank among the un-popped states by (penalty total order, queue position); the keys of
+                        // 256 states at a time are staged in shared memory (s_pc is free until the next chunk)
+                        uint32_t rank = 0;
+                        for (uint32_t f0 = 0; f0 < ncut; f0 += BS) {
+                            __syncthreads();
+                            s_pc[tid] = (f0 + tid < ncut) ? fac_total_order_u32(queue[hc + f0 + tid].pen) : 0xFFFFFFFFu;
+                            __syncthreads();
+                            const uint32_t nf = min((uint32_t)BS, ncut - f0);
+                            for (uint32_t f = 0; f < nf; f++) {
+                                const uint32_t ok = s_pc[f];
+                                rank += (ok < mykey || (ok == mykey && f0 + f < e)) ? 1u : 0u;
                             }
-                            keep = rank < bw;
                         }
+                        keep = e < ncut && rank < bw;
                         uint32_t total;
-                        const uint32_t r = fac_block_rank(keep, s_scan, parity, total);
+                        const uint32_t r = fac_block_rank_t<NWB>(keep, s_scan, parity, total);
                         if (keep) *reinterpret_cast<uint4 *>(&stage[kept + r]) = me;
                         kept += total;
                     }
                     __syncthreads();
-                    for (uint32_t e = tid; e < kept; e += FAC_BLOCK)
+                    for (uint32_t e = tid; e < kept; e += BS)
                         *reinterpret_cast<uint4 *>(&queue[hc + e]) = *reinterpret_cast<const uint4 *>(&stage[e]);
                     h = hc; t = hc + kept;  // queue.truncate(q_idx + bw)
                 }
@@ -239,12 +249,13 @@ __global__ void __launch_bounds__(FAC_BLOCK) k_expand_beam(const __grid_constant
         }
         // ---- reset the visited table; account the window ----
         const uint32_t vc = min(s_vcount, vcap);
-        for (uint32_t k = tid; k < vc; k += FAC_BLOCK) { const uint32_t hh = vslot[k]; if (hh != FAC_EMPTY) vtab[hh] = FAC_EMPTY; }
+        for (uint32_t k = tid; k < vc; k += BS) { const uint32_t hh = vslot[k]; if (hh != FAC_EMPTY) vtab[hh] = FAC_EMPTY; }
         if (s_vcount > vcap) failed = true;
         if (tid == 0) {
             if (failed) {
                 const unsigned long long fi = atomicAdd(&P.counters[3], 1ull);
                 if (fi < P.failed_cap) P.failed_tiles[fi] = t_idx;
+                if (P.failed_bitmap) atomicOr(&P.failed_bitmap[t_idx >> 5], 1u << (t_idx & 31u));
             } else {
                 atomicAdd(&P.counters[2], (unsigned long long)t);
                 if (P.per_window) P.per_window[start] = t;

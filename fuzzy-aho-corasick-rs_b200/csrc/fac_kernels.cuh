@@ -30,56 +30,49 @@ __device__ __forceinline__ uint32_t fac_lane() { return threadIdx.x & 31u; }
 __device__ __forceinline__ uint32_t fac_warp() { return threadIdx.x >> 5; }
 
 // Block-wide exclusive scan of one u32 per thread.  `buf` is a [2][FAC_NWARPS+1] shared array,
-// `parity` alternates per call so consecutive calls need no trailing barrier.
-__device__ __forceinline__ uint32_t fac_block_scan(uint32_t v, uint32_t (*buf)[FAC_NWARPS + 1], uint32_t &parity, uint32_t &total) {
+// `parity` alternates per call.  ONE barrier per call: every warp publishes its total, and after the
+// barrier every warp scans the FAC_NWARPS totals itself (the barrier of the next call orders the
+// reads of this call before the buffer is written again two calls later).
+template <int NW>
+__device__ __forceinline__ uint32_t fac_block_offsets_t(uint32_t warp_total, uint32_t (*buf)[NW + 1], uint32_t &parity, uint32_t &total) {
+    if (NW == 1) { __syncwarp(); total = warp_total; return 0u; }   // single-warp CTAs need no exchange
+    uint32_t *b = buf[parity & 1u];
+    parity++;
+    if (fac_lane() == 0) b[fac_warp()] = warp_total;
+    __syncthreads();
+    const uint32_t x = fac_lane() < (uint32_t)NW ? b[fac_lane()] : 0u;
+    uint32_t xi = x;
+#pragma unroll
+    for (int d = 1; d < NW; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, xi, d);
+        if (fac_lane() >= (uint32_t)d) xi += t;
+    }
+    total = __shfl_sync(0xFFFFFFFFu, xi, NW - 1);
+    return __shfl_sync(0xFFFFFFFFu, xi - x, fac_warp());
+}
+template <int NW>
+__device__ __forceinline__ uint32_t fac_block_scan_t(uint32_t v, uint32_t (*buf)[NW + 1], uint32_t &parity, uint32_t &total) {
     uint32_t incl = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
         if (fac_lane() >= (uint32_t)d) incl += t;
     }
-    uint32_t *b = buf[parity & 1u];
-    parity++;
-    if (fac_lane() == 31) b[fac_warp()] = incl;
-    __syncthreads();
-    if (fac_warp() == 0) {
-        const uint32_t x = fac_lane() < FAC_NWARPS ? b[fac_lane()] : 0u;
-        uint32_t xi = x;
-#pragma unroll
-        for (int d = 1; d < FAC_NWARPS; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, xi, d);
-            if (fac_lane() >= (uint32_t)d) xi += t;
-        }
-        if (fac_lane() < FAC_NWARPS) b[fac_lane()] = xi - x;
-        if (fac_lane() == FAC_NWARPS - 1) b[FAC_NWARPS] = xi;
-    }
-    __syncthreads();
-    total = b[FAC_NWARPS];
-    return b[fac_warp()] + incl - v;
+    const uint32_t warp_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    return fac_block_offsets_t<NW>(warp_total, buf, parity, total) + incl - v;
 }
-
 // Same for a 1-bit predicate: ballot + popc inside the warp (order-preserving compaction rank).
-__device__ __forceinline__ uint32_t fac_block_rank(bool p, uint32_t (*buf)[FAC_NWARPS + 1], uint32_t &parity, uint32_t &total) {
+template <int NW>
+__device__ __forceinline__ uint32_t fac_block_rank_t(bool p, uint32_t (*buf)[NW + 1], uint32_t &parity, uint32_t &total) {
     const uint32_t bal = __ballot_sync(0xFFFFFFFFu, p);
     const uint32_t in_warp = __popc(bal & ((1u << fac_lane()) - 1u));
-    uint32_t *b = buf[parity & 1u];
-    parity++;
-    if (fac_lane() == 0) b[fac_warp()] = __popc(bal);
-    __syncthreads();
-    if (fac_warp() == 0) {
-        const uint32_t x = fac_lane() < FAC_NWARPS ? b[fac_lane()] : 0u;
-        uint32_t xi = x;
-#pragma unroll
-        for (int d = 1; d < FAC_NWARPS; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, xi, d);
-            if (fac_lane() >= (uint32_t)d) xi += t;
-        }
-        if (fac_lane() < FAC_NWARPS) b[fac_lane()] = xi - x;
-        if (fac_lane() == FAC_NWARPS - 1) b[FAC_NWARPS] = xi;
-    }
-    __syncthreads();
-    total = b[FAC_NWARPS];
-    return b[fac_warp()] + in_warp;
+    return fac_block_offsets_t<NW>(__popc(bal), buf, parity, total) + in_warp;
+}
+__device__ __forceinline__ uint32_t fac_block_scan(uint32_t v, uint32_t (*buf)[FAC_NWARPS + 1], uint32_t &parity, uint32_t &total) {
+    return fac_block_scan_t<FAC_NWARPS>(v, buf, parity, total);
+}
+__device__ __forceinline__ uint32_t fac_block_rank(bool p, uint32_t (*buf)[FAC_NWARPS + 1], uint32_t &parity, uint32_t &total) {
+    return fac_block_rank_t<FAC_NWARPS>(p, buf, parity, total);
 }
 
 // ---- TMA (bulk async copy engine) 1-D global -> shared with an mbarrier -------------------------
