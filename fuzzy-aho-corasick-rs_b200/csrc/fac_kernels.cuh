@@ -19,7 +19,9 @@
 #include "fac_types.h"
 #include "fac_unicode.h"
 
+#ifndef FAC_BLOCK
 #define FAC_BLOCK 256
+#endif
 #define FAC_NWARPS (FAC_BLOCK / 32)
 #define FAC_EMPTY 0xFFFFFFFFu
 

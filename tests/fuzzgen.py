@@ -100,3 +100,64 @@ def rand_case(r, backend, unicode_=False, allow_mappings=True, max_hay=60):
     desc["thr"] = thr
     desc["hay"] = hay
     return engine, hay, thr, desc
+
+
+def rand_dense_case(r, backend):
+    """Engines inside the fast kernel's domain (single-byte alphabet <= 31 symbols, edits(1..3)) with a few
+    hundred random patterns over a small alphabet, so that the trie is dense, ties are common and outputs pile
+    up -- plus random penalties / similarity / weights / case folding.  Returns (engine, haystack, thr, desc)."""
+    from fac_b200 import SearchOptions  # noqa: F401
+    alpha = r.choice(["abcde", "abcdefghij", "etaoinshrdlu", "abcdefghijklmnopqrstuvwxyz", "ab01-_ ."])
+    npat = r.choice([20, 60, 200, 500])
+    lo, hi = r.choice([(2, 6), (3, 9), (5, 12)])
+    pats, seen = [], set()
+    while len(pats) < npat:
+        w = "".join(r.choice(alpha) for _ in range(r.randrange(lo, hi + 1)))
+        if w not in seen:
+            seen.add(w)
+            pats.append(w)
+    edits = r.choice([1, 2, 2, 3])
+    ci = r.random() < 0.4
+    b = FuzzyAhoCorasickBuilder.new(backend).case_insensitive(ci).fuzzy(FuzzyLimits.new().edits(edits))
+    desc = {"alpha": alpha, "npat": npat, "edits": edits, "ci": ci}
+    if r.random() < 0.4:
+        b = b.penalties(FuzzyPenalties.default().swap(r.choice([0.3, 0.6, 0.52])).insertion(r.choice([0.5, 0.25]))
+                        .deletion(r.choice([0.8, 0.91, 0.4])).substitution(r.choice([1.0, 1.43, 0.7])))
+        desc["pen"] = True
+    if r.random() < 0.3:
+        b = b.min_symbol_similarity(r.choice([0.3, 0.5]))
+        desc["minsym"] = True
+    if r.random() < 0.3:
+        pairs = {(a, c): r.choice([0.25, 0.5, 0.75]) for a in alpha[:6] for c in alpha[:6] if a != c and r.random() < 0.4}
+        b = b.similarity(pairs)
+        desc["sim"] = len(pairs)
+    plist = pats
+    if r.random() < 0.3:
+        plist = [Pattern.from_(p).weight(r.choice([0.75, 1.0, 1.25])) if r.random() < 0.5 else p for p in pats]
+        desc["weights"] = True
+    engine = b.build(plist)
+    n = r.choice([200, 1000, 3000])
+    hay = []
+    while len(hay) < n:
+        if r.random() < 0.15:
+            w = list(r.choice(pats))
+            for _ in range(r.randrange(0, 3)):
+                i = r.randrange(len(w))
+                op = r.randrange(4)
+                if op == 0 and len(w) > 1:
+                    del w[i]
+                elif op == 1:
+                    w.insert(i, r.choice(alpha))
+                elif op == 2:
+                    w[i] = r.choice(alpha)
+                elif i + 1 < len(w):
+                    w[i], w[i + 1] = w[i + 1], w[i]
+            hay += w
+        else:
+            hay.append(r.choice(alpha))
+    hay = "".join(hay[:n])
+    if ci and r.random() < 0.5:
+        hay = "".join(c.upper() if r.random() < 0.3 else c for c in hay)
+    thr = r.choice([0.5, 0.6, 0.7, 0.8, 0.9])
+    desc["thr"] = thr
+    return engine, hay, thr, desc

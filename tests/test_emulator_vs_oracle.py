@@ -6,7 +6,7 @@ import pytest
 
 from emu_backend import EmuBackend
 from fac_b200 import SearchOptions
-from fuzzgen import rand_case
+from fuzzgen import rand_case, rand_dense_case
 
 
 @pytest.fixture(scope="module")
@@ -75,3 +75,16 @@ def test_succinct_ties(oracle):
         e = mk(emu).search(hay, SearchOptions.new().threshold(0.3))
         assert o.tuples() == e.tuples(), (t, pats, hay, edits)
     assert emu.succinct_dirty > 0
+
+
+def test_succinct_dense_tries(oracle):
+    emu = EmuBackend(tile=16)
+    emu.succinct = True
+    r1, r2 = random.Random(177), random.Random(177)
+    for t in range(25):
+        eo, hay, thr, desc = rand_dense_case(r1, oracle)
+        ee, _, _, _ = rand_dense_case(r2, emu)
+        o = eo.search(hay[:600], SearchOptions.new().threshold(thr))
+        e = ee.search(hay[:600], SearchOptions.new().threshold(thr))
+        assert o.tuples() == e.tuples(), (t, desc)
+    assert emu.succinct_used == 25

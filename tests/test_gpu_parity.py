@@ -9,7 +9,7 @@ import pytest
 
 from fac_b200 import (FuzzyAhoCorasickBuilder, FuzzyLimits, Order, Overlap, SearchOptions, workload)
 from fac_b200._abi import fac_match
-from fuzzgen import rand_case
+from fuzzgen import rand_case, rand_dense_case
 
 pytestmark = pytest.mark.gpu
 
@@ -43,6 +43,20 @@ def test_fuzz_ascii(oracle, gpu, faithful, monkeypatch):
 @pytest.mark.parametrize("faithful", [True, False])
 def test_fuzz_unicode(oracle, gpu, faithful, monkeypatch):
     _fuzz(oracle, gpu, 12, True, 400, faithful, monkeypatch)
+
+
+def test_fast_kernel_dense_tries(oracle, gpu, monkeypatch):
+    # dense random tries over small alphabets: survivor masks, two-deep masks, walk queue, ties, many outputs
+    monkeypatch.setenv("FAC_FAITHFUL", "0")
+    r1, r2 = random.Random(77), random.Random(77)
+    ropt = random.Random(78)
+    for t in range(60):
+        eo, hay, thr, desc = rand_dense_case(r1, oracle)
+        eg, _, _, _ = rand_dense_case(r2, gpu)
+        order, overlap = ropt.choice(ALL_OPTS)
+        o = eo.search(hay, SearchOptions(thr, order, overlap))
+        g = eg.search(hay, SearchOptions(thr, order, overlap))
+        assert o.tuples() == g.tuples(), (t, order, overlap, desc)
 
 
 def test_fast_kernel_tie_redo(oracle, gpu, monkeypatch):
