@@ -200,7 +200,7 @@ struct fac_engine {
     const uint64_t *d_bp_mask = nullptr;
     const uint8_t *d_bp_m = nullptr;
     // succinct-trie fast kernel (fac_succinct.cuh)
-    bool succ_ok = false;
+    bool succ_ok = false, succ_exact = false;
     const uint32_t *d_s_bm = nullptr, *d_s_fc = nullptr, *d_s_out_idx = nullptr, *d_s_out2 = nullptr;
     const float *d_s_plen = nullptr, *d_s_plow = nullptr, *d_s_subpen = nullptr;
     const uint8_t *d_s_symof = nullptr;
@@ -297,6 +297,7 @@ fac_status launch_succinct(const fac_engine *E, Workspace *ws, const uint8_t *d_
     P.K.thr = thr;
     P.K.maxpen = S.prune_len[0] - S.prune_low[0] * thr;  // search.rs:487 (host compiled without contraction)
     P.K.pen_ins = E->host.pen_ins; P.K.pen_del = E->host.pen_del; P.K.pen_swap = E->host.pen_swap; P.K.mef = E->host.mef;
+    P.exact_only = S.exact_only ? 1 : 0;
     P.ci = E->host.ci; P.wskip = E->host.wskip; P.first_mask = S.first_mask; P.second_mask = S.second_mask;
     P.seg_begin = seg_begin; P.seg_end = seg_end; P.text_end = text_end;
     P.tile = E->succ_tile; P.n_tiles = cdiv((uint64_t)seg_end - seg_begin, P.tile); P.lookahead = E->lookahead;
@@ -434,15 +435,17 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
     P.per_window = R.d_per_window;
     P.use_tma = E->use_tma;
     const size_t smem = expand_smem_bytes(E, ascii, P.smem_text_cap);
-    const bool use_succ = R.fast && E->succ_ok && ascii && (!explicit_tiles || R.slices) && !R.beam && !R.d_per_window;
+    const bool use_succ = R.fast && (E->succ_ok || E->succ_exact) && ascii && (!explicit_tiles || R.slices) && !R.beam && !R.d_per_window;
+    // an exact-only engine is "fast" only through the succinct kernel; the generic FAST kernel needs an edit budget
+    const bool fast_run = R.fast && (E->fast_ok || use_succ);
     if (use_succ && explicit_tiles && max_count > E->succ_tile) { set_err("internal: slice tile larger than the succinct tile"); return FAC_INVALID_ARGUMENT; }
     const uint32_t n_win_seg = R.seg_end - R.seg_begin;
     const uint32_t dirty_words = n_win_seg / 32 + 1;
-    if (R.fast) CKS(ws->dirty.ensure((size_t)dirty_words * 4));
+    if (fast_run) CKS(ws->dirty.ensure((size_t)dirty_words * 4));
 
     for (int attempt = 0; attempt < 3; attempt++) {
         CK(cudaMemsetAsync(ws->counters.p, 0, 16 * 8, s));
-        if (R.fast) CK(cudaMemsetAsync(ws->dirty.p, 0, (size_t)dirty_words * 4, s));
+        if (fast_run) CK(cudaMemsetAsync(ws->dirty.p, 0, (size_t)dirty_words * 4, s));
         CK(cudaMemsetAsync(ws->failed_bitmap.p, 0, (size_t)4 * (n_tiles / 32 + 1), s));
         P.pass = 0; P.cand_cap = cand_cap; P.cands = ws->cands.as<FacCand>();
         CK(cudaEventRecord(ws->evk0, s));
@@ -454,7 +457,7 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
             CKS(launch_succinct(E, ws, R.tv.bytes, R.thr, R.seg_begin, R.seg_end, R.text_end, ws->cands.as<FacCand>(), cand_cap, s,
                                 explicit_tiles ? ws->tiles.as<uint4>() : nullptr, n_tiles));
             stats.launches++;
-        } else CKS(launch_expand(P, grid, smem, s, R.fast));
+        } else CKS(launch_expand(P, grid, smem, s, fast_run));
         CK(cudaEventRecord(ws->evk1, s));
         stats.launches++;
         CK(cudaMemcpyAsync(ws->h_counters, ws->counters.p, 8 * 8, cudaMemcpyDeviceToHost, s));
@@ -504,7 +507,7 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
             CK(cudaMemsetAsync((uint8_t *)ws->counters.p + 24, 0, 8, s));
             CK(cudaEventRecord(ws->evk0, s));
             if (R.beam) { k_expand_beam<256><<<rgrid, 256, 0, s>>>(Q, R.bw); CK(cudaGetLastError()); }
-            else CKS(launch_expand(Q, rgrid, smem, s, R.fast));
+            else CKS(launch_expand(Q, rgrid, smem, s, fast_run));
             CK(cudaEventRecord(ws->evk1, s));
             stats.launches++;
             CK(cudaMemcpyAsync(ws->h_counters, ws->counters.p, 8 * 8, cudaMemcpyDeviceToHost, s));
@@ -551,7 +554,7 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
         B.out_cap = (uint32_t)n_cand;
         CK(cudaMemsetAsync((uint8_t *)ws->counters.p + 32, 0, 8, s));
         B.out_count = ws->counters.as<unsigned long long>() + 4;
-        if (!R.fast) {
+        if (!fast_run) {
             k_best_insert<<<cdiv(n_cand, 256), 256, 0, s>>>(B);
             k_best_select<<<cdiv(n_cand, 256), 256, 0, s>>>(B);
             CK(cudaGetLastError());
@@ -1007,12 +1010,12 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
         bool fallback = false;
         CKS(prefilter_slices(E, ws, d_text, (uint32_t)n, thr, slices, &fallback, stats));
         if (!fallback) {
-            const uint32_t tile_w = E->succ_ok ? E->succ_tile : 64u;
+            const uint32_t tile_w = (E->succ_ok || E->succ_exact) ? E->succ_tile : 64u;
             size_t si = 0;
             while (si < slices.size()) {
                 // batches of slices bounded by a window budget so the candidate buffers stay modest
                 ExpandRun R;
-                R.tv = tv; R.d_windows = ws->windows.as<FacWindow>(); R.thr = thr; R.fast = E->fast_ok; R.slices = &slices;
+                R.tv = tv; R.d_windows = ws->windows.as<FacWindow>(); R.thr = thr; R.fast = E->fast_ok || (E->succ_exact && ascii); R.slices = &slices;
                 uint64_t wins = 0;
                 const size_t s0 = si;
                 for (; si < slices.size() && wins < (1u << 25); si++) {
@@ -1033,7 +1036,7 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
     const uint64_t SEG = (uint64_t)env_int("FAC_SEGMENT_WINDOWS", 1 << 25);
     uint32_t tile = E->default_tile;
     bool calibrated = tile != 0;
-    if (E->succ_ok && ascii) { calibrated = true; if (!tile) tile = 8; }  // the succinct kernel tiles by itself
+    if ((E->succ_ok || E->succ_exact) && ascii) { calibrated = true; if (!tile) tile = 8; }  // the succinct kernel tiles by itself
     if (!calibrated) tile = 4;
     uint64_t pos = g_begin;
     while (pos < g_end) {
@@ -1041,7 +1044,7 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
         if (!calibrated) seg = std::min<uint64_t>(seg, 1 << 16);  // small calibration segment decides the tile size
         ExpandRun R;
         R.tv = tv; R.seg_begin = (uint32_t)pos; R.seg_end = (uint32_t)(pos + seg); R.text_end = (uint32_t)n;
-        R.d_windows = ws->windows.as<FacWindow>(); R.thr = thr; R.fast = E->fast_ok;
+        R.d_windows = ws->windows.as<FacWindow>(); R.thr = thr; R.fast = E->fast_ok || (E->succ_exact && ascii);
         double spw = 0;
         // keep what is already in m_a: grow by copy before the reduction writes
         CKS(grow_keep(ws->m_a, n_matches * sizeof(WMatch), (n_matches + (1u << 20)) * sizeof(WMatch), s));
@@ -1167,6 +1170,9 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
     E->use_tma = env_int("FAC_USE_TMA", 1);
     E->fast_ok = H.mef != 255 && H.beam_width == 0 && !H.has_auto_beam && env_int("FAC_FAITHFUL", 0) == 0;
     E->succ_ok = E->fast_ok && H.succ.ok && env_int("FAC_SUCCINCT", 1) != 0;
+    // engines without limits: the exact chain is all that can emit; only the succinct kernel has that shortcut
+    E->succ_exact = H.succ.ok && H.succ.exact_only && H.beam_width == 0 && !H.has_auto_beam && env_int("FAC_FAITHFUL", 0) == 0 &&
+                    env_int("FAC_SUCCINCT", 1) != 0;
     E->succ_nt = (uint32_t)env_int("FAC_SUCC_THREADS", 1024);
     E->succ_tile = (uint32_t)std::max(32, env_int("FAC_SUCC_TILE", 1024));
     E->succ_stack = (uint32_t)env_int("FAC_SUCC_STACK", 0);

@@ -448,7 +448,8 @@ fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_
         HostSuccinct &S = A.succ;
         S = HostSuccinct();
         memset(S.sym_of, 31, sizeof(S.sym_of));
-        bool ok = !A.has_mappings && A.mef != 255 && N <= SUCC_MAX_NODES;
+        S.exact_only = !A.has_global_limits && !A.has_pattern_limits;
+        bool ok = !A.has_mappings && (A.mef != 255 || S.exact_only) && N <= SUCC_MAX_NODES;
         std::vector<int> sym_of_char(128, -1);
         std::vector<uint32_t> chars;
         for (size_t i = 0; i < N && ok; i++)

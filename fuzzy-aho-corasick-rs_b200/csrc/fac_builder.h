@@ -60,6 +60,10 @@ struct HostBitap {
 // engine is outside that kernel's domain (mappings, per-type limits, multi-byte edges, > 31 symbols).
 struct HostSuccinct {
     bool ok = false;
+    // engines without any FuzzyLimits: the reference still expands one substitution per start window
+    // (src/search.rs:143-145) but rejects every output whose edit counts are not all zero (:166-168), so the
+    // results are exactly the outputs along the exact chain from the root
+    bool exact_only = false;
     uint32_t n_syms = 0;
     uint8_t sym_of[256];                 // folded text byte -> dense symbol, 31 = not in the alphabet
     std::vector<uint32_t> bm, fc_sym;    // [N] child bitmap; first_child | in-symbol << 27

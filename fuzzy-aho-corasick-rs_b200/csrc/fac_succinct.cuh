@@ -35,6 +35,7 @@ struct SuccParams {
     uint32_t n_nodes, n_smem_nodes;
     SuccConsts K;
     int32_t ci, wskip;
+    int32_t exact_only;      // engine without FuzzyLimits: only the exact chain from the root can emit
     uint32_t first_mask, second_mask;
     uint32_t seg_begin, seg_end, text_end, tile, n_tiles, lookahead;
     const uint4 *tiles;      // optional explicit tiles {start, count (<= tile), text_end, _} (pre-filter slices); null = uniform tiling
@@ -202,6 +203,13 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
         __syncthreads();
         const SuccTextDev T{s_byte, s_sym, base};
 
+        if (P.exact_only) {
+            // no edit is ever accepted (search.rs:166-168): one LANE per start window walks the exact chain
+            for (uint32_t w = tid; w < count; w += NT)
+                n_states += succ_walk(K, R, out2, T, emit, tile_start + w, text_end, R(0u), 0.f, 0u, 0u, 0u);
+            __syncthreads();
+            continue;
+        }
         // ---- windows of the tile, one per warp at a time ----
         for (;;) {
             uint32_t w = 0;

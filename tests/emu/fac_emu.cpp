@@ -243,6 +243,10 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
                 if (!((S.second_mask >> T.sym(start + 1)) & 1u)) continue;
             }
         }
+        if (S.exact_only) {  // engine without FuzzyLimits: only the exact chain from the root can emit
+            states += succ_walk(K, R, out2, T, emit, start, text_end, R(0u), 0.f, 0u, 0u, 0u);
+            continue;
+        }
         std::vector<FacState> stack;
         stack.push_back(FacState{0, 0.f, 0, 0});
         while (!stack.empty()) {

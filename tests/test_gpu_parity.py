@@ -45,6 +45,20 @@ def test_fuzz_unicode(oracle, gpu, faithful, monkeypatch):
     _fuzz(oracle, gpu, 12, True, 400, faithful, monkeypatch)
 
 
+def test_exact_engine_fast_path(oracle, gpu, monkeypatch):
+    # engines without FuzzyLimits (plain multi-pattern matching): the fast kernel walks the exact chain only
+    monkeypatch.setenv("FAC_FAITHFUL", "0")
+    cfg = workload.cfg2(1 << 16, n_patterns=3000)
+    for ci in (False, True):
+        mk = lambda b: FuzzyAhoCorasickBuilder.new(b).case_insensitive(ci).build(cfg["patterns"] + ["ab", "b", "the"])
+        eo, eg = mk(oracle), mk(gpu)
+        text = bytes(cfg["text"]) if not ci else bytes(cfg["text"]).upper()
+        for opts in (SearchOptions.new().threshold(0.8), SearchOptions.new().threshold(0.5).sorted().non_overlapping()):
+            o, g = eo.search(text, opts), eg.search(text, opts)
+            assert len(o) > 100
+            assert o.tuples() == g.tuples()
+
+
 def test_fast_kernel_dense_tries(oracle, gpu, monkeypatch):
     # dense random tries over small alphabets: survivor masks, two-deep masks, walk queue, ties, many outputs
     monkeypatch.setenv("FAC_FAITHFUL", "0")
