@@ -381,6 +381,7 @@ struct ExpandRun {
     // pre-filter mode: the merged slices (gs, ge) the explicit tiles were cut from; a start window's
     // text_end is the end of its slice (each slice is searched as its own haystack, prefilter.rs:346-350)
     const std::vector<std::pair<uint32_t, uint32_t>> *slices = nullptr;
+    bool slice_tags = false;  // stream batches: slice i is haystack window i (the candidate tag)
 };
 
 // Run K3 (+ retry of failed tiles) and the best-per-span reduction; appends WMatch records to
@@ -609,7 +610,9 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
             if (R.slices)
                 for (uint4 &t4 : R2.tiles) {  // the window's haystack ends where its slice ends
                     auto it = std::upper_bound(R.slices->begin(), R.slices->end(), std::make_pair(t4.x, 0xFFFFFFFFu));
-                    t4.z = (--it)->second;
+                    --it;
+                    t4.z = it->second;
+                    if (R.slice_tags) t4.w = (uint32_t)(it - R.slices->begin());
                 }
             stats.dirty_windows += n_dirty;
             CKS(expand_and_reduce(E, ws, R2, 1, n_matches, stats, nullptr));

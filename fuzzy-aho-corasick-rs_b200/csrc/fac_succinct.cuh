@@ -38,7 +38,7 @@ struct SuccParams {
     int32_t exact_only;      // engine without FuzzyLimits: only the exact chain from the root can emit
     uint32_t first_mask, second_mask;
     uint32_t seg_begin, seg_end, text_end, tile, n_tiles, lookahead;
-    const uint4 *tiles;      // optional explicit tiles {start, count (<= tile), text_end, _} (pre-filter slices); null = uniform tiling
+    const uint4 *tiles;      // optional explicit tiles {start, count (<= tile), text_end, window id} (pre-filter slices, stream batches); null = uniform tiling
     const uint32_t *gm;      // [gm_nodes * 32] grandchild masks (fac_succinct.h)
     uint32_t gm_nodes;
     const uint32_t *gm2;     // [gm2_nodes * 1024] two-deep masks
@@ -110,12 +110,13 @@ struct SuccEmitDev {
     FacCand *cands;
     uint32_t cap;
     unsigned long long *counter;
+    uint32_t tag;   // haystack-window id of the tile being searched (stream batches), 0 otherwise
     __device__ __forceinline__ void operator()(uint32_t sg, uint32_t eg, uint32_t pat, float sim, uint32_t cnt) {
         const unsigned long long ci = atomicAdd(counter, 1ull);
         if (ci < cap) {
             uint4 *dst = reinterpret_cast<uint4 *>(&cands[ci]);
             dst[0] = make_uint4(sg, eg, pat, __float_as_uint(sim));
-            dst[1] = make_uint4(cnt, 0u, 0u, 0u);
+            dst[1] = make_uint4(cnt, 0u, 0u, tag);
         }
     }
 };
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
     const SuccGMDev G{P.gm, P.gm_nodes, R};
     const SuccGM2Dev G2{P.gm2, P.gm2_nodes, G};
     const SuccOut *out2 = reinterpret_cast<const SuccOut *>(P.out2);
-    SuccEmitDev emit{P.cands, P.cand_cap, &P.counters[1]};
+    SuccEmitDev emit{P.cands, P.cand_cap, &P.counters[1], 0u};
     uint4 *const stk = s_stack + (size_t)warp * P.stack_cap;
     uint4 *const wq = s_wq + (size_t)warp * SUCC_WQ_CAP;
     const uint32_t cap = P.stack_cap;
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
         const uint32_t t = s_tile_idx;
         if (t >= P.n_tiles) break;
         uint32_t tile_start, count, text_end;
-        if (P.tiles) { const uint4 d = P.tiles[t]; tile_start = d.x; count = d.y; text_end = d.z; }
+        if (P.tiles) { const uint4 d = P.tiles[t]; tile_start = d.x; count = d.y; text_end = d.z; emit.tag = d.w; }
         else { tile_start = P.seg_begin + t * P.tile; count = min(P.tile, P.seg_end - tile_start); text_end = P.text_end; }
 
         // ---- stage the tile: TMA bulk copy of the 16-byte aligned body, plain loads for the tail ----

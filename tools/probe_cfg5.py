@@ -24,3 +24,15 @@ for label, mk in (("auto_beam(200000,100)", lambda b: b.auto_beam(200000, 100)),
             tot += len(r)
         dt = time.time() - t0
     print("%s: %d B in 256 KiB windows: %.3f s -> %.4f GB/s, %d matches" % (label, n, dt, n / dt / 1e9, tot), flush=True)
+
+# streaming API throughput (fac_search_stream): windows cut by the library, searched in batches
+import io
+for label, mk in (("stream no beam", lambda b: b),):
+    eng = mk(FuzzyAhoCorasickBuilder.new(gpu).fuzzy(FuzzyLimits.new().edits(2)).case_insensitive(True)).build(cfg["patterns"])
+    big = bytes(cfg["text"]) * max(1, (32 << 20) // n)
+    for rep in range(2):
+        cnt = [0]
+        t0 = time.time()
+        eng.search_stream(io.BytesIO(big), 0.8, lambda m: cnt.__setitem__(0, cnt[0] + 1))
+        dt = time.time() - t0
+    print("%s: %d B: %.3f s -> %.4f GB/s, %d matches" % (label, len(big), dt, len(big) / dt / 1e9, cnt[0]), flush=True)
