@@ -204,7 +204,7 @@ struct fac_engine {
     const uint32_t *d_s_bm = nullptr, *d_s_fc = nullptr, *d_s_out_idx = nullptr, *d_s_out2 = nullptr;
     const float *d_s_plen = nullptr, *d_s_plow = nullptr, *d_s_subpen = nullptr;
     const uint8_t *d_s_symof = nullptr;
-    const uint32_t *d_s_gm = nullptr, *d_s_gm2 = nullptr;
+    const uint32_t *d_s_gm = nullptr, *d_s_gm2 = nullptr, *d_s_node_lim = nullptr;
     uint32_t succ_nt = 1024, succ_tile = 1024, succ_stack = 0;
     int smem_optin = 0;
     bool fast_ok = false;  // FAST kernel allowed (fast-path edit ceiling, no beam); FAC_FAITHFUL=1 forces the order-faithful kernel
@@ -277,8 +277,13 @@ fac_status launch_expand(const ExpandParams &P, uint32_t grid, size_t smem, cuda
 // ---- succinct fast kernel launch (fac_succinct.cuh) ----
 template <int NT>
 fac_status launch_succ_t(const SuccParams &P, uint32_t grid, size_t smem, cudaStream_t s) {
-    CK(cudaFuncSetAttribute(k_expand_succinct<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_expand_succinct<NT><<<grid, NT, smem, s>>>(P);
+    if (P.K.lim) {
+        CK(cudaFuncSetAttribute(k_expand_succinct<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_expand_succinct<NT, true><<<grid, NT, smem, s>>>(P);
+    } else {
+        CK(cudaFuncSetAttribute(k_expand_succinct<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_expand_succinct<NT, false><<<grid, NT, smem, s>>>(P);
+    }
     CK(cudaGetLastError());
     return FAC_OK;
 }
@@ -297,15 +302,19 @@ fac_status launch_succinct(const fac_engine *E, Workspace *ws, const uint8_t *d_
     P.K.thr = thr;
     P.K.maxpen = S.prune_len[0] - S.prune_low[0] * thr;  // search.rs:487 (host compiled without contraction)
     P.K.pen_ins = E->host.pen_ins; P.K.pen_del = E->host.pen_del; P.K.pen_swap = E->host.pen_swap; P.K.mef = E->host.mef;
+    if (S.limits_mode) {   // per-state permissions from the limits tables; mef = bound on a state's total edits
+        P.K.mef = (int32_t)S.edit_bound; P.K.lim = E->dview.lim; P.K.node_lim = E->d_s_node_lim; P.K.has_global = E->host.has_global_limits;
+    }
     P.exact_only = S.exact_only ? 1 : 0;
     P.ci = E->host.ci; P.wskip = E->host.wskip; P.first_mask = S.first_mask; P.second_mask = S.second_mask;
     P.seg_begin = seg_begin; P.seg_end = seg_end; P.text_end = text_end;
     P.tile = E->succ_tile; P.n_tiles = cdiv((uint64_t)seg_end - seg_begin, P.tile); P.lookahead = E->lookahead;
     if (d_tiles) { P.tiles = d_tiles; P.n_tiles = n_explicit; }
     // deeper edit budgets push whole sibling sets of non-final states: fewer warps, deeper stacks
-    const uint32_t nt = E->host.mef <= 2 ? E->succ_nt : std::min<uint32_t>(E->succ_nt, 512u);
+    const bool deep = S.limits_mode || E->host.mef > 2;
+    const uint32_t nt = !deep ? E->succ_nt : std::min<uint32_t>(E->succ_nt, 512u);
     const uint32_t nw = nt / 32;
-    P.stack_cap = E->succ_stack ? E->succ_stack : (E->host.mef <= 2 ? 128u : 384u);
+    P.stack_cap = E->succ_stack ? E->succ_stack : (!deep ? 128u : 384u);
     P.text_cap = (P.tile + P.lookahead + 16u + 15u) & ~15u;
     P.gm = E->d_s_gm; P.gm_nodes = S.gm_nodes; P.gm2 = E->d_s_gm2; P.gm2_nodes = S.gm2_nodes;
     const size_t fixed = (size_t)nw * (P.stack_cap + SUCC_WQ_CAP) * 16 + 32 * 128 * 4 + (size_t)P.text_cap * 3 + 256;
@@ -1160,6 +1169,7 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
         if ((st = upload(E, symof, &E->d_s_symof)) != FAC_OK) return fail(st);
         if ((st = upload(E, S.gmask, &E->d_s_gm)) != FAC_OK) return fail(st);
         if ((st = upload(E, S.gmask2, &E->d_s_gm2)) != FAC_OK) return fail(st);
+        if ((st = upload(E, S.node_lim, &E->d_s_node_lim)) != FAC_OK) return fail(st);
     }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -1173,8 +1183,9 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
     E->use_tma = env_int("FAC_USE_TMA", 1);
     E->fast_ok = H.mef != 255 && H.beam_width == 0 && !H.has_auto_beam && env_int("FAC_FAITHFUL", 0) == 0;
     E->succ_ok = E->fast_ok && H.succ.ok && env_int("FAC_SUCCINCT", 1) != 0;
-    // engines without limits: the exact chain is all that can emit; only the succinct kernel has that shortcut
-    E->succ_exact = H.succ.ok && H.succ.exact_only && H.beam_width == 0 && !H.has_auto_beam && env_int("FAC_FAITHFUL", 0) == 0 &&
+    // engines on the reference's generic path (no limits at all, or per-pattern / per-type limits): order-independent
+    // only through the succinct kernel (exact-chain shortcut / limits mode)
+    E->succ_exact = H.succ.ok && (H.succ.exact_only || H.succ.limits_mode) && H.beam_width == 0 && !H.has_auto_beam && env_int("FAC_FAITHFUL", 0) == 0 &&
                     env_int("FAC_SUCCINCT", 1) != 0;
     E->succ_nt = (uint32_t)env_int("FAC_SUCC_THREADS", 1024);
     E->succ_tile = (uint32_t)std::max(32, env_int("FAC_SUCC_TILE", 1024));

@@ -449,7 +449,23 @@ fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_
         S = HostSuccinct();
         memset(S.sym_of, 31, sizeof(S.sym_of));
         S.exact_only = !A.has_global_limits && !A.has_pattern_limits;
-        bool ok = !A.has_mappings && (A.mef != 255 || S.exact_only) && N <= SUCC_MAX_NODES;
+        S.limits_mode = A.mef == 255 && !S.exact_only;
+        bool ok = !A.has_mappings && N <= SUCC_MAX_NODES;
+        if (S.limits_mode) {
+            // bound on the total edits of a state: the largest edits(e) budget plus, for limit sets without a total,
+            // the per-type caps (a state may arrive at such a node having spent edits of other types elsewhere)
+            uint32_t max_e = 0, cap[4] = {0, 0, 0, 0};
+            for (size_t li = A.has_global_limits ? 0 : 1; li < A.lim.size(); li++) {
+                const FacLimits &L = A.lim[li];
+                if (L.edits >= 0) max_e = std::max<uint32_t>(max_e, (uint32_t)L.edits);
+                else {
+                    const int16_t t[4] = {L.ins, L.del, L.sub, L.swp};
+                    for (int k = 0; k < 4; k++) cap[k] = std::max<uint32_t>(cap[k], t[k] < 0 ? 255u : (uint32_t)t[k]);
+                }
+            }
+            S.edit_bound = max_e + cap[0] + cap[1] + cap[2] + cap[3];
+            if (S.edit_bound == 0 || S.edit_bound > 6) ok = false;   // deeper budgets stay on the generic kernel
+        }
         std::vector<int> sym_of_char(128, -1);
         std::vector<uint32_t> chars;
         for (size_t i = 0; i < N && ok; i++)
@@ -482,10 +498,11 @@ fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_
                     S.old_of.push_back(c.second);
                 }
             }
-            S.prune_len.resize(N); S.prune_low.resize(N); S.out_idx.assign(N, FAC_NONE);
+            S.prune_len.resize(N); S.prune_low.resize(N); S.out_idx.assign(N, FAC_NONE); S.node_lim.assign(N, FAC_NONE);
             for (size_t h = 0; h < N; h++) {
                 const uint32_t old = S.old_of[h];
                 S.prune_len[h] = A.node_prune_len[old]; S.prune_low[h] = A.node_prune_low[old];
+                S.node_lim[h] = A.node_lim[old];
                 const auto &o = nodes[old].output;
                 if (!o.empty()) {
                     S.out_idx[h] = (uint32_t)(S.out2.size() / 4);
@@ -493,7 +510,7 @@ fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_
                         union { float f; uint32_t u; } g, w;
                         g.f = A.pat_glen[o[k]]; w.f = A.pat_weight[o[k]];
                         S.out2.push_back(o[k] | (k + 1 == o.size() ? 0x80000000u : 0u));
-                        S.out2.push_back(g.u); S.out2.push_back(w.u); S.out2.push_back(0);
+                        S.out2.push_back(g.u); S.out2.push_back(w.u); S.out2.push_back(A.pat_lim[o[k]]);
                     }
                 }
             }

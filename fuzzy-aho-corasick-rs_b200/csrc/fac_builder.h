@@ -64,6 +64,11 @@ struct HostSuccinct {
     // (src/search.rs:143-145) but rejects every output whose edit counts are not all zero (:166-168), so the
     // results are exactly the outputs along the exact chain from the root
     bool exact_only = false;
+    // per-pattern / per-type limits (the reference's generic MAX_EDITS_FAST = 255 path): permissions are evaluated
+    // per state from node_lim; edit_bound = an upper bound on the edits any state can accumulate
+    bool limits_mode = false;
+    uint32_t edit_bound = 0;
+    std::vector<uint32_t> node_lim;      // [N] BFS order: index into HostAutomaton::lim or FAC_NONE
     uint32_t n_syms = 0;
     uint8_t sym_of[256];                 // folded text byte -> dense symbol, 31 = not in the alphabet
     std::vector<uint32_t> bm, fc_sym;    // [N] child bitmap; first_child | in-symbol << 27

@@ -131,7 +131,8 @@ __device__ __forceinline__ void succ_warp_push(uint4 *stk, uint32_t &top, bool p
 
 #define SUCC_WQ_CAP 96u
 
-template <int NT>
+// LIM = limits mode: per-pattern / per-type FuzzyLimits evaluated per state (the reference's MAX_EDITS_FAST = 255 path).
+template <int NT, bool LIM>
 __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant__ SuccParams P) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
         if (P.exact_only) {
             // no edit is ever accepted (search.rs:166-168): one LANE per start window walks the exact chain
             for (uint32_t w = tid; w < count; w += NT)
-                n_states += succ_walk(K, R, out2, T, emit, tile_start + w, text_end, R(0u), 0.f, 0u, 0u, 0u);
+                n_states += succ_walk<false>(K, R, out2, T, emit, tile_start + w, text_end, R(0u), 0.f, 0u, 0u, 0u);
             __syncthreads();
             continue;
         }
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                     const uint32_t n = min(wn, 32u);
                     if (lane < n) {
                         const uint4 q = wq[wn - n + lane];
-                        n_states += succ_walk(K, R, out2, T, emit, start, text_end, R(q.x), __uint_as_float(q.y), q.z, q.w >> 10, q.w & 1023u);
+                        n_states += succ_walk<LIM>(K, R, out2, T, emit, start, text_end, R(q.x), __uint_as_float(q.y), q.z, q.w >> 10, q.w & 1023u);
                     }
                     wn -= n;
                     continue;
@@ -314,16 +315,16 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                 C.sub_m = C.del_m = 0;
                 if (active) {
                     n_states++;
-                    if (rec.w != FAC_NONE) succ_outputs(K, out2, emit, rec.w, pen, sv.z, start, start + (sv.w & 1023u));
-                    succ_make_ctx2(K, T, G, G2, start, text_end, sv.x, rec, pen, sv.z, sv.w, C);
+                    if (rec.w != FAC_NONE) succ_outputs<LIM>(K, out2, emit, rec.w, pen, sv.z, start, start + (sv.w & 1023u));
+                    succ_make_ctx2<LIM>(K, T, G, G2, start, text_end, sv.x, rec, pen, sv.z, sv.w, C);
                     const uint32_t jr = sv.w >> 10;
                     const uint32_t cur_s = (C.packed >> 8) & 0xFFu;
                     if (succ_has_edge(rec, cur_s)) {   // exact transition, search.rs:776-798
                         p_ex = true;
                         c_ex.node = succ_child(rec, cur_s); c_ex.pen = pen; c_ex.cnt = sv.z; c_ex.pos = succ_make_pos(jr + 1, jr + 1);
                     }
-                    p_sw = succ_swap2(K, R, C, c_sw);
-                    p_in = succ_ins2(K, C, sv.x, rec.w != FAC_NONE, c_in);
+                    p_sw = succ_swap2<LIM>(K, R, C, c_sw);
+                    p_in = succ_ins2<LIM>(K, C, sv.x, rec.w != FAC_NONE, c_in);
                 }
                 succ_warp_push(stk, top, p_ex, c_ex);
                 {

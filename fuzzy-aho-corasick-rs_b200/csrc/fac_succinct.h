@@ -43,8 +43,20 @@ struct SuccOut { uint32_t pat_last; uint32_t glen_bits; uint32_t weight_bits; ui
 
 struct SuccConsts {
     float thr, maxpen, pen_ins, pen_del, pen_swap;
-    int32_t mef;
+    int32_t mef;             // edit budget of the fast monomorphisations (1..6); in limits mode the largest
+                             // total edit count any FuzzyLimits of the engine admits
+    // limits mode (LIM = true): the reference's generic MAX_EDITS_FAST = 255 path (per-pattern / per-type limits)
+    const FacLimits *lim;    // [L] index 0 = global limits (valid iff has_global)
+    const uint32_t *node_lim;  // [N] BFS order: limits index of the pattern that created the node, or FAC_NONE
+    int32_t has_global;
 };
+
+// `limits.or(self.limits.as_ref())` (src/search.rs:93, 109, 125, 140, 160)
+FAC_HD bool succ_pick_limits(const SuccConsts &K, uint32_t idx, FacLimits &L) {
+    if (idx != FAC_NONE) { L = K.lim[idx]; return true; }
+    if (K.has_global) { L = K.lim[0]; return true; }
+    return false;
+}
 
 FAC_HD uint32_t succ_child(const SuccRec &r, uint32_t sym) { return (r.y & SUCC_FC_MASK) + FAC_POPC(r.x & ((1u << sym) - 1u)); }
 FAC_HD bool succ_has_edge(const SuccRec &r, uint32_t sym) { return (r.x >> sym) & 1u; }
@@ -52,10 +64,22 @@ FAC_HD uint32_t succ_make_pos(uint32_t jr, uint32_t mr) { return (jr << 10) | mr
 
 // Outputs of one node visit (search.rs:659-737): fast-path limit check is `edits > MAX_EDITS_FAST`,
 // never true here because no state exceeds the budget.
-template <class Emit>
+// In limits mode every pattern is checked against its own (or the global) limits: within_limits,
+// src/search.rs:151-169 (`pad` of the output entry is the pattern's limits index).
+template <bool LIM, class Emit>
 FAC_HD void succ_outputs(const SuccConsts &K, const SuccOut *out2, Emit &emit, uint32_t idx, float pen, uint32_t cnt, uint32_t sg, uint32_t eg) {
     for (;;) {
         const SuccOut o = out2[idx++];
+        if (LIM) {
+            FacLimits L;
+            bool ok;
+            if (succ_pick_limits(K, o.pad, L))
+                ok = fac_none_or_le(L.edits, (int)fac_edits_of(cnt)) && fac_none_or_le(L.ins, (int)(cnt & 0xFF)) &&
+                     fac_none_or_le(L.del, (int)((cnt >> 8) & 0xFF)) && fac_none_or_le(L.sub, (int)((cnt >> 16) & 0xFF)) &&
+                     fac_none_or_le(L.swp, (int)(cnt >> 24));
+            else ok = cnt == 0;
+            if (!ok) { if (o.pat_last >> 31) break; continue; }
+        }
         const float total = FAC_AS_FLOAT(o.glen_bits);
         const float sim = FAC_MUL(FAC_DIV(FAC_SUB(total, pen), total), FAC_AS_FLOAT(o.weight_bits));  // search.rs:698-699
         if (!(sim < K.thr)) emit(sg, eg, o.pat_last & 0x7FFFFFFFu, sim, cnt);
@@ -66,14 +90,14 @@ FAC_HD void succ_outputs(const SuccConsts &K, const SuccOut *out2, Emit &emit, u
 // A state that has spent its whole edit budget follows exact transitions only (sub / swap / ins /
 // del all need edits < MAX_EDITS_FAST, search.rs:810, 937, 1003, 1043): walk the chain with the
 // per-pop checks (ceiling :638-642, outputs :659-737, exact :776-798).  Returns the nodes visited.
-template <class Recs, class Text, class Emit>
+template <bool LIM, class Recs, class Text, class Emit>
 FAC_HD uint32_t succ_walk(const SuccConsts &K, const Recs &R, const SuccOut *out2, const Text &T, Emit &emit, uint32_t start, uint32_t text_end,
                           SuccRec rec, float pen, uint32_t cnt, uint32_t jr, uint32_t mr) {
     uint32_t steps = 0;
     for (;;) {
         steps++;
         if (pen > FAC_AS_FLOAT(rec.z)) break;
-        if (rec.w != FAC_NONE) succ_outputs(K, out2, emit, rec.w, pen, cnt, start, start + mr);
+        if (rec.w != FAC_NONE) succ_outputs<LIM>(K, out2, emit, rec.w, pen, cnt, start, start + mr);
         const uint32_t j = start + jr;
         if (j >= text_end) break;
         const uint32_t s = T.sym(j);
@@ -84,7 +108,7 @@ FAC_HD uint32_t succ_walk(const SuccConsts &K, const Recs &R, const SuccOut *out
     return steps;
 }
 
-enum : uint32_t { SUCC_F_IN_TEXT = 1u, SUCC_F_LAST = 2u, SUCC_F_DEL = 4u, SUCC_F_HAS_NXT = 8u };
+enum : uint32_t { SUCC_F_IN_TEXT = 1u, SUCC_F_LAST = 2u, SUCC_F_DEL = 4u, SUCC_F_HAS_NXT = 8u, SUCC_F_INS = 16u };
 
 // ---- survivor masks -------------------------------------------------------------------------------
 // For a state on its last edit the dead-end filter keeps a child c iff
@@ -109,7 +133,12 @@ struct SuccCtx2 {
 // outside  outm | gm2[node][y1][y2]  walks c -> g and stops there without visiting an output node, i.e. it
 // cannot emit a candidate: dropping it is result-neutral (only the visited-state statistic changes).
 // `G2(node, y1, y2)` returns that set, or the one-deep set gm[node][y1] for nodes beyond the table.
-template <class Text, class GM, class GM2>
+// Limits mode: the per-state permissions follow within_limits_*_ahead of the limits of the pattern that created
+// the node (src/search.rs:66-148); with neither pattern nor global limits only a fresh state may substitute
+// (:143-145).  The dead-end filter does not exist on that path, but dropping exhausted children whose exact walk
+// cannot reach an output stays result-neutral, so the same masks are applied once `last` (no limits of the engine
+// admit another edit after this one).
+template <bool LIM, class Text, class GM, class GM2>
 FAC_HD void succ_make_ctx2(const SuccConsts &K, const Text &T, const GM &G, const GM2 &G2, uint32_t start, uint32_t text_end, uint32_t node,
                            const SuccRec &rec, float pen, uint32_t cnt, uint32_t pos, SuccCtx2 &C) {
     // Text contract: T.sym(j) == SUCC_NOSYM and T.byte(j) == 0 for text_end <= j <= start + look-ahead, so the
@@ -119,16 +148,27 @@ FAC_HD void succ_make_ctx2(const SuccConsts &K, const Text &T, const GM &G, cons
     const bool last = (int)fac_edits_of(cnt) + 1 >= K.mef;
     const bool in_text = j < text_end;
     const uint32_t cur_b = T.byte(j), cur_s = T.sym(j), nxt_s = T.sym(j + 1), nxt2_s = T.sym(j + 2);
-    const bool del_ok = K.pen_del <= FAC_SUB(K.maxpen, pen);  // search.rs:1035
+    bool del_ok = K.pen_del <= FAC_SUB(K.maxpen, pen);  // search.rs:1035
+    bool sub_ok = true, ins_ok = true;
+    if (LIM) {
+        FacLimits L;
+        const int edits = (int)fac_edits_of(cnt);
+        if (succ_pick_limits(K, K.node_lim[node], L)) {
+            const bool e_ok = fac_none_or_lt(L.edits, edits);
+            sub_ok = e_ok && fac_none_or_lt(L.sub, (int)((cnt >> 16) & 0xFF));
+            ins_ok = e_ok && fac_none_or_lt(L.ins, (int)(cnt & 0xFF));
+            del_ok = del_ok && e_ok && fac_none_or_lt(L.del, (int)((cnt >> 8) & 0xFF));
+        } else { sub_ok = edits == 0 && ((cnt >> 16) & 0xFF) == 0; ins_ok = false; del_ok = false; }
+    }
     const uint32_t flags = (last ? SUCC_F_LAST : 0u) | (in_text ? SUCC_F_IN_TEXT : 0u) | (j + 1 < text_end ? SUCC_F_HAS_NXT : 0u) |
-                           (del_ok ? SUCC_F_DEL : 0u);
+                           (del_ok ? SUCC_F_DEL : 0u) | (ins_ok ? SUCC_F_INS : 0u);
     uint32_t keep_sub = 0xFFFFFFFFu, keep_del = 0xFFFFFFFFu;  // states not on their last edit keep every child
     if (last) {
         const uint32_t outm = G(node, SUCC_NOSYM);
         keep_sub = outm | (nxt_s != SUCC_NOSYM ? G2(node, nxt_s, nxt2_s) : 0u);
         keep_del = outm | (cur_s != SUCC_NOSYM ? G2(node, cur_s, nxt_s) : 0u);
     }
-    const uint32_t sub_m = in_text ? (rec.x & keep_sub & ~(1u << cur_s)) : 0u;
+    const uint32_t sub_m = (in_text && sub_ok) ? (rec.x & keep_sub & ~(1u << cur_s)) : 0u;
     const uint32_t del_m = del_ok ? (rec.x & keep_del) : 0u;
     C.bm = rec.x; C.fc = rec.y; C.pen = pen; C.cnt = cnt; C.pos = pos;
     C.packed = cur_b | (cur_s << 8) | (nxt_s << 16);
@@ -171,7 +211,7 @@ FAC_HD bool succ_item2(const SuccConsts &K, const float *sub_pen, const SuccCtx2
 // Swap (search.rs:935-989: node -text[j+1]-> x -text[j]-> n2, matched_start unchanged) and insertion
 // (search.rs:994-1029: forbidden before anything is consumed, matched_end unchanged, dead-end filter on the
 // current node when this is the last edit).
-template <class Recs>
+template <bool LIM, class Recs>
 FAC_HD bool succ_swap2(const SuccConsts &K, const Recs &R, const SuccCtx2 &C, FacState &out) {
     if ((C.flags & (SUCC_F_IN_TEXT | SUCC_F_HAS_NXT)) != (SUCC_F_IN_TEXT | SUCC_F_HAS_NXT)) return false;
     if (!(K.pen_swap <= FAC_SUB(K.maxpen, C.pen))) return false;
@@ -181,14 +221,21 @@ FAC_HD bool succ_swap2(const SuccConsts &K, const Recs &R, const SuccCtx2 &C, Fa
     if (!succ_has_edge(rx, cur_s)) return false;
     const uint32_t jr = C.pos >> 10;
     out.node = succ_child(rx, cur_s); out.pen = FAC_ADD(C.pen, K.pen_swap); out.cnt = C.cnt + 0x1000000u; out.pos = succ_make_pos(jr + 2, jr + 2);
+    if (LIM) {  // within_limits_swap_ahead of the TARGET node's limits (search.rs:119-130, 962-975)
+        FacLimits L;
+        if (!succ_pick_limits(K, K.node_lim[out.node], L)) return false;
+        if (!(fac_none_or_lt(L.edits, (int)fac_edits_of(C.cnt)) && fac_none_or_lt(L.swp, (int)(C.cnt >> 24)))) return false;
+    }
     return true;
 }
+template <bool LIM>
 FAC_HD bool succ_ins2(const SuccConsts &K, const SuccCtx2 &C, uint32_t node, bool has_out, FacState &out) {
     if (!(C.flags & SUCC_F_IN_TEXT)) return false;
     const uint32_t jr = C.pos >> 10, mr = C.pos & 1023u;
     if (mr == 0 && jr == 0) return false;
     if (!(K.pen_ins <= FAC_SUB(K.maxpen, C.pen))) return false;
-    if ((C.flags & SUCC_F_LAST) && !has_out) {
+    if (!(C.flags & SUCC_F_INS)) return false;
+    if (!LIM && (C.flags & SUCC_F_LAST) && !has_out) {
         if (!(C.flags & SUCC_F_HAS_NXT) || !((C.bm >> ((C.packed >> 16) & 0xFFu)) & 1u)) return false;
     }
     out.node = node; out.pen = FAC_ADD(C.pen, K.pen_ins); out.cnt = C.cnt + 1u; out.pos = succ_make_pos(jr + 1, mr);

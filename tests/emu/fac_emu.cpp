@@ -224,7 +224,9 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
         recs[i] = SuccRec{S.bm[i], S.fc_sym[i], c.u, S.out_idx[i]};
     }
     SuccConsts K;
-    K.thr = thr; K.maxpen = FAC_AS_FLOAT(recs[0].z); K.pen_ins = HA.pen_ins; K.pen_del = HA.pen_del; K.pen_swap = HA.pen_swap; K.mef = HA.mef;
+    K.thr = thr; K.maxpen = FAC_AS_FLOAT(recs[0].z); K.pen_ins = HA.pen_ins; K.pen_del = HA.pen_del; K.pen_swap = HA.pen_swap; K.mef = S.limits_mode ? (int32_t)S.edit_bound : HA.mef;
+    K.lim = HA.lim.data(); K.node_lim = S.node_lim.data(); K.has_global = HA.has_global_limits;
+    const bool LIMM = S.limits_mode;
     const EmuRecs R{recs.data()};
     const EmuGM G{S.gmask.data(), S.gm_nodes, recs.data()};
     const EmuGM2 G2{S.gmask2.data(), S.gm2_nodes, G};
@@ -244,7 +246,7 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
             }
         }
         if (S.exact_only) {  // engine without FuzzyLimits: only the exact chain from the root can emit
-            states += succ_walk(K, R, out2, T, emit, start, text_end, R(0u), 0.f, 0u, 0u, 0u);
+            states += succ_walk<false>(K, R, out2, T, emit, start, text_end, R(0u), 0.f, 0u, 0u, 0u);
             continue;
         }
         std::vector<FacState> stack;
@@ -260,20 +262,20 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
             states++;
             const SuccRec rec = R(s.node);
             if (s.pen > FAC_AS_FLOAT(rec.z)) continue;  /*dead*/
-            if (rec.w != FAC_NONE) succ_outputs(K, out2, emit, rec.w, s.pen, s.cnt, start, start + (s.pos & 1023u));
+            if (rec.w != FAC_NONE) { if (LIMM) succ_outputs<true>(K, out2, emit, rec.w, s.pen, s.cnt, start, start + (s.pos & 1023u)); else succ_outputs<false>(K, out2, emit, rec.w, s.pen, s.cnt, start, start + (s.pos & 1023u)); }
             SuccCtx2 C;
-            succ_make_ctx2(K, T, G, G2, start, text_end, s.node, rec, s.pen, s.cnt, s.pos, C);
+            if (LIMM) succ_make_ctx2<true>(K, T, G, G2, start, text_end, s.node, rec, s.pen, s.cnt, s.pos, C); else succ_make_ctx2<false>(K, T, G, G2, start, text_end, s.node, rec, s.pen, s.cnt, s.pos, C);
             const bool last = (C.flags & SUCC_F_LAST) != 0;
             const uint32_t jr = s.pos >> 10;
             auto child = [&](const FacState &c) {
-                if (last) { const uint32_t w_ = succ_walk(K, R, out2, T, emit, start, text_end, R(c.node), c.pen, c.cnt, c.pos >> 10, c.pos & 1023u); states += w_; st_walk += w_; st_surv++; lane_work += w_; }
+                if (last) { const uint32_t w_ = LIMM ? succ_walk<true>(K, R, out2, T, emit, start, text_end, R(c.node), c.pen, c.cnt, c.pos >> 10, c.pos & 1023u) : succ_walk<false>(K, R, out2, T, emit, start, text_end, R(c.node), c.pen, c.cnt, c.pos >> 10, c.pos & 1023u); states += w_; st_walk += w_; st_surv++; lane_work += w_; }
                 else stack.push_back(c);
             };
             const uint32_t cur_s = (C.packed >> 8) & 0xFFu;
             if (succ_has_edge(rec, cur_s)) stack.push_back(FacState{succ_child(rec, cur_s), s.pen, s.cnt, succ_make_pos(jr + 1, jr + 1)});
             FacState c;
-            if (succ_swap2(K, R, C, c)) child(c);
-            if (succ_ins2(K, C, s.node, rec.w != FAC_NONE, c)) child(c);
+            if (LIMM ? succ_swap2<true>(K, R, C, c) : succ_swap2<false>(K, R, C, c)) child(c);
+            if (LIMM ? succ_ins2<true>(K, C, s.node, rec.w != FAC_NONE, c) : succ_ins2<false>(K, C, s.node, rec.w != FAC_NONE, c)) child(c);
             const uint32_t n_items = FAC_POPC(C.sub_m) + FAC_POPC(C.del_m);
             st_pop++; st_items += n_items; st_deg_hist[std::min<uint32_t>(n_items, 32)]++;
             for (uint32_t r = 0; r < n_items; r++)

@@ -118,8 +118,14 @@ def rand_dense_case(r, backend):
             pats.append(w)
     edits = r.choice([1, 2, 2, 3])
     ci = r.random() < 0.4
-    b = FuzzyAhoCorasickBuilder.new(backend).case_insensitive(ci).fuzzy(FuzzyLimits.new().edits(edits))
-    desc = {"alpha": alpha, "npat": npat, "edits": edits, "ci": ci}
+    lim_mode = r.choice([0, 0, 0, 1, 2, 3])   # 0: edits(e) fast path; 1: per-type global; 2: per-pattern limits; 3: no limits
+    b = FuzzyAhoCorasickBuilder.new(backend).case_insensitive(ci)
+    if lim_mode == 0:
+        b = b.fuzzy(FuzzyLimits.new().edits(edits))
+    elif lim_mode == 1:
+        b = b.fuzzy(r.choice([FuzzyLimits.new().substitutions(1).deletions(1), FuzzyLimits.new().insertions(1).swaps(1),
+                              FuzzyLimits.new().edits(2).substitutions(1), FuzzyLimits.new().edits(2).swaps(0)]))
+    desc = {"alpha": alpha, "npat": npat, "edits": edits, "ci": ci, "lim_mode": lim_mode}
     if r.random() < 0.4:
         b = b.penalties(FuzzyPenalties.default().swap(r.choice([0.3, 0.6, 0.52])).insertion(r.choice([0.5, 0.25]))
                         .deletion(r.choice([0.8, 0.91, 0.4])).substitution(r.choice([1.0, 1.43, 0.7])))
@@ -132,7 +138,13 @@ def rand_dense_case(r, backend):
         b = b.similarity(pairs)
         desc["sim"] = len(pairs)
     plist = pats
-    if r.random() < 0.3:
+    if lim_mode == 2:
+        kinds = [FuzzyLimits.new().edits(1), FuzzyLimits.new().edits(2), FuzzyLimits.new().edits(2).swaps(0),
+                 FuzzyLimits.new().substitutions(1).deletions(1)]
+        plist = [Pattern.from_(p).fuzzy(r.choice(kinds)) if r.random() < 0.8 else p for p in pats]
+        if r.random() < 0.5:
+            plist = [(q.weight(r.choice([0.75, 1.0, 1.5])) if isinstance(q, Pattern) and r.random() < 0.5 else q) for q in plist]
+    elif r.random() < 0.3:
         plist = [Pattern.from_(p).weight(r.choice([0.75, 1.0, 1.25])) if r.random() < 0.5 else p for p in pats]
         desc["weights"] = True
     engine = b.build(plist)

@@ -81,10 +81,12 @@ def test_succinct_dense_tries(oracle):
     emu = EmuBackend(tile=16)
     emu.succinct = True
     r1, r2 = random.Random(177), random.Random(177)
-    for t in range(25):
+    modes = set()
+    for t in range(40):
         eo, hay, thr, desc = rand_dense_case(r1, oracle)
         ee, _, _, _ = rand_dense_case(r2, emu)
-        o = eo.search(hay[:600], SearchOptions.new().threshold(thr))
-        e = ee.search(hay[:600], SearchOptions.new().threshold(thr))
+        o = eo.search(hay[:400], SearchOptions.new().threshold(thr))
+        e = ee.search(hay[:400], SearchOptions.new().threshold(thr))
         assert o.tuples() == e.tuples(), (t, desc)
-    assert emu.succinct_used == 25
+        modes.add(desc["lim_mode"])
+    assert emu.succinct_used == 40 and modes == {0, 1, 2, 3}
