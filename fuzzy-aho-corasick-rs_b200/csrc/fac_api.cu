@@ -200,7 +200,7 @@ struct fac_engine {
     const uint64_t *d_bp_mask = nullptr;
     const uint8_t *d_bp_m = nullptr;
     // succinct-trie fast kernel (fac_succinct.cuh)
-    bool succ_ok = false, succ_exact = false;
+    bool succ_ok = false, succ_generic_ok = false;
     const uint32_t *d_s_bm = nullptr, *d_s_fc = nullptr, *d_s_out_idx = nullptr, *d_s_out2 = nullptr;
     const float *d_s_plen = nullptr, *d_s_plow = nullptr, *d_s_subpen = nullptr;
     const uint8_t *d_s_symof = nullptr;
@@ -445,7 +445,7 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
     P.per_window = R.d_per_window;
     P.use_tma = E->use_tma;
     const size_t smem = expand_smem_bytes(E, ascii, P.smem_text_cap);
-    const bool use_succ = R.fast && (E->succ_ok || E->succ_exact) && ascii && (!explicit_tiles || R.slices) && !R.beam && !R.d_per_window;
+    const bool use_succ = R.fast && (E->succ_ok || E->succ_generic_ok) && ascii && (!explicit_tiles || R.slices) && !R.beam && !R.d_per_window;
     // an exact-only engine is "fast" only through the succinct kernel; the generic FAST kernel needs an edit budget
     const bool fast_run = R.fast && (E->fast_ok || use_succ);
     if (use_succ && explicit_tiles && max_count > E->succ_tile) { set_err("internal: slice tile larger than the succinct tile"); return FAC_INVALID_ARGUMENT; }
@@ -1022,12 +1022,12 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
         bool fallback = false;
         CKS(prefilter_slices(E, ws, d_text, (uint32_t)n, thr, slices, &fallback, stats));
         if (!fallback) {
-            const uint32_t tile_w = (E->succ_ok || E->succ_exact) ? E->succ_tile : 64u;
+            const uint32_t tile_w = (E->succ_ok || E->succ_generic_ok) ? E->succ_tile : 64u;
             size_t si = 0;
             while (si < slices.size()) {
                 // batches of slices bounded by a window budget so the candidate buffers stay modest
                 ExpandRun R;
-                R.tv = tv; R.d_windows = ws->windows.as<FacWindow>(); R.thr = thr; R.fast = E->fast_ok || (E->succ_exact && ascii); R.slices = &slices;
+                R.tv = tv; R.d_windows = ws->windows.as<FacWindow>(); R.thr = thr; R.fast = E->fast_ok || (E->succ_generic_ok && ascii); R.slices = &slices;
                 uint64_t wins = 0;
                 const size_t s0 = si;
                 for (; si < slices.size() && wins < (1u << 25); si++) {
@@ -1048,7 +1048,7 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
     const uint64_t SEG = (uint64_t)env_int("FAC_SEGMENT_WINDOWS", 1 << 25);
     uint32_t tile = E->default_tile;
     bool calibrated = tile != 0;
-    if ((E->succ_ok || E->succ_exact) && ascii) { calibrated = true; if (!tile) tile = 8; }  // the succinct kernel tiles by itself
+    if ((E->succ_ok || E->succ_generic_ok) && ascii) { calibrated = true; if (!tile) tile = 8; }  // the succinct kernel tiles by itself
     if (!calibrated) tile = 4;
     uint64_t pos = g_begin;
     while (pos < g_end) {
@@ -1056,7 +1056,7 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
         if (!calibrated) seg = std::min<uint64_t>(seg, 1 << 16);  // small calibration segment decides the tile size
         ExpandRun R;
         R.tv = tv; R.seg_begin = (uint32_t)pos; R.seg_end = (uint32_t)(pos + seg); R.text_end = (uint32_t)n;
-        R.d_windows = ws->windows.as<FacWindow>(); R.thr = thr; R.fast = E->fast_ok || (E->succ_exact && ascii);
+        R.d_windows = ws->windows.as<FacWindow>(); R.thr = thr; R.fast = E->fast_ok || (E->succ_generic_ok && ascii);
         double spw = 0;
         // keep what is already in m_a: grow by copy before the reduction writes
         CKS(grow_keep(ws->m_a, n_matches * sizeof(WMatch), (n_matches + (1u << 20)) * sizeof(WMatch), s));
@@ -1185,7 +1185,7 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
     E->succ_ok = E->fast_ok && H.succ.ok && env_int("FAC_SUCCINCT", 1) != 0;
     // engines on the reference's generic path (no limits at all, or per-pattern / per-type limits): order-independent
     // only through the succinct kernel (exact-chain shortcut / limits mode)
-    E->succ_exact = H.succ.ok && (H.succ.exact_only || H.succ.limits_mode) && H.beam_width == 0 && !H.has_auto_beam && env_int("FAC_FAITHFUL", 0) == 0 &&
+    E->succ_generic_ok = H.succ.ok && (H.succ.exact_only || H.succ.limits_mode) && H.beam_width == 0 && !H.has_auto_beam && env_int("FAC_FAITHFUL", 0) == 0 &&
                     env_int("FAC_SUCCINCT", 1) != 0;
     E->succ_nt = (uint32_t)env_int("FAC_SUCC_THREADS", 1024);
     E->succ_tile = (uint32_t)std::max(32, env_int("FAC_SUCC_TILE", 1024));
