@@ -287,7 +287,7 @@ fac_status launch_succ_t(const SuccParams &P, uint32_t grid, size_t smem, cudaSt
     CK(cudaGetLastError());
     return FAC_OK;
 }
-fac_status launch_succinct(const fac_engine *E, Workspace *ws, const uint8_t *d_text, float thr, uint32_t seg_begin, uint32_t seg_end,
+fac_status launch_succinct(const fac_engine *E, Workspace *ws, const TextView &tv, float thr, uint32_t seg_begin, uint32_t seg_end,
                            uint32_t text_end, FacCand *cands, uint32_t cand_cap, cudaStream_t s, const uint4 *d_tiles = nullptr,
                            uint32_t n_explicit = 0) {
     const fac::HostSuccinct &S = E->host.succ;
@@ -297,7 +297,7 @@ fac_status launch_succinct(const fac_engine *E, Workspace *ws, const uint8_t *d_
     CK(cudaGetLastError());
     SuccParams P;
     memset(&P, 0, sizeof(P));
-    P.rec = ws->srec.as<uint4>(); P.out2 = (const uint4 *)E->d_s_out2; P.sub_pen = E->d_s_subpen; P.sym_of = E->d_s_symof; P.text = d_text;
+    P.rec = ws->srec.as<uint4>(); P.out2 = (const uint4 *)E->d_s_out2; P.sub_pen = E->d_s_subpen; P.sym_of = E->d_s_symof; P.text = tv.bytes; P.first = tv.ascii ? nullptr : tv.first;
     P.n_nodes = N;
     P.K.thr = thr;
     P.K.maxpen = S.prune_len[0] - S.prune_low[0] * thr;  // search.rs:487 (host compiled without contraction)
@@ -317,7 +317,7 @@ fac_status launch_succinct(const fac_engine *E, Workspace *ws, const uint8_t *d_
     P.stack_cap = E->succ_stack ? E->succ_stack : (!deep ? 128u : 384u);
     P.text_cap = (P.tile + P.lookahead + 16u + 15u) & ~15u;
     P.gm = E->d_s_gm; P.gm_nodes = S.gm_nodes; P.gm2 = E->d_s_gm2; P.gm2_nodes = S.gm2_nodes;
-    const size_t fixed = (size_t)nw * (P.stack_cap + SUCC_WQ_CAP) * 16 + 32 * 128 * 4 + (size_t)P.text_cap * 3 + 256;
+    const size_t fixed = (size_t)nw * (P.stack_cap + SUCC_WQ_CAP) * 16 + 32 * SUCC_SP_STRIDE * 4 + (size_t)P.text_cap * (tv.ascii ? 3 : 6) + 256;
     const size_t budget = (size_t)E->smem_optin - 1024;  // static shared + reserve
     if (fixed + 16 * 64 > budget) { set_err("succinct kernel: shared-memory budget too small for the configured stack / tile"); return FAC_UNSUPPORTED; }
     P.n_smem_nodes = (uint32_t)std::min<size_t>(N, (budget - fixed) / 16);
@@ -445,7 +445,8 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
     P.per_window = R.d_per_window;
     P.use_tma = E->use_tma;
     const size_t smem = expand_smem_bytes(E, ascii, P.smem_text_cap);
-    const bool use_succ = R.fast && (E->succ_ok || E->succ_generic_ok) && ascii && (!explicit_tiles || R.slices) && !R.beam && !R.d_per_window;
+    const bool succ_text = ascii || E->host.succ.unicode_text_ok;   // K1 first-char stream works too
+    const bool use_succ = R.fast && (E->succ_ok || E->succ_generic_ok) && succ_text && (!explicit_tiles || R.slices) && !R.beam && !R.d_per_window;
     // an exact-only engine is "fast" only through the succinct kernel; the generic FAST kernel needs an edit budget
     const bool fast_run = R.fast && (E->fast_ok || use_succ);
     if (use_succ && explicit_tiles && max_count > E->succ_tile) { set_err("internal: slice tile larger than the succinct tile"); return FAC_INVALID_ARGUMENT; }
@@ -464,7 +465,7 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
             else k_expand_beam<256><<<grid, 256, 0, s>>>(P, R.bw);
             CK(cudaGetLastError());
         } else if (use_succ) {
-            CKS(launch_succinct(E, ws, R.tv.bytes, R.thr, R.seg_begin, R.seg_end, R.text_end, ws->cands.as<FacCand>(), cand_cap, s,
+            CKS(launch_succinct(E, ws, R.tv, R.thr, R.seg_begin, R.seg_end, R.text_end, ws->cands.as<FacCand>(), cand_cap, s,
                                 explicit_tiles ? ws->tiles.as<uint4>() : nullptr, n_tiles));
             stats.launches++;
         } else CKS(launch_expand(P, grid, smem, s, fast_run));
@@ -1048,7 +1049,7 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
     const uint64_t SEG = (uint64_t)env_int("FAC_SEGMENT_WINDOWS", 1 << 25);
     uint32_t tile = E->default_tile;
     bool calibrated = tile != 0;
-    if ((E->succ_ok || E->succ_generic_ok) && ascii) { calibrated = true; if (!tile) tile = 8; }  // the succinct kernel tiles by itself
+    if ((E->succ_ok || E->succ_generic_ok) && (ascii || E->host.succ.unicode_text_ok)) { calibrated = true; if (!tile) tile = 8; }  // the succinct kernel tiles by itself
     if (!calibrated) tile = 4;
     uint64_t pos = g_begin;
     while (pos < g_end) {
@@ -1056,7 +1057,7 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
         if (!calibrated) seg = std::min<uint64_t>(seg, 1 << 16);  // small calibration segment decides the tile size
         ExpandRun R;
         R.tv = tv; R.seg_begin = (uint32_t)pos; R.seg_end = (uint32_t)(pos + seg); R.text_end = (uint32_t)n;
-        R.d_windows = ws->windows.as<FacWindow>(); R.thr = thr; R.fast = E->fast_ok || (E->succ_generic_ok && ascii);
+        R.d_windows = ws->windows.as<FacWindow>(); R.thr = thr; R.fast = E->fast_ok || (E->succ_generic_ok && (ascii || E->host.succ.unicode_text_ok));
         double spw = 0;
         // keep what is already in m_a: grow by copy before the reduction writes
         CKS(grow_keep(ws->m_a, n_matches * sizeof(WMatch), (n_matches + (1u << 20)) * sizeof(WMatch), s));

@@ -516,15 +516,21 @@ fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_
             }
             if (S.out2.empty()) S.out2.assign(4, 0x80000000u);
             const float inf = std::numeric_limits<float>::infinity();
-            S.sub_pen.assign(32 * 128, inf);
+            S.sub_pen.assign(32 * SUCC_SP_STRIDE, inf);
             for (size_t k = 0; k < chars.size(); k++)
                 for (uint32_t b = 0; b < 128; b++) {
                     const float sm = chars[k] == b ? 1.0f : A.sim_ascii[chars[k] * 128 + b];  // get_similarity, search.rs:76-82
                     if (sm < A.min_sym) continue;                                              // search.rs:822-825
                     volatile float one_minus = 1.0f - sm;
                     volatile float pp = A.pen_sub * one_minus;                                 // search.rs:829
-                    S.sub_pen[k * 128 + b] = pp;
+                    S.sub_pen[k * SUCC_SP_STRIDE + b] = pp;
                 }
+            // non-ASCII text first chars: similarity 0 with every (ASCII) pattern char unless the similarity map says otherwise
+            S.unicode_text_ok = A.sim_keys.empty();
+            if (!(0.0f < A.min_sym)) {
+                volatile float pp0 = A.pen_sub * (1.0f - 0.0f);
+                for (size_t k = 0; k < chars.size(); k++) S.sub_pen[k * SUCC_SP_STRIDE + SUCC_NONASCII] = pp0;
+            }
             S.first_mask = S.bm[0];
             for (uint32_t c = 0; c < (uint32_t)FAC_POPC_HOST(S.bm[0]); c++) S.second_mask |= S.bm[(S.fc_sym[0] & SUCC_FC_MASK) + c];
             S.first_mask |= S.second_mask;

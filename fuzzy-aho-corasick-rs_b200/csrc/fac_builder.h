@@ -66,6 +66,9 @@ struct HostSuccinct {
     bool exact_only = false;
     // per-pattern / per-type limits (the reference's generic MAX_EDITS_FAST = 255 path): permissions are evaluated
     // per state from node_lim; edit_bound = an upper bound on the edits any state can accumulate
+    // non-ASCII haystacks (grapheme stream of first chars from K1) are inside the kernel's domain when no similarity
+    // entry involves a non-ASCII char
+    bool unicode_text_ok = false;
     bool limits_mode = false;
     uint32_t edit_bound = 0;
     std::vector<uint32_t> node_lim;      // [N] BFS order: index into HostAutomaton::lim or FAC_NONE
@@ -75,7 +78,7 @@ struct HostSuccinct {
     std::vector<float> prune_len, prune_low;  // [N] in BFS numbering
     std::vector<uint32_t> out_idx;       // [N] first entry in out2 or FAC_NONE
     std::vector<uint32_t> out2;          // 4 words per entry: pat | last << 31, glen f32 bits, weight f32 bits, 0
-    std::vector<float> sub_pen;          // [32 * 128] pen_sub * (1 - sim(edge char, text byte)), +inf below min_symbol_similarity
+    std::vector<float> sub_pen;          // [32][SUCC_SP_STRIDE] pen_sub * (1 - sim(edge char, text first char)), +inf below min_symbol_similarity
     std::vector<uint32_t> old_of;        // [N] reference node index of BFS node i
     uint32_t first_mask = 0, second_mask = 0;  // 2-gram window skip (search.rs:504-521) in symbol space
     // grandchild masks of the first gm_nodes BFS nodes (fac_succinct.h): [gm_nodes * 32]

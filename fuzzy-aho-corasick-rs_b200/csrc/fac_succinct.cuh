@@ -29,9 +29,10 @@
 struct SuccParams {
     const uint4 *rec;        // [n_nodes] per-call node records (SuccRec)
     const uint4 *out2;       // SuccOut entries
-    const float *sub_pen;    // [32 * 128]
+    const float *sub_pen;    // [32][SUCC_SP_STRIDE]
     const uint8_t *sym_of;   // [256]
-    const uint8_t *text;     // ASCII haystack bytes
+    const uint8_t *text;     // ASCII haystack bytes, or
+    const uint32_t *first;   // non-ASCII haystack: first char of every folded grapheme (K1 stream); null for ASCII
     uint32_t n_nodes, n_smem_nodes;
     SuccConsts K;
     int32_t ci, wskip;
@@ -145,13 +146,13 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
     uint4 *s_stack = s_rec + P.n_smem_nodes;
     uint4 *s_wq = s_stack + (size_t)NW * P.stack_cap;
     float *s_subpen = reinterpret_cast<float *>(s_wq + (size_t)NW * SUCC_WQ_CAP);
-    uint8_t *s_raw = reinterpret_cast<uint8_t *>(s_subpen + 32 * 128);
-    uint8_t *s_byte = s_raw + P.text_cap;
+    uint8_t *s_raw = reinterpret_cast<uint8_t *>(s_subpen + 32 * SUCC_SP_STRIDE);
+    uint8_t *s_byte = s_raw + (size_t)P.text_cap * (P.first ? 4u : 1u);
     uint8_t *s_sym = s_byte + P.text_cap;
     uint8_t *s_symof = s_sym + P.text_cap;
 
     for (uint32_t k = tid; k < P.n_smem_nodes; k += NT) s_rec[k] = P.rec[k];
-    for (uint32_t k = tid; k < 32 * 128; k += NT) s_subpen[k] = P.sub_pen[k];
+    for (uint32_t k = tid; k < 32 * SUCC_SP_STRIDE; k += NT) s_subpen[k] = P.sub_pen[k];
     for (uint32_t k = tid; k < 256; k += NT) s_symof[k] = P.sym_of[k];
     if (tid == 0) fac_mbar_init(&s_mbar, 1);
     __syncthreads();
@@ -178,27 +179,36 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
         else { tile_start = P.seg_begin + t * P.tile; count = min(P.tile, P.seg_end - tile_start); text_end = P.text_end; }
 
         // ---- stage the tile: TMA bulk copy of the 16-byte aligned body, plain loads for the tail ----
-        uint32_t lead = (uint32_t)(((uintptr_t)(P.text + tile_start)) & 15u);
+        // elements are haystack bytes (ASCII) or u32 first chars of the K1 grapheme stream (non-ASCII haystack)
+        const uint32_t esz = P.first ? 4u : 1u;
+        const uint8_t *src = P.first ? reinterpret_cast<const uint8_t *>(P.first) : P.text;
+        uint32_t lead = (uint32_t)(((uintptr_t)(src + (size_t)tile_start * esz)) & 15u) / esz;
         if (lead > tile_start) lead = 0;
         const uint32_t base = tile_start - lead;
         const uint32_t span = count + P.lookahead + lead;                 // positions the tile must answer
-        const uint32_t avail = min(span, text_end - base);                // bytes that exist
-        const bool aligned = ((((uintptr_t)(P.text + base)) & 15u) == 0u);
-        const uint32_t bulk = aligned ? (avail & ~15u) : 0u;
+        const uint32_t avail = min(span, text_end - base);                // elements that exist
+        const bool aligned = ((((uintptr_t)(src + (size_t)base * esz)) & 15u) == 0u);
+        const uint32_t bulk = aligned ? ((avail * esz) & ~15u) : 0u;      // bytes
         if (bulk && tid == 0) {
             fac_fence_proxy_async();
             fac_mbar_expect_tx(&s_mbar, bulk);
-            fac_tma_load_1d(s_raw, P.text + base, bulk, &s_mbar);
+            fac_tma_load_1d(s_raw, src + (size_t)base * esz, bulk, &s_mbar);
         }
-        for (uint32_t k = bulk + tid; k < avail; k += NT) s_raw[k] = P.text[base + k];
+        for (uint32_t k = bulk + tid; k < avail * esz; k += NT) s_raw[k] = src[(size_t)base * esz + k];
         if (bulk) { fac_mbar_wait(&s_mbar, mbar_phase & 1u); mbar_phase++; }
         __syncthreads();
         for (uint32_t k = tid; k < span; k += NT) {
             uint32_t b = 0, s = SUCC_NOSYM;
             if (k < avail) {
-                b = s_raw[k];
-                if (P.ci && b >= 'A' && b <= 'Z') b += 32u;   // to_ascii_lowercase, grapheme.rs:110-117
-                s = s_symof[b];
+                if (P.first) {   // already folded by K1; non-ASCII first chars match no edge and have similarity 0
+                    const uint32_t c = reinterpret_cast<const uint32_t *>(s_raw)[k];
+                    b = c < 128u ? c : SUCC_NONASCII;
+                    s = c < 128u ? s_symof[c] : SUCC_NOSYM;
+                } else {
+                    b = s_raw[k];
+                    if (P.ci && b >= 'A' && b <= 'Z') b += 32u;   // to_ascii_lowercase, grapheme.rs:110-117
+                    s = s_symof[b];
+                }
             }
             s_byte[k] = (uint8_t)b; s_sym[k] = (uint8_t)s;
         }
@@ -220,9 +230,10 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
             if (w >= count) break;
             const uint32_t start = tile_start + w;
             if (P.wskip) {  // 2-gram window skip (search.rs:535-553); result-neutral
-                if (!((P.first_mask >> T.sym(start)) & 1u)) {
+                // only ASCII first chars take part in the skip test (`c < 128 && !bit`, search.rs:538-551)
+                if (T.byte(start) != SUCC_NONASCII && !((P.first_mask >> T.sym(start)) & 1u)) {
                     if (start + 1 >= text_end) continue;
-                    if (!((P.second_mask >> T.sym(start + 1)) & 1u)) continue;
+                    if (T.byte(start + 1) != SUCC_NONASCII && !((P.second_mask >> T.sym(start + 1)) & 1u)) continue;
                 }
             }
             uint32_t top = 1, wn = 0;      // stack height, walk-queue length (warp-uniform)

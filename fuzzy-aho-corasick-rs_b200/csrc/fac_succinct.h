@@ -28,6 +28,10 @@
 #define SUCC_FC_MASK 0x07FFFFFFu
 #define SUCC_NOSYM 31u
 #define SUCC_MAX_NODES 0x07FFFFFFu
+// sub_pen is [32][SUCC_SP_STRIDE]: column b < 128 = text first char b, column 128 = any non-ASCII text first char
+// (similarity 0: only offered when the engine has no similarity entry with a non-ASCII member)
+#define SUCC_SP_STRIDE 132u
+#define SUCC_NONASCII 128u
 
 #if defined(__CUDA_ARCH__)
 #define FAC_POPC(x) __popc(x)
@@ -199,7 +203,7 @@ FAC_HD bool succ_item2(const SuccConsts &K, const float *sub_pen, const SuccCtx2
     const bool is_sub = r < ns;
     const uint32_t s = succ_nth_bit(is_sub ? C.sub_m : C.del_m, is_sub ? r : r - ns);
     // +inf in the table when similarity < min_symbol_similarity; deletions read a valid slot and ignore it
-    const float tp = sub_pen[s * 128u + (C.packed & 0x7Fu)];
+    const float tp = sub_pen[s * SUCC_SP_STRIDE + (C.packed & 0xFFu)];
     const float pp = is_sub ? tp : K.pen_del;
     out.node = (C.fc & SUCC_FC_MASK) + FAC_POPC(C.bm & ((1u << s) - 1u));
     out.pen = FAC_ADD(C.pen, pp);

@@ -176,10 +176,15 @@ int emu_search(const fac_config *cfg, const fac_pattern *pats, size_t np, const 
 // kernel, a plain LIFO stack instead of the warp stack machine, the order-independent reduction with
 // tie detection, and the faithful emulation above for tied ("dirty") windows. ----
 struct EmuRecs { const SuccRec *r; SuccRec operator()(uint32_t n) const { return r[n]; } };
-struct EmuSText {   // bytes / symbols of the haystack; positions past the end read as (0, SUCC_NOSYM) like the kernel's padded tile
-    const uint8_t *b; const uint8_t *symof; bool ci; uint32_t n;
-    uint32_t byte(uint32_t j) const { if (j >= n) return 0; const uint32_t c = b[j]; return (ci && c >= 'A' && c <= 'Z') ? c + 32u : c; }
-    uint32_t sym(uint32_t j) const { return j >= n ? SUCC_NOSYM : symof[byte(j)]; }
+struct EmuSText {   // first chars / symbols of the haystack graphemes; positions past the end read as (0, SUCC_NOSYM) like the kernel's padded tile
+    const uint8_t *b; const uint32_t *first; const uint8_t *symof; bool ci; uint32_t n;
+    uint32_t byte(uint32_t j) const {
+        if (j >= n) return 0;
+        if (first) return first[j] < 128u ? first[j] : SUCC_NONASCII;   // K1 stream: already folded
+        const uint32_t c = b[j];
+        return (ci && c >= 'A' && c <= 'Z') ? c + 32u : c;
+    }
+    uint32_t sym(uint32_t j) const { if (j >= n) return SUCC_NOSYM; const uint32_t c = byte(j); return c < 128u ? symof[c] : SUCC_NOSYM; }
 };
 struct EmuGM {   // grandchild-mask rows: table for the first gm_nodes nodes, recomputed from the children beyond
     const uint32_t *gm; uint32_t gm_nodes; const SuccRec *r;
@@ -214,9 +219,10 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
     fac_status st = build_automaton(cfg, pats, np, HA, err);
     if (st != FAC_OK) return (int)st;
     const HostSuccinct &S = HA.succ;
-    for (size_t i = 0; i < len; i++) if (hay[i] >= 0x80) return -3;
     if (!S.ok || HA.beam_width != 0 || HA.has_auto_beam) return -3;
-    const uint32_t N = (uint32_t)S.bm.size(), n = (uint32_t)len, text_end = n;
+    EmuText ET; segment_host(HA, hay, len, ET);
+    if (!ET.tv.ascii && !S.unicode_text_ok) return -3;
+    const uint32_t N = (uint32_t)S.bm.size(), n = ET.tv.n, text_end = n;
     std::vector<SuccRec> recs(N);
     for (uint32_t i = 0; i < N; i++) {
         union { float f; uint32_t u; } c;
@@ -230,7 +236,7 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
     const EmuRecs R{recs.data()};
     const EmuGM G{S.gmask.data(), S.gm_nodes, recs.data()};
     const EmuGM2 G2{S.gmask2.data(), S.gm2_nodes, G};
-    const EmuSText T{hay, S.sym_of, HA.ci, n};
+    const EmuSText T{hay, ET.tv.ascii ? nullptr : ET.first.data(), S.sym_of, HA.ci, n};
     const SuccOut *out2 = (const SuccOut *)S.out2.data();
     std::vector<FacCand> cands;
     EmuEmit emit{&cands};
@@ -240,9 +246,9 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
     uint64_t st_pop = 0, st_items = 0, st_surv = 0, st_walk = 0, st_deg_hist[33] = {0};
     for (uint32_t start = 0; start < n; start++) {
         if (HA.wskip) {
-            if (!((S.first_mask >> T.sym(start)) & 1u)) {
+            if (T.byte(start) != SUCC_NONASCII && !((S.first_mask >> T.sym(start)) & 1u)) {
                 if (start + 1 >= n) continue;
-                if (!((S.second_mask >> T.sym(start + 1)) & 1u)) continue;
+                if (T.byte(start + 1) != SUCC_NONASCII && !((S.second_mask >> T.sym(start + 1)) & 1u)) continue;
             }
         }
         if (S.exact_only) {  // engine without FuzzyLimits: only the exact chain from the root can emit
@@ -303,7 +309,8 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
         if (dirty[std::get<0>(kv.first)]) continue;
         fac_match m; memset(&m, 0, sizeof(m));
         const uint32_t cnt = kv.second.cmin;
-        m.start = std::get<0>(kv.first); m.end = std::get<1>(kv.first); m.pattern_index = std::get<2>(kv.first); m.similarity = kv.second.sim;
+        m.start = fac_byte_offset(ET.tv, std::get<0>(kv.first)); m.end = fac_byte_offset(ET.tv, std::get<1>(kv.first));
+        m.pattern_index = std::get<2>(kv.first); m.similarity = kv.second.sim;
         m.insertions = cnt & 0xFF; m.deletions = (cnt >> 8) & 0xFF; m.substitutions = (cnt >> 16) & 0xFF; m.swaps = cnt >> 24;
         m.edits = (uint8_t)fac_edits_of(cnt);
         res.push_back(m);
@@ -312,7 +319,9 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
         fac_match *fm = nullptr; size_t fn = 0; uint64_t fs = 0;
         const int rc = emu_search(cfg, pats, np, hay, len, thr, 16, &fm, &fn, &fs, nullptr);
         if (rc != 0) return rc;
-        for (size_t i = 0; i < fn; i++) if (dirty[fm[i].start]) res.push_back(fm[i]);
+        std::vector<uint8_t> dirty_byte(len + 1, 0);
+        for (uint32_t g = 0; g < n; g++) if (dirty[g]) dirty_byte[fac_byte_offset(ET.tv, g)] = 1;
+        for (size_t i = 0; i < fn; i++) if (dirty_byte[fm[i].start]) res.push_back(fm[i]);
         free(fm);
     }
     std::sort(res.begin(), res.end(), [](const fac_match &a, const fac_match &b) {

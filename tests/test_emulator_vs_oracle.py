@@ -90,3 +90,28 @@ def test_succinct_dense_tries(oracle):
         assert o.tuples() == e.tuples(), (t, desc)
         modes.add(desc["lim_mode"])
     assert emu.succinct_used == 40 and modes == {0, 1, 2, 3}
+
+
+def test_succinct_on_unicode_haystacks(oracle):
+    """ASCII-alphabet engines on non-ASCII haystacks: the fast formulation reads the K1 first-char stream
+    (first-char identity, src/structs.rs:512-519; dead-end filter blind to non-ASCII chars, :471-475)."""
+    emu = EmuBackend(tile=16)
+    emu.succinct = True
+    from fac_b200 import FuzzyAhoCorasickBuilder, FuzzyLimits
+    r = random.Random(515)
+    words = ["hello", "world", "help", "cafe", "naive", "resume", "abc", "eclair", "senor", "uber"]
+    fill = ["a", "e", "\u00e9", "e\u0301", "\u00f1", " ", "o", "l", "h", "\u4e2d", "\r\n", "\u0301", "E", "\U0001F600", "r", "s"]
+    used0 = emu.succinct_used
+    for t in range(600):
+        pats = r.sample(words, r.randrange(1, 6))
+        edits = r.choice([1, 2, 2, 3])
+        ci = r.random() < 0.5
+        hay = ""
+        for _ in range(r.randrange(0, 50)):
+            hay += (r.choice(pats) if r.random() < 0.5 else "".join(r.choice(fill) for _ in range(3))) if r.randrange(6) == 0 else r.choice(fill)
+        mk = lambda b: FuzzyAhoCorasickBuilder.new(b).fuzzy(FuzzyLimits.new().edits(edits)).case_insensitive(ci).build(pats)
+        thr = r.choice([0.3, 0.5, 0.7, 0.8])
+        o = mk(oracle).search(hay, SearchOptions.new().threshold(thr))
+        e = mk(emu).search(hay, SearchOptions.new().threshold(thr))
+        assert o.tuples() == e.tuples(), (t, pats, edits, ci, thr, hay)
+    assert emu.succinct_used - used0 == 600

@@ -45,6 +45,33 @@ def test_fuzz_unicode(oracle, gpu, faithful, monkeypatch):
     _fuzz(oracle, gpu, 12, True, 400, faithful, monkeypatch)
 
 
+def test_fast_kernel_on_non_ascii_haystack(oracle, gpu, monkeypatch):
+    # ASCII-alphabet engine, haystack with accents / CJK / combining marks / emoji / CRLF sprinkled in: the fast
+    # kernel reads the K1 grapheme stream (first chars), byte offsets come from the K1 offset table
+    monkeypatch.setenv("FAC_FAITHFUL", "0")
+    cfg = workload.cfg2(1 << 14, n_patterns=2000)
+    base = bytes(cfg["text"]).decode("ascii")
+    r = random.Random(5)
+    extra = ["\u00e9", "e\u0301", "\u4e2d\u6587", "\U0001F600", "\r\n", "\u00df", "\u0301", "\u00c9"]
+    parts, pos = [], 0
+    while pos < len(base):
+        step = r.randrange(5, 120)
+        parts.append(base[pos:pos + step])
+        parts.append(r.choice(extra))
+        pos += step
+    text = "".join(parts)
+    for ci, edits in ((False, 2), (True, 1)):
+        mk = lambda b: FuzzyAhoCorasickBuilder.new(b).fuzzy(FuzzyLimits.new().edits(edits)).case_insensitive(ci).build(cfg["patterns"])
+        eo, eg = mk(oracle), mk(gpu)
+        for opts in (SearchOptions.new().threshold(0.8), SearchOptions.new().threshold(0.7).sorted().non_overlapping()):
+            o, g = eo.search(text, opts), eg.search(text, opts)
+            assert len(o) > 50
+            assert o.tuples() == g.tuples()
+        monkeypatch.setenv("FAC_FAITHFUL", "1")
+        assert mk(gpu).search(text, SearchOptions.new().threshold(0.8)).tuples() == eo.search(text, SearchOptions.new().threshold(0.8)).tuples()
+        monkeypatch.setenv("FAC_FAITHFUL", "0")
+
+
 def test_exact_engine_fast_path(oracle, gpu, monkeypatch):
     # engines without FuzzyLimits (plain multi-pattern matching): the fast kernel walks the exact chain only
     monkeypatch.setenv("FAC_FAITHFUL", "0")

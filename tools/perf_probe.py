@@ -42,3 +42,11 @@ if __name__ == "__main__":
         probe("cfg2", workload.cfg2(int(os.environ.get("CFG2_BYTES", 1 << 20)), int(os.environ.get("CFG2_PATTERNS", 10000))))
     if which in ("cfg3",):
         probe("cfg3 (unicode, mappings)", workload.cfg3(int(os.environ.get("CFG3_BYTES", 8 << 20))), reps=2)
+    if which in ("cfg2u",):  # cfg2 with one non-ASCII grapheme every ~1 KiB: the whole haystack takes the K1 + grapheme-stream route
+        import numpy as np
+        c = workload.cfg2(int(os.environ.get("CFG2_BYTES", 8 << 20)), int(os.environ.get("CFG2_PATTERNS", 10000)))
+        t = c["text"].copy()
+        for p in range(512, len(t) - 2, 1024):
+            t[p] = 0xC3; t[p + 1] = 0xA9   # e-acute
+        c["text"] = t
+        probe("cfg2 + non-ASCII graphemes", c)
