@@ -72,6 +72,52 @@ def test_fast_kernel_on_non_ascii_haystack(oracle, gpu, monkeypatch):
         monkeypatch.setenv("FAC_FAITHFUL", "0")
 
 
+def test_tile_and_segment_boundaries(oracle, gpu, monkeypatch):
+    # tiny tiles and tiny launch segments: matches whose look-ahead crosses tile / segment ends, ragged last tile
+    monkeypatch.setenv("FAC_FAITHFUL", "0")
+    monkeypatch.setenv("FAC_SUCC_TILE", "32")
+    monkeypatch.setenv("FAC_SEGMENT_WINDOWS", "3001")
+    cfg = workload.cfg2(10007, n_patterns=1500)
+    eo, eg = _engines(oracle, gpu, cfg)
+    text = bytes(cfg["text"])
+    for n in (10007, 3001, 3002, 33, 32, 31, 5, 1):
+        o = eo.search(text[:n], SearchOptions.new().threshold(0.75))
+        g = eg.search(text[:n], SearchOptions.new().threshold(0.75))
+        assert o.tuples() == g.tuples(), n
+    # a pattern at the very end of the haystack, cut short (deletions at end of text) and complete
+    tail = text[:200] + cfg["patterns"][3].encode()
+    for cut in (0, 1, 2):
+        t = tail[:len(tail) - cut]
+        assert eo.search(t, SearchOptions.new().threshold(0.6)).tuples() == eg.search(t, SearchOptions.new().threshold(0.6)).tuples(), cut
+
+
+def test_concurrent_searches_on_one_engine(oracle, gpu):
+    # &self search from several host threads (src/stream.rs:395-402): per-call stream + pooled workspace
+    import threading
+    cfg = workload.cfg2(1 << 16, n_patterns=2000)
+    eo, eg = _engines(oracle, gpu, cfg)
+    text = bytes(cfg["text"])
+    slices = [text[i * 8192:(i + 1) * 8192 + 64] for i in range(8)]
+    want = [eo.search(s, SearchOptions.new().threshold(0.8).sorted()).tuples() for s in slices]
+    got = [None] * len(slices)
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                got[i] = eg.search(slices[i], SearchOptions.new().threshold(0.8).sorted()).tuples()
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(slices))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs
+    assert got == want
+
+
 def test_exact_engine_fast_path(oracle, gpu, monkeypatch):
     # engines without FuzzyLimits (plain multi-pattern matching): the fast kernel walks the exact chain only
     monkeypatch.setenv("FAC_FAITHFUL", "0")
