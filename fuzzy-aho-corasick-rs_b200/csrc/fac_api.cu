@@ -201,10 +201,12 @@ struct fac_engine {
     const uint8_t *d_bp_m = nullptr;
     // succinct-trie fast kernel (fac_succinct.cuh)
     bool succ_ok = false, succ_generic_ok = false;
-    const uint32_t *d_s_bm = nullptr, *d_s_fc = nullptr, *d_s_out_idx = nullptr, *d_s_out2 = nullptr;
+    const void *d_s_bm = nullptr;   // u32 [N] (narrow) or u64 [N] with bit 63 = has outputs (wide)
+    const uint32_t *d_s_fc = nullptr, *d_s_out_idx = nullptr, *d_s_out2 = nullptr;
     const float *d_s_plen = nullptr, *d_s_plow = nullptr, *d_s_subpen = nullptr;
     const uint8_t *d_s_symof = nullptr;
-    const uint32_t *d_s_gm = nullptr, *d_s_gm2 = nullptr, *d_s_node_lim = nullptr;
+    const void *d_s_gm = nullptr, *d_s_gm2 = nullptr;
+    const uint32_t *d_s_node_lim = nullptr;
     uint32_t succ_nt = 1024, succ_tile = 1024, succ_stack = 0;
     int smem_optin = 0;
     bool fast_ok = false;  // FAST kernel allowed (fast-path edit ceiling, no beam); FAC_FAITHFUL=1 forces the order-faithful kernel
@@ -275,17 +277,17 @@ fac_status launch_expand(const ExpandParams &P, uint32_t grid, size_t smem, cuda
 }
 
 // ---- succinct fast kernel launch (fac_succinct.cuh) ----
-template <int NT>
-fac_status launch_succ_t(const SuccParams &P, uint32_t grid, size_t smem, cudaStream_t s) {
-    if (P.K.lim) {
-        CK(cudaFuncSetAttribute(k_expand_succinct<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_expand_succinct<NT, true><<<grid, NT, smem, s>>>(P);
-    } else {
-        CK(cudaFuncSetAttribute(k_expand_succinct<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_expand_succinct<NT, false><<<grid, NT, smem, s>>>(P);
-    }
+template <int NT, bool LIM, bool W>
+fac_status launch_succ_tt(const SuccParams &P, uint32_t grid, size_t smem, cudaStream_t s) {
+    CK(cudaFuncSetAttribute(k_expand_succinct<NT, LIM, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_expand_succinct<NT, LIM, W><<<grid, NT, smem, s>>>(P);
     CK(cudaGetLastError());
     return FAC_OK;
+}
+template <int NT>
+fac_status launch_succ_t(const SuccParams &P, bool wide, uint32_t grid, size_t smem, cudaStream_t s) {
+    if (wide) return P.K.lim ? launch_succ_tt<NT, true, true>(P, grid, smem, s) : launch_succ_tt<NT, false, true>(P, grid, smem, s);
+    return P.K.lim ? launch_succ_tt<NT, true, false>(P, grid, smem, s) : launch_succ_tt<NT, false, false>(P, grid, smem, s);
 }
 fac_status launch_succinct(const fac_engine *E, Workspace *ws, const TextView &tv, float thr, uint32_t seg_begin, uint32_t seg_end,
                            uint32_t text_end, FacCand *cands, uint32_t cand_cap, cudaStream_t s, const uint4 *d_tiles = nullptr,
@@ -293,7 +295,8 @@ fac_status launch_succinct(const fac_engine *E, Workspace *ws, const TextView &t
     const fac::HostSuccinct &S = E->host.succ;
     const uint32_t N = (uint32_t)S.bm.size();
     CKS(ws->srec.ensure((size_t)N * 16));
-    k_succ_prepare<<<cdiv(N, 256), 256, 0, s>>>(E->d_s_bm, E->d_s_fc, E->d_s_plen, E->d_s_plow, E->d_s_out_idx, thr, N, ws->srec.as<uint4>());
+    if (S.wide) k_succ_prepare<true><<<cdiv(N, 256), 256, 0, s>>>(E->d_s_bm, E->d_s_fc, E->d_s_plen, E->d_s_plow, E->d_s_out_idx, thr, N, ws->srec.as<uint4>());
+    else k_succ_prepare<false><<<cdiv(N, 256), 256, 0, s>>>(E->d_s_bm, E->d_s_fc, E->d_s_plen, E->d_s_plow, E->d_s_out_idx, thr, N, ws->srec.as<uint4>());
     CK(cudaGetLastError());
     SuccParams P;
     memset(&P, 0, sizeof(P));
@@ -306,18 +309,20 @@ fac_status launch_succinct(const fac_engine *E, Workspace *ws, const TextView &t
         P.K.mef = (int32_t)S.edit_bound; P.K.lim = E->dview.lim; P.K.node_lim = E->d_s_node_lim; P.K.has_global = E->host.has_global_limits;
     }
     P.exact_only = S.exact_only ? 1 : 0;
+    P.K.out_idx = E->d_s_out_idx;
     P.ci = E->host.ci; P.wskip = E->host.wskip; P.first_mask = S.first_mask; P.second_mask = S.second_mask;
     P.seg_begin = seg_begin; P.seg_end = seg_end; P.text_end = text_end;
     P.tile = E->succ_tile; P.n_tiles = cdiv((uint64_t)seg_end - seg_begin, P.tile); P.lookahead = E->lookahead;
     if (d_tiles) { P.tiles = d_tiles; P.n_tiles = n_explicit; }
     // deeper edit budgets push whole sibling sets of non-final states: fewer warps, deeper stacks
     const bool deep = S.limits_mode || E->host.mef > 2;
-    const uint32_t nt = !deep ? E->succ_nt : std::min<uint32_t>(E->succ_nt, 512u);
+    // 64-bit masks need more registers than a 1024-thread CTA leaves per thread
+    const uint32_t nt = deep ? std::min<uint32_t>(E->succ_nt, 512u) : (S.wide ? std::min<uint32_t>(E->succ_nt, 768u) : E->succ_nt);
     const uint32_t nw = nt / 32;
     P.stack_cap = E->succ_stack ? E->succ_stack : (!deep ? 128u : 384u);
     P.text_cap = (P.tile + P.lookahead + 16u + 15u) & ~15u;
     P.gm = E->d_s_gm; P.gm_nodes = S.gm_nodes; P.gm2 = E->d_s_gm2; P.gm2_nodes = S.gm2_nodes;
-    const size_t fixed = (size_t)nw * (P.stack_cap + SUCC_WQ_CAP) * 16 + 32 * SUCC_SP_STRIDE * 4 + (size_t)P.text_cap * (tv.ascii ? 3 : 6) + 256;
+    const size_t fixed = (size_t)nw * (P.stack_cap + SUCC_WQ_CAP) * 16 + (S.wide ? 64u : 32u) * SUCC_SP_STRIDE * 4 + (size_t)P.text_cap * (tv.ascii ? 3 : 6) + 256;
     const size_t budget = (size_t)E->smem_optin - 1024;  // static shared + reserve
     if (fixed + 16 * 64 > budget) { set_err("succinct kernel: shared-memory budget too small for the configured stack / tile"); return FAC_UNSUPPORTED; }
     P.n_smem_nodes = (uint32_t)std::min<size_t>(N, (budget - fixed) / 16);
@@ -327,10 +332,9 @@ fac_status launch_succinct(const fac_engine *E, Workspace *ws, const TextView &t
     const size_t smem = fixed + (size_t)P.n_smem_nodes * 16;
     const uint32_t grid = std::min<uint32_t>((uint32_t)E->sm_count, P.n_tiles);
     switch (nt) {
-        case 1024: return launch_succ_t<1024>(P, grid, smem, s);
-        case 512: return launch_succ_t<512>(P, grid, smem, s);
-        case 256: return launch_succ_t<256>(P, grid, smem, s);
-        default: return launch_succ_t<768>(P, grid, smem, s);
+        case 1024: return launch_succ_t<1024>(P, S.wide, grid, smem, s);
+        case 512: return launch_succ_t<512>(P, S.wide, grid, smem, s);
+        default: return launch_succ_t<768>(P, S.wide, grid, smem, s);
     }
 }
 
@@ -1159,17 +1163,40 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
     }
     if (H.succ.ok) {
         const fac::HostSuccinct &S = H.succ;
+        const size_t Nn = S.bm.size();
         std::vector<uint8_t> symof(S.sym_of, S.sym_of + 256);
-        if ((st = upload(E, S.bm, &E->d_s_bm)) != FAC_OK) return fail(st);
-        if ((st = upload(E, S.fc_sym, &E->d_s_fc)) != FAC_OK) return fail(st);
+        std::vector<uint32_t> fcsym(Nn);
+        for (size_t i = 0; i < Nn; i++) fcsym[i] = S.fc[i] | ((uint32_t)S.insym[i] << (S.wide ? 26 : 27));
+        if (S.wide) {
+            std::vector<uint64_t> bm(Nn);
+            for (size_t i = 0; i < Nn; i++) bm[i] = S.bm[i] | (S.out_idx[i] != FAC_NONE ? 1ull << 63 : 0ull);
+            const uint64_t *p64;
+            if ((st = upload(E, bm, &p64)) != FAC_OK) return fail(st);
+            E->d_s_bm = p64;
+            if ((st = upload(E, S.gmask, &p64)) != FAC_OK) return fail(st);
+            E->d_s_gm = p64;
+            if ((st = upload(E, S.gmask2, &p64)) != FAC_OK) return fail(st);
+            E->d_s_gm2 = p64;
+        } else {
+            std::vector<uint32_t> bm(Nn), gm(S.gmask.size()), gm2(S.gmask2.size());
+            for (size_t i = 0; i < Nn; i++) bm[i] = (uint32_t)S.bm[i];
+            for (size_t i = 0; i < gm.size(); i++) gm[i] = (uint32_t)S.gmask[i];
+            for (size_t i = 0; i < gm2.size(); i++) gm2[i] = (uint32_t)S.gmask2[i];
+            const uint32_t *p32;
+            if ((st = upload(E, bm, &p32)) != FAC_OK) return fail(st);
+            E->d_s_bm = p32;
+            if ((st = upload(E, gm, &p32)) != FAC_OK) return fail(st);
+            E->d_s_gm = p32;
+            if ((st = upload(E, gm2, &p32)) != FAC_OK) return fail(st);
+            E->d_s_gm2 = p32;
+        }
+        if ((st = upload(E, fcsym, &E->d_s_fc)) != FAC_OK) return fail(st);
         if ((st = upload(E, S.out_idx, &E->d_s_out_idx)) != FAC_OK) return fail(st);
         if ((st = upload(E, S.out2, &E->d_s_out2)) != FAC_OK) return fail(st);
         if ((st = upload(E, S.prune_len, &E->d_s_plen)) != FAC_OK) return fail(st);
         if ((st = upload(E, S.prune_low, &E->d_s_plow)) != FAC_OK) return fail(st);
         if ((st = upload(E, S.sub_pen, &E->d_s_subpen)) != FAC_OK) return fail(st);
         if ((st = upload(E, symof, &E->d_s_symof)) != FAC_OK) return fail(st);
-        if ((st = upload(E, S.gmask, &E->d_s_gm)) != FAC_OK) return fail(st);
-        if ((st = upload(E, S.gmask2, &E->d_s_gm2)) != FAC_OK) return fail(st);
         if ((st = upload(E, S.node_lim, &E->d_s_node_lim)) != FAC_OK) return fail(st);
     }
     cudaDeviceProp prop;

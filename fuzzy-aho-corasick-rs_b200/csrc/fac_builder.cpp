@@ -2,6 +2,7 @@
 #include "fac_builder.h"
 #include "fac_succinct.h"
 #include <limits>
+#include <functional>
 #include <cstdlib>
 #define FAC_POPC_HOST(x) __builtin_popcount(x)
 #include "fac_core.h"
@@ -447,7 +448,6 @@ fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_
     {
         HostSuccinct &S = A.succ;
         S = HostSuccinct();
-        memset(S.sym_of, 31, sizeof(S.sym_of));
         S.exact_only = !A.has_global_limits && !A.has_pattern_limits;
         S.limits_mode = A.mef == 255 && !S.exact_only;
         bool ok = !A.has_mappings && N <= SUCC_MAX_NODES;
@@ -476,25 +476,27 @@ fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_
         if (ok) {
             std::sort(chars.begin(), chars.end());
             chars.erase(std::unique(chars.begin(), chars.end()), chars.end());
-            if (chars.size() > 31) ok = false;
+            const char *ev = getenv("FAC_SUCC_FORCE_WIDE");
+            S.wide = chars.size() > 31 || (ev && *ev == '1');
+            if (chars.size() > 63) ok = false;
         }
         if (ok) {
+            const uint32_t NOSYM = S.wide ? 63u : 31u, ROW = NOSYM + 1u;
+            memset(S.sym_of, (int)NOSYM, sizeof(S.sym_of));
             S.n_syms = (uint32_t)chars.size();
             for (size_t k = 0; k < chars.size(); k++) { sym_of_char[chars[k]] = (int)k; S.sym_of[chars[k]] = (uint8_t)k; }
             // BFS numbering: children of a node contiguous, sorted by symbol
-            std::vector<uint32_t> new_of(N, 0);
             S.old_of.assign(1, 0);
-            S.bm.assign(N, 0); S.fc_sym.assign(N, 0);
+            S.bm.assign(N, 0); S.fc.assign(N, 0); S.insym.assign(N, 0);
             for (size_t h = 0; h < S.old_of.size(); h++) {
                 const uint32_t old = S.old_of[h];
                 std::vector<std::pair<uint32_t, uint32_t>> ch;  // (sym, old child)
                 for (auto &kv : nodes[old].order) ch.emplace_back((uint32_t)sym_of_char[(uint8_t)kv.first[0]], kv.second);
                 std::sort(ch.begin(), ch.end());
-                S.fc_sym[h] |= (uint32_t)S.old_of.size();
+                S.fc[h] = (uint32_t)S.old_of.size();
                 for (auto &c : ch) {
-                    S.bm[h] |= 1u << c.first;
-                    new_of[c.second] = (uint32_t)S.old_of.size();
-                    S.fc_sym[S.old_of.size()] = c.first << 27;
+                    S.bm[h] |= 1ull << c.first;
+                    S.insym[S.old_of.size()] = (uint8_t)c.first;
                     S.old_of.push_back(c.second);
                 }
             }
@@ -516,7 +518,7 @@ fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_
             }
             if (S.out2.empty()) S.out2.assign(4, 0x80000000u);
             const float inf = std::numeric_limits<float>::infinity();
-            S.sub_pen.assign(32 * SUCC_SP_STRIDE, inf);
+            S.sub_pen.assign((size_t)ROW * SUCC_SP_STRIDE, inf);
             for (size_t k = 0; k < chars.size(); k++)
                 for (uint32_t b = 0; b < 128; b++) {
                     const float sm = chars[k] == b ? 1.0f : A.sim_ascii[chars[k] * 128 + b];  // get_similarity, search.rs:76-82
@@ -532,48 +534,37 @@ fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_
                 for (size_t k = 0; k < chars.size(); k++) S.sub_pen[k * SUCC_SP_STRIDE + SUCC_NONASCII] = pp0;
             }
             S.first_mask = S.bm[0];
-            for (uint32_t c = 0; c < (uint32_t)FAC_POPC_HOST(S.bm[0]); c++) S.second_mask |= S.bm[(S.fc_sym[0] & SUCC_FC_MASK) + c];
+            for (uint32_t c = 0; c < (uint32_t)__builtin_popcountll(S.bm[0]); c++) S.second_mask |= S.bm[S.fc[0] + c];
             S.first_mask |= S.second_mask;
-            {   // grandchild masks: gm[n][y] = symbols s with child(n, s) having edge y; gm[n][31] = children with an output
+            auto for_children = [&](uint32_t h, const std::function<void(uint32_t, uint32_t)> &fn) {  // fn(sym, child)
+                uint64_t bmv = S.bm[h];
+                uint32_t k = 0;
+                while (bmv) { const uint32_t sy = (uint32_t)__builtin_ctzll(bmv); bmv &= bmv - 1; fn(sy, S.fc[h] + k++); }
+            };
+            {   // grandchild masks: gm[n][y] = symbols s with child(n, s) having edge y; gm[n][NOSYM] = children with an output
                 const char *ev = getenv("FAC_GM_NODES");
                 const size_t lim = ev && *ev ? (size_t)atoll(ev) : 65536;
                 S.gm_nodes = (uint32_t)std::min<size_t>(N, lim);
-                S.gmask.assign((size_t)std::max<uint32_t>(S.gm_nodes, 1) * 32, 0);
-                for (uint32_t h = 0; h < S.gm_nodes; h++) {
-                    uint32_t bmv = S.bm[h], k = 0;
-                    while (bmv) {
-                        const uint32_t sy = (uint32_t)__builtin_ctz(bmv);
-                        bmv &= bmv - 1;
-                        const uint32_t c = (S.fc_sym[h] & SUCC_FC_MASK) + k++;
-                        uint32_t cb = S.bm[c];
-                        while (cb) { S.gmask[(size_t)h * 32 + (uint32_t)__builtin_ctz(cb)] |= 1u << sy; cb &= cb - 1; }
-                        if (S.out_idx[c] != FAC_NONE) S.gmask[(size_t)h * 32 + 31] |= 1u << sy;
-                    }
-                }
+                S.gmask.assign((size_t)std::max<uint32_t>(S.gm_nodes, 1) * ROW, 0);
+                for (uint32_t h = 0; h < S.gm_nodes; h++)
+                    for_children(h, [&](uint32_t sy, uint32_t c) {
+                        for_children(c, [&](uint32_t y, uint32_t) { S.gmask[(size_t)h * ROW + y] |= 1ull << sy; });
+                        if (S.out_idx[c] != FAC_NONE) S.gmask[(size_t)h * ROW + NOSYM] |= 1ull << sy;
+                    });
             }
             {   // two-deep masks for the shallow nodes (where almost all last-edit expansions happen)
                 const char *ev = getenv("FAC_GM2_NODES");
-                const size_t lim = ev && *ev ? (size_t)atoll(ev) : 2048;
+                const size_t lim = ev && *ev ? (size_t)atoll(ev) : (S.wide ? 1024 : 2048);
                 S.gm2_nodes = (uint32_t)std::min<size_t>(std::min<size_t>(N, lim), S.gm_nodes);
-                S.gmask2.assign((size_t)std::max<uint32_t>(S.gm2_nodes, 1) * 1024, 0);
-                for (uint32_t h = 0; h < S.gm2_nodes; h++) {
-                    uint32_t bmv = S.bm[h], k = 0;
-                    while (bmv) {
-                        const uint32_t sy = (uint32_t)__builtin_ctz(bmv);
-                        bmv &= bmv - 1;
-                        const uint32_t c = (S.fc_sym[h] & SUCC_FC_MASK) + k++;
-                        uint32_t cb = S.bm[c], kk = 0;
-                        while (cb) {
-                            const uint32_t y1 = (uint32_t)__builtin_ctz(cb);
-                            cb &= cb - 1;
-                            const uint32_t g = (S.fc_sym[c] & SUCC_FC_MASK) + kk++;
-                            uint32_t *row = &S.gmask2[((size_t)h * 32 + y1) * 32];
-                            const bool gout = S.out_idx[g] != FAC_NONE;
-                            if (gout) { for (uint32_t y2 = 0; y2 < 32; y2++) row[y2] |= 1u << sy; }
-                            else { uint32_t gb = S.bm[g]; while (gb) { row[__builtin_ctz(gb)] |= 1u << sy; gb &= gb - 1; } }
-                        }
-                    }
-                }
+                S.gmask2.assign((size_t)std::max<uint32_t>(S.gm2_nodes, 1) * ROW * ROW, 0);
+                for (uint32_t h = 0; h < S.gm2_nodes; h++)
+                    for_children(h, [&](uint32_t sy, uint32_t c) {
+                        for_children(c, [&](uint32_t y1, uint32_t g) {
+                            uint64_t *row = &S.gmask2[((size_t)h * ROW + y1) * ROW];
+                            if (S.out_idx[g] != FAC_NONE) { for (uint32_t y2 = 0; y2 < ROW; y2++) row[y2] |= 1ull << sy; }
+                            else for_children(g, [&](uint32_t y2, uint32_t) { row[y2] |= 1ull << sy; });
+                        });
+                    });
             }
             S.ok = true;
         }

@@ -57,35 +57,38 @@ struct HostBitap {
 };
 
 // Succinct BFS-ordered trie for the fast expansion kernel (fac_succinct.h).  `ok` is false when the
-// engine is outside that kernel's domain (mappings, per-type limits, multi-byte edges, > 31 symbols).
+// engine is outside that kernel's domain (mappings, multi-byte edges, > 63 symbols, edit bounds above 6).
 struct HostSuccinct {
     bool ok = false;
     // engines without any FuzzyLimits: the reference still expands one substitution per start window
     // (src/search.rs:143-145) but rejects every output whose edit counts are not all zero (:166-168), so the
     // results are exactly the outputs along the exact chain from the root
     bool exact_only = false;
-    // per-pattern / per-type limits (the reference's generic MAX_EDITS_FAST = 255 path): permissions are evaluated
-    // per state from node_lim; edit_bound = an upper bound on the edits any state can accumulate
     // non-ASCII haystacks (grapheme stream of first chars from K1) are inside the kernel's domain when no similarity
     // entry involves a non-ASCII char
     bool unicode_text_ok = false;
+    // per-pattern / per-type limits (the reference's generic MAX_EDITS_FAST = 255 path): permissions are evaluated
+    // per state from node_lim; edit_bound = an upper bound on the edits any state can accumulate
     bool limits_mode = false;
     uint32_t edit_bound = 0;
     std::vector<uint32_t> node_lim;      // [N] BFS order: index into HostAutomaton::lim or FAC_NONE
     uint32_t n_syms = 0;
-    uint8_t sym_of[256];                 // folded text byte -> dense symbol, 31 = not in the alphabet
-    std::vector<uint32_t> bm, fc_sym;    // [N] child bitmap; first_child | in-symbol << 27
+    bool wide = false;                   // 32..63 symbols: 64-bit child bitmaps (SuccW<true>), else 32-bit
+    uint8_t sym_of[256];                 // folded text byte -> dense symbol, NOSYM (31 / 63) = not in the alphabet
+    std::vector<uint64_t> bm;            // [N] child bitmap over symbols
+    std::vector<uint32_t> fc;            // [N] first child (children are contiguous in BFS order, sorted by symbol)
+    std::vector<uint8_t> insym;          // [N] symbol of the edge leading into the node
     std::vector<float> prune_len, prune_low;  // [N] in BFS numbering
     std::vector<uint32_t> out_idx;       // [N] first entry in out2 or FAC_NONE
-    std::vector<uint32_t> out2;          // 4 words per entry: pat | last << 31, glen f32 bits, weight f32 bits, 0
-    std::vector<float> sub_pen;          // [32][SUCC_SP_STRIDE] pen_sub * (1 - sim(edge char, text first char)), +inf below min_symbol_similarity
+    std::vector<uint32_t> out2;          // 4 words per entry: pat | last << 31, glen f32 bits, weight f32 bits, limits index
+    std::vector<float> sub_pen;          // [ROW][SUCC_SP_STRIDE] pen_sub * (1 - sim(edge char, text first char)), +inf below min_symbol_similarity
     std::vector<uint32_t> old_of;        // [N] reference node index of BFS node i
-    uint32_t first_mask = 0, second_mask = 0;  // 2-gram window skip (search.rs:504-521) in symbol space
-    // grandchild masks of the first gm_nodes BFS nodes (fac_succinct.h): [gm_nodes * 32]
-    std::vector<uint32_t> gmask;
+    uint64_t first_mask = 0, second_mask = 0;  // 2-gram window skip (search.rs:504-521) in symbol space
+    // grandchild masks of the first gm_nodes BFS nodes (fac_succinct.h): [gm_nodes * ROW]
+    std::vector<uint64_t> gmask;
     uint32_t gm_nodes = 0;
-    // two-deep masks of the first gm2_nodes BFS nodes: [gm2_nodes * 32 * 32]
-    std::vector<uint32_t> gmask2;
+    // two-deep masks of the first gm2_nodes BFS nodes: [gm2_nodes * ROW * ROW]
+    std::vector<uint64_t> gmask2;
     uint32_t gm2_nodes = 0;
 };
 

@@ -37,12 +37,12 @@ struct SuccParams {
     SuccConsts K;
     int32_t ci, wskip;
     int32_t exact_only;      // engine without FuzzyLimits: only the exact chain from the root can emit
-    uint32_t first_mask, second_mask;
+    unsigned long long first_mask, second_mask;
     uint32_t seg_begin, seg_end, text_end, tile, n_tiles, lookahead;
     const uint4 *tiles;      // optional explicit tiles {start, count (<= tile), text_end, window id} (pre-filter slices, stream batches); null = uniform tiling
-    const uint32_t *gm;      // [gm_nodes * 32] grandchild masks (fac_succinct.h)
+    const void *gm;          // [gm_nodes * ROW] grandchild masks (fac_succinct.h): u32 (narrow) or u64 (wide) entries
     uint32_t gm_nodes;
-    const uint32_t *gm2;     // [gm2_nodes * 1024] two-deep masks
+    const void *gm2;         // [gm2_nodes * ROW * ROW] two-deep masks
     uint32_t gm2_nodes;
     uint32_t stack_cap;      // states per warp stack
     uint32_t text_cap;       // bytes of the shared text tile (multiple of 16)
@@ -52,14 +52,19 @@ struct SuccParams {
     uint32_t *dirty;         // bitmap over start windows (bit sg - seg_begin): set when a window's stack overflowed
 };
 
-// per-call records: ceiling = prune_len - prune_low * thr (search.rs:638-642), exact f32 ops
-__global__ void __launch_bounds__(256) k_succ_prepare(const uint32_t *__restrict__ bm, const uint32_t *__restrict__ fc_sym, const float *__restrict__ plen,
+// per-call records: ceiling = prune_len - prune_low * thr (search.rs:638-642), exact f32 ops.
+// narrow: bm is u32 [n], fc_sym = first_child | in-symbol << 27;  wide: bm is u64 [n] (bit 63 = has outputs), << 26.
+template <bool W>
+__global__ void __launch_bounds__(256) k_succ_prepare(const void *__restrict__ bm, const uint32_t *__restrict__ fc_sym, const float *__restrict__ plen,
                                                       const float *__restrict__ plow, const uint32_t *__restrict__ out_idx, float thr, uint32_t n,
                                                       uint4 *__restrict__ rec) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float c = __fsub_rn(plen[i], __fmul_rn(plow[i], thr));
-    rec[i] = make_uint4(bm[i], fc_sym[i], __float_as_uint(c), out_idx[i]);
+    if (W) {
+        const unsigned long long b = reinterpret_cast<const unsigned long long *>(bm)[i];
+        rec[i] = make_uint4((uint32_t)b, (uint32_t)(b >> 32), fc_sym[i], __float_as_uint(c));
+    } else rec[i] = make_uint4(reinterpret_cast<const uint32_t *>(bm)[i], fc_sym[i], __float_as_uint(c), out_idx[i]);
 }
 
 struct SuccRecsDev {
@@ -74,30 +79,35 @@ struct SuccRecsDev {
         return r;
     }
 };
+template <bool W>
 struct SuccGMDev {
-    const uint32_t *gm;
+    typedef typename SuccW<W>::M M;
+    const M *gm;
     uint32_t gm_nodes;
     SuccRecsDev R;
-    __device__ __forceinline__ uint32_t operator()(uint32_t node, uint32_t y) const {
-        if (node < gm_nodes) return __ldg(&gm[(size_t)node * 32u + y]);
+    __device__ __forceinline__ M operator()(uint32_t node, uint32_t y) const {
+        if (node < gm_nodes) return __ldg(&gm[(size_t)node * SuccW<W>::ROW + y]);
         // beyond the table: recompute the row entry from the children's records
         const SuccRec r = R(node);
-        uint32_t bmv = r.x, k = 0, m = 0;
+        M bmv = succ_bm<W>(r), m = 0;
+        uint32_t k = 0;
         while (bmv) {
-            const uint32_t sy = __ffs(bmv) - 1u;
-            bmv &= bmv - 1u;
-            const SuccRec c = R((r.y & SUCC_FC_MASK) + k++);
-            if (y == SUCC_NOSYM ? c.w != FAC_NONE : ((c.x >> y) & 1u)) m |= 1u << sy;
+            const uint32_t sy = W ? (uint32_t)(__ffsll((long long)bmv) - 1) : (uint32_t)(__ffs((int)bmv) - 1);
+            bmv &= bmv - 1;
+            const SuccRec c = R(succ_fc<W>(r) + k++);
+            if (y == SuccW<W>::NOSYM ? succ_has_out<W>(c) : succ_has_edge<W>(c, y)) m |= M(1) << sy;
         }
         return m;
     }
 };
+template <bool W>
 struct SuccGM2Dev {
-    const uint32_t *gm2;
+    typedef typename SuccW<W>::M M;
+    const M *gm2;
     uint32_t gm2_nodes;
-    SuccGMDev G;
-    __device__ __forceinline__ uint32_t operator()(uint32_t node, uint32_t y1, uint32_t y2) const {
-        if (node < gm2_nodes) return __ldg(&gm2[((size_t)node * 32u + y1) * 32u + y2]);
+    SuccGMDev<W> G;
+    __device__ __forceinline__ M operator()(uint32_t node, uint32_t y1, uint32_t y2) const {
+        if (node < gm2_nodes) return __ldg(&gm2[((size_t)node * SuccW<W>::ROW + y1) * SuccW<W>::ROW + y2]);
         return G(node, y1);
     }
 };
@@ -133,7 +143,8 @@ __device__ __forceinline__ void succ_warp_push(uint4 *stk, uint32_t &top, bool p
 #define SUCC_WQ_CAP 96u
 
 // LIM = limits mode: per-pattern / per-type FuzzyLimits evaluated per state (the reference's MAX_EDITS_FAST = 255 path).
-template <int NT, bool LIM>
+// W = wide layout: 32..63 pattern symbols, 64-bit child bitmaps and masks.
+template <int NT, bool LIM, bool W>
 __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant__ SuccParams P) {
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t s_mbar;
@@ -146,21 +157,23 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
     uint4 *s_stack = s_rec + P.n_smem_nodes;
     uint4 *s_wq = s_stack + (size_t)NW * P.stack_cap;
     float *s_subpen = reinterpret_cast<float *>(s_wq + (size_t)NW * SUCC_WQ_CAP);
-    uint8_t *s_raw = reinterpret_cast<uint8_t *>(s_subpen + 32 * SUCC_SP_STRIDE);
+    typedef typename SuccW<W>::M M;
+    constexpr uint32_t NOSYM = SuccW<W>::NOSYM;
+    uint8_t *s_raw = reinterpret_cast<uint8_t *>(s_subpen + SuccW<W>::ROW * SUCC_SP_STRIDE);
     uint8_t *s_byte = s_raw + (size_t)P.text_cap * (P.first ? 4u : 1u);
     uint8_t *s_sym = s_byte + P.text_cap;
     uint8_t *s_symof = s_sym + P.text_cap;
 
     for (uint32_t k = tid; k < P.n_smem_nodes; k += NT) s_rec[k] = P.rec[k];
-    for (uint32_t k = tid; k < 32 * SUCC_SP_STRIDE; k += NT) s_subpen[k] = P.sub_pen[k];
+    for (uint32_t k = tid; k < SuccW<W>::ROW * SUCC_SP_STRIDE; k += NT) s_subpen[k] = P.sub_pen[k];
     for (uint32_t k = tid; k < 256; k += NT) s_symof[k] = P.sym_of[k];
     if (tid == 0) fac_mbar_init(&s_mbar, 1);
     __syncthreads();
 
     const SuccConsts K = P.K;
     const SuccRecsDev R{s_rec, P.rec, P.n_smem_nodes};
-    const SuccGMDev G{P.gm, P.gm_nodes, R};
-    const SuccGM2Dev G2{P.gm2, P.gm2_nodes, G};
+    const SuccGMDev<W> G{reinterpret_cast<const M *>(P.gm), P.gm_nodes, R};
+    const SuccGM2Dev<W> G2{reinterpret_cast<const M *>(P.gm2), P.gm2_nodes, G};
     const SuccOut *out2 = reinterpret_cast<const SuccOut *>(P.out2);
     SuccEmitDev emit{P.cands, P.cand_cap, &P.counters[1], 0u};
     uint4 *const stk = s_stack + (size_t)warp * P.stack_cap;
@@ -198,12 +211,12 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
         if (bulk) { fac_mbar_wait(&s_mbar, mbar_phase & 1u); mbar_phase++; }
         __syncthreads();
         for (uint32_t k = tid; k < span; k += NT) {
-            uint32_t b = 0, s = SUCC_NOSYM;
+            uint32_t b = 0, s = NOSYM;
             if (k < avail) {
                 if (P.first) {   // already folded by K1; non-ASCII first chars match no edge and have similarity 0
                     const uint32_t c = reinterpret_cast<const uint32_t *>(s_raw)[k];
                     b = c < 128u ? c : SUCC_NONASCII;
-                    s = c < 128u ? s_symof[c] : SUCC_NOSYM;
+                    s = c < 128u ? s_symof[c] : NOSYM;
                 } else {
                     b = s_raw[k];
                     if (P.ci && b >= 'A' && b <= 'Z') b += 32u;   // to_ascii_lowercase, grapheme.rs:110-117
@@ -218,7 +231,7 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
         if (P.exact_only) {
             // no edit is ever accepted (search.rs:166-168): one LANE per start window walks the exact chain
             for (uint32_t w = tid; w < count; w += NT)
-                n_states += succ_walk<false>(K, R, out2, T, emit, tile_start + w, text_end, R(0u), 0.f, 0u, 0u, 0u);
+                n_states += succ_walk<false, W>(K, R, out2, T, emit, tile_start + w, text_end, 0u, R(0u), 0.f, 0u, 0u, 0u);
             __syncthreads();
             continue;
         }
@@ -239,8 +252,8 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
             uint32_t top = 1, wn = 0;      // stack height, walk-queue length (warp-uniform)
             uint32_t b0 = 0, total = 0;    // item rounds of the current pop
             uint32_t off = 0;              // exclusive prefix of the lanes' item counts
-            SuccCtx2 C;
-            C.bm = C.fc = C.cnt = C.pos = C.packed = C.flags = C.sub_m = C.del_m = 0; C.pen = 0.f;
+            SuccCtx2<W> C;
+            C.bm = C.sub_m = C.del_m = 0; C.fc = C.cnt = C.pos = C.packed = C.flags = 0; C.pen = 0.f;
             if (lane == 0) stk[0] = make_uint4(0u, 0u, 0u, 0u);
             for (;;) {
                 __syncwarp();
@@ -249,7 +262,7 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                     const uint32_t n = min(wn, 32u);
                     if (lane < n) {
                         const uint4 q = wq[wn - n + lane];
-                        n_states += succ_walk<LIM>(K, R, out2, T, emit, start, text_end, R(q.x), __uint_as_float(q.y), q.z, q.w >> 10, q.w & 1023u);
+                        n_states += succ_walk<LIM, W>(K, R, out2, T, emit, start, text_end, q.x, R(q.x), __uint_as_float(q.y), q.z, q.w >> 10, q.w & 1023u);
                     }
                     wn -= n;
                     continue;
@@ -265,7 +278,7 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                         const uint32_t v = __shfl_sync(0xFFFFFFFFu, off, cand & 31u);
                         if (cand < 32u && v <= it) lo = cand;
                     }
-                    SuccCtx2 O;
+                    SuccCtx2<W> O;
                     O.bm = __shfl_sync(0xFFFFFFFFu, C.bm, lo);
                     O.fc = __shfl_sync(0xFFFFFFFFu, C.fc, lo);
                     O.pen = __shfl_sync(0xFFFFFFFFu, C.pen, lo);
@@ -278,7 +291,7 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                     const uint32_t r = it - __shfl_sync(0xFFFFFFFFu, off, lo);
                     FacState c;
                     c.node = 0; c.pen = 0.f; c.cnt = 0; c.pos = 0;
-                    const bool ok = it < total && succ_item2(K, s_subpen, O, r, c);
+                    const bool ok = it < total && succ_item2<W>(K, s_subpen, O, r, c);
                     const bool to_walk = ok && (O.flags & SUCC_F_LAST);
                     const bool to_stack = ok && !(O.flags & SUCC_F_LAST);
                     if (__any_sync(0xFFFFFFFFu, to_walk)) succ_warp_push(wq, wn, to_walk, c);
@@ -293,10 +306,10 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                 SuccRec rec; rec.x = rec.y = rec.z = 0; rec.w = FAC_NONE;
                 if (has) { sv = stk[top - 1u - lane]; rec = R(sv.x); }
                 const float pen = __uint_as_float(sv.y);
-                const bool dead = !has || pen > __uint_as_float(rec.z);   // node ceiling, search.rs:638-642
+                const bool dead = !has || pen > succ_ceil<W>(rec);   // node ceiling, search.rs:638-642
                 const bool last = (int)fac_edits_of(sv.z) + 1 >= K.mef;
                 // worst-case stack pushes of this state: only the exact child when its edit-children are exhausted
-                const uint32_t ub = dead ? 0u : (last ? 1u : 2u * (uint32_t)__popc(rec.x) + 3u);
+                const uint32_t ub = dead ? 0u : (last ? 1u : 2u * succ_popc(succ_bm<W>(rec)) + 3u);
                 uint32_t n_pop = navail;
                 if (__any_sync(0xFFFFFFFFu, ub > 1u)) {  // states on their last edit push at most the exact child: always fits
                     uint32_t incl = ub;
@@ -326,16 +339,16 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                 C.sub_m = C.del_m = 0;
                 if (active) {
                     n_states++;
-                    if (rec.w != FAC_NONE) succ_outputs<LIM>(K, out2, emit, rec.w, pen, sv.z, start, start + (sv.w & 1023u));
-                    succ_make_ctx2<LIM>(K, T, G, G2, start, text_end, sv.x, rec, pen, sv.z, sv.w, C);
+                    if (succ_has_out<W>(rec)) succ_outputs<LIM>(K, out2, emit, succ_out_idx<W>(K, rec, sv.x), pen, sv.z, start, start + (sv.w & 1023u));
+                    succ_make_ctx2<LIM, W>(K, T, G, G2, start, text_end, sv.x, rec, pen, sv.z, sv.w, C);
                     const uint32_t jr = sv.w >> 10;
                     const uint32_t cur_s = (C.packed >> 8) & 0xFFu;
-                    if (succ_has_edge(rec, cur_s)) {   // exact transition, search.rs:776-798
+                    if (succ_has_edge<W>(rec, cur_s)) {   // exact transition, search.rs:776-798
                         p_ex = true;
-                        c_ex.node = succ_child(rec, cur_s); c_ex.pen = pen; c_ex.cnt = sv.z; c_ex.pos = succ_make_pos(jr + 1, jr + 1);
+                        c_ex.node = succ_child<W>(rec, cur_s); c_ex.pen = pen; c_ex.cnt = sv.z; c_ex.pos = succ_make_pos(jr + 1, jr + 1);
                     }
-                    p_sw = succ_swap2<LIM>(K, R, C, c_sw);
-                    p_in = succ_ins2<LIM>(K, C, sv.x, rec.w != FAC_NONE, c_in);
+                    p_sw = succ_swap2<LIM, W>(K, R, C, c_sw);
+                    p_in = succ_ins2<LIM, W>(K, C, sv.x, succ_has_out<W>(rec), c_in);
                 }
                 succ_warp_push(stk, top, p_ex, c_ex);
                 {
@@ -345,7 +358,7 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                     if (__any_sync(0xFFFFFFFFu, p_in && lw)) succ_warp_push(wq, wn, p_in && lw, c_in);
                     if (__any_sync(0xFFFFFFFFu, p_in && !lw)) succ_warp_push(stk, top, p_in && !lw, c_in);
                 }
-                const uint32_t n_items = (uint32_t)__popc(C.sub_m) + (uint32_t)__popc(C.del_m);
+                const uint32_t n_items = succ_popc(C.sub_m) + succ_popc(C.del_m);
                 off = n_items;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {

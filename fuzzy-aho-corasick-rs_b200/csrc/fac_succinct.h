@@ -3,14 +3,17 @@
 //
 // Applies to engines the reference dispatches to its fast monomorphisations
 // `search_unsorted_impl<MAPPINGS=false, _, MAX_EDITS_FAST=1..6>` (src/search.rs:204-393) when, in
-// addition, every trie edge is one ASCII byte and the pattern alphabet has at most 31 symbols.
+// addition, every trie edge is one ASCII byte and the pattern alphabet has at most 31 symbols (narrow
+// layout, W = false) or at most 63 symbols (wide layout, W = true: 64-bit child bitmaps).
 //
 // Layout.  Nodes are renumbered in BFS order with the children of a node contiguous and sorted by
 // symbol, so the whole node is one 16-byte record
-//     x = child bitmap over the dense symbol alphabet (bit 31 never set)
-//     y = first_child | (symbol of the edge that leads INTO this node) << 27
-//     z = f32 bits of the node ceiling  prune_len - prune_len_over_weight * threshold  (search.rs:638-642)
-//     w = index of the node's first output entry, or FAC_NONE
+//     narrow: x = child bitmap over the dense symbol alphabet (bit 31 never set)
+//             y = first_child | (symbol of the edge that leads INTO this node) << 27
+//             z = f32 bits of the node ceiling  prune_len - prune_len_over_weight * threshold  (search.rs:638-642)
+//             w = index of the node's first output entry, or FAC_NONE
+//     wide:   x, y = 64-bit child bitmap (bit 63 = "node has outputs"; the output index lives in a side array)
+//             z = first_child | in-symbol << 26,   w = ceiling
 // and  child(n, sym) = first_child + popc(x & below(sym)).  There is no edge array and no hash
 // table: the exact transition (Node::find_transition_char_no_mappings, src/structs.rs:512-519) is a
 // bit test + popcount, and the last-edit dead-end filter (search.rs:839-847, 1005-1007, 1057-1063:
@@ -25,25 +28,40 @@
 #include "fac_core.h"
 #include "fac_types.h"
 
-#define SUCC_FC_MASK 0x07FFFFFFu
-#define SUCC_NOSYM 31u
-#define SUCC_MAX_NODES 0x07FFFFFFu
-// sub_pen is [32][SUCC_SP_STRIDE]: column b < 128 = text first char b, column 128 = any non-ASCII text first char
+#define SUCC_MAX_NODES 0x03FFFFFFu
+// sub_pen is [ROW][SUCC_SP_STRIDE]: column b < 128 = text first char b, column 128 = any non-ASCII text first char
 // (similarity 0: only offered when the engine has no similarity entry with a non-ASCII member)
 #define SUCC_SP_STRIDE 132u
 #define SUCC_NONASCII 128u
 
 #if defined(__CUDA_ARCH__)
 #define FAC_POPC(x) __popc(x)
+#define FAC_POPC64(x) __popcll(x)
 #define FAC_AS_FLOAT(u) __uint_as_float(u)
 #else
 #define FAC_POPC(x) ((uint32_t)__builtin_popcount(x))
+#define FAC_POPC64(x) ((uint32_t)__builtin_popcountll(x))
 static inline float fac_as_float_host(uint32_t u) { union { uint32_t u; float f; } v; v.u = u; return v.f; }
 #define FAC_AS_FLOAT(u) fac_as_float_host(u)
 #endif
 
 struct SuccRec { uint32_t x, y, z, w; };   // same bytes as uint4
-struct SuccOut { uint32_t pat_last; uint32_t glen_bits; uint32_t weight_bits; uint32_t pad; };  // pat | last<<31
+struct SuccOut { uint32_t pat_last; uint32_t glen_bits; uint32_t weight_bits; uint32_t pad; };  // pat | last<<31; pad = limits index
+
+// Layout traits: mask type, "no symbol" code (its bit is never an edge), table row length.
+template <bool W> struct SuccW;
+template <> struct SuccW<false> { typedef uint32_t M; enum : uint32_t { NOSYM = 31u, ROW = 32u, FC_MASK = 0x07FFFFFFu, SYM_SHIFT = 27u }; };
+template <> struct SuccW<true> { typedef uint64_t M; enum : uint32_t { NOSYM = 63u, ROW = 64u, FC_MASK = 0x03FFFFFFu, SYM_SHIFT = 26u }; };
+
+FAC_HD uint32_t succ_popc(uint32_t m) { return FAC_POPC(m); }
+FAC_HD uint32_t succ_popc(uint64_t m) { return FAC_POPC64(m); }
+
+template <bool W> FAC_HD typename SuccW<W>::M succ_bm(const SuccRec &r);
+template <> FAC_HD uint32_t succ_bm<false>(const SuccRec &r) { return r.x; }
+template <> FAC_HD uint64_t succ_bm<true>(const SuccRec &r) { return ((uint64_t)(r.y & 0x7FFFFFFFu) << 32) | r.x; }
+template <bool W> FAC_HD uint32_t succ_fc(const SuccRec &r) { return (W ? r.z : r.y) & SuccW<W>::FC_MASK; }
+template <bool W> FAC_HD float succ_ceil(const SuccRec &r) { return FAC_AS_FLOAT(W ? r.w : r.z); }
+template <bool W> FAC_HD bool succ_has_out(const SuccRec &r) { return W ? (r.y >> 31) != 0u : r.w != FAC_NONE; }
 
 struct SuccConsts {
     float thr, maxpen, pen_ins, pen_del, pen_swap;
@@ -53,7 +71,9 @@ struct SuccConsts {
     const FacLimits *lim;    // [L] index 0 = global limits (valid iff has_global)
     const uint32_t *node_lim;  // [N] BFS order: limits index of the pattern that created the node, or FAC_NONE
     int32_t has_global;
+    const uint32_t *out_idx;   // [N] wide layout: first output entry of the node (the narrow record carries it)
 };
+template <bool W> FAC_HD uint32_t succ_out_idx(const SuccConsts &K, const SuccRec &r, uint32_t node) { return W ? K.out_idx[node] : r.w; }
 
 // `limits.or(self.limits.as_ref())` (src/search.rs:93, 109, 125, 140, 160)
 FAC_HD bool succ_pick_limits(const SuccConsts &K, uint32_t idx, FacLimits &L) {
@@ -62,8 +82,12 @@ FAC_HD bool succ_pick_limits(const SuccConsts &K, uint32_t idx, FacLimits &L) {
     return false;
 }
 
-FAC_HD uint32_t succ_child(const SuccRec &r, uint32_t sym) { return (r.y & SUCC_FC_MASK) + FAC_POPC(r.x & ((1u << sym) - 1u)); }
-FAC_HD bool succ_has_edge(const SuccRec &r, uint32_t sym) { return (r.x >> sym) & 1u; }
+template <class M> FAC_HD M succ_below(uint32_t sym) { return (M(1) << sym) - M(1); }
+template <bool W> FAC_HD uint32_t succ_child(const SuccRec &r, uint32_t sym) {
+    typedef typename SuccW<W>::M M;
+    return succ_fc<W>(r) + succ_popc((M)(succ_bm<W>(r) & succ_below<M>(sym)));
+}
+template <bool W> FAC_HD bool succ_has_edge(const SuccRec &r, uint32_t sym) { return (succ_bm<W>(r) >> sym) & 1u; }
 FAC_HD uint32_t succ_make_pos(uint32_t jr, uint32_t mr) { return (jr << 10) | mr; }
 
 // Outputs of one node visit (search.rs:659-737): fast-path limit check is `edits > MAX_EDITS_FAST`,
@@ -94,19 +118,20 @@ FAC_HD void succ_outputs(const SuccConsts &K, const SuccOut *out2, Emit &emit, u
 // A state that has spent its whole edit budget follows exact transitions only (sub / swap / ins /
 // del all need edits < MAX_EDITS_FAST, search.rs:810, 937, 1003, 1043): walk the chain with the
 // per-pop checks (ceiling :638-642, outputs :659-737, exact :776-798).  Returns the nodes visited.
-template <bool LIM, class Recs, class Text, class Emit>
+template <bool LIM, bool W, class Recs, class Text, class Emit>
 FAC_HD uint32_t succ_walk(const SuccConsts &K, const Recs &R, const SuccOut *out2, const Text &T, Emit &emit, uint32_t start, uint32_t text_end,
-                          SuccRec rec, float pen, uint32_t cnt, uint32_t jr, uint32_t mr) {
+                          uint32_t node, SuccRec rec, float pen, uint32_t cnt, uint32_t jr, uint32_t mr) {
     uint32_t steps = 0;
     for (;;) {
         steps++;
-        if (pen > FAC_AS_FLOAT(rec.z)) break;
-        if (rec.w != FAC_NONE) succ_outputs<LIM>(K, out2, emit, rec.w, pen, cnt, start, start + mr);
+        if (pen > succ_ceil<W>(rec)) break;
+        if (succ_has_out<W>(rec)) succ_outputs<LIM>(K, out2, emit, succ_out_idx<W>(K, rec, node), pen, cnt, start, start + mr);
         const uint32_t j = start + jr;
         if (j >= text_end) break;
         const uint32_t s = T.sym(j);
-        if (!succ_has_edge(rec, s)) break;
-        rec = R(succ_child(rec, s));
+        if (!succ_has_edge<W>(rec, s)) break;
+        node = succ_child<W>(rec, s);
+        rec = R(node);
         jr++; mr = jr;
     }
     return steps;
@@ -119,21 +144,22 @@ enum : uint32_t { SUCC_F_IN_TEXT = 1u, SUCC_F_LAST = 2u, SUCC_F_DEL = 4u, SUCC_F
 //     c has an output  ||  c has a single-byte edge for the look-ahead symbol
 // (substitution: look-ahead = text[j+1], search.rs:839-847; deletion: text[j], :1057-1063).  Per node
 // and symbol the builder precomputes  gm[node][y] = { symbols s : child(node, s) has edge y }  and
-// gm[node][31] = { s : child(node, s) has an output }  ("grandchild masks", symbol space), so the
-// children that survive are known from two 4-byte loads instead of one record load per child.
+// gm[node][NOSYM] = { s : child(node, s) has an output }  ("grandchild masks", symbol space), so the
+// children that survive are known from two loads instead of one record load per child.
 // States that are not on their last edit keep every child.  `GM(node, y)` returns the row entry.
+template <bool W>
 struct SuccCtx2 {
-    uint32_t bm, fc;
+    typename SuccW<W>::M bm, sub_m, del_m;
+    uint32_t fc;       // first child
     float pen;
     uint32_t cnt, pos;
     uint32_t packed;   // cur byte | cur sym << 8 | next sym << 16
     uint32_t flags;
-    uint32_t sub_m, del_m;
 };
 
 //
 // Two-deep refinement for the first gm2_nodes nodes:  gm2[node][y1][y2] = { s : c = child(node, s) has edge y1 and
-// g = child(c, y1) has an output or an edge y2 } and gm2[node][y1][31] = { s : ... g has an output }.  A child
+// g = child(c, y1) has an output or an edge y2 } and gm2[node][y1][NOSYM] = { s : ... g has an output }.  A child
 // outside  outm | gm2[node][y1][y2]  walks c -> g and stops there without visiting an output node, i.e. it
 // cannot emit a candidate: dropping it is result-neutral (only the visited-state statistic changes).
 // `G2(node, y1, y2)` returns that set, or the one-deep set gm[node][y1] for nodes beyond the table.
@@ -142,10 +168,12 @@ struct SuccCtx2 {
 // (:143-145).  The dead-end filter does not exist on that path, but dropping exhausted children whose exact walk
 // cannot reach an output stays result-neutral, so the same masks are applied once `last` (no limits of the engine
 // admit another edit after this one).
-template <bool LIM, class Text, class GM, class GM2>
+template <bool LIM, bool W, class Text, class GM, class GM2>
 FAC_HD void succ_make_ctx2(const SuccConsts &K, const Text &T, const GM &G, const GM2 &G2, uint32_t start, uint32_t text_end, uint32_t node,
-                           const SuccRec &rec, float pen, uint32_t cnt, uint32_t pos, SuccCtx2 &C) {
-    // Text contract: T.sym(j) == SUCC_NOSYM and T.byte(j) == 0 for text_end <= j <= start + look-ahead, so the
+                           const SuccRec &rec, float pen, uint32_t cnt, uint32_t pos, SuccCtx2<W> &C) {
+    typedef typename SuccW<W>::M M;
+    const uint32_t NOSYM = SuccW<W>::NOSYM;
+    // Text contract: T.sym(j) == NOSYM and T.byte(j) == 0 for text_end <= j <= start + look-ahead, so the
     // three look-ahead symbols are read unconditionally (few branches: the kernel is issue-bound).
     const uint32_t jr = pos >> 10;
     const uint32_t j = start + jr;
@@ -166,17 +194,19 @@ FAC_HD void succ_make_ctx2(const SuccConsts &K, const Text &T, const GM &G, cons
     }
     const uint32_t flags = (last ? SUCC_F_LAST : 0u) | (in_text ? SUCC_F_IN_TEXT : 0u) | (j + 1 < text_end ? SUCC_F_HAS_NXT : 0u) |
                            (del_ok ? SUCC_F_DEL : 0u) | (ins_ok ? SUCC_F_INS : 0u);
-    uint32_t keep_sub = 0xFFFFFFFFu, keep_del = 0xFFFFFFFFu;  // states not on their last edit keep every child
+    const M bm = succ_bm<W>(rec);
+    M keep_sub = ~M(0), keep_del = ~M(0);  // states not on their last edit keep every child
     if (last) {
-        const uint32_t outm = G(node, SUCC_NOSYM);
-        keep_sub = outm | (nxt_s != SUCC_NOSYM ? G2(node, nxt_s, nxt2_s) : 0u);
-        keep_del = outm | (cur_s != SUCC_NOSYM ? G2(node, cur_s, nxt_s) : 0u);
+        const M outm = G(node, NOSYM);
+        keep_sub = outm | (nxt_s != NOSYM ? G2(node, nxt_s, nxt2_s) : M(0));
+        keep_del = outm | (cur_s != NOSYM ? G2(node, cur_s, nxt_s) : M(0));
     }
-    const uint32_t sub_m = (in_text && sub_ok) ? (rec.x & keep_sub & ~(1u << cur_s)) : 0u;
-    const uint32_t del_m = del_ok ? (rec.x & keep_del) : 0u;
-    C.bm = rec.x; C.fc = rec.y; C.pen = pen; C.cnt = cnt; C.pos = pos;
+    C.bm = bm;
+    C.sub_m = (in_text && sub_ok) ? (bm & keep_sub & ~(M(1) << cur_s)) : M(0);
+    C.del_m = del_ok ? (bm & keep_del) : M(0);
+    C.fc = succ_fc<W>(rec); C.pen = pen; C.cnt = cnt; C.pos = pos;
     C.packed = cur_b | (cur_s << 8) | (nxt_s << 16);
-    C.flags = flags; C.sub_m = sub_m; C.del_m = del_m;
+    C.flags = flags;
 }
 
 // position of the n-th (0-based) set bit of m; m must have more than n bits set
@@ -193,19 +223,25 @@ FAC_HD uint32_t succ_nth_bit(uint32_t m, uint32_t n) {
     if (n >= (m & 1u)) pos += 1;
     return pos;
 }
+FAC_HD uint32_t succ_nth_bit(uint64_t m, uint32_t n) {
+    const uint32_t lo = (uint32_t)m, c = FAC_POPC(lo);
+    return n >= c ? 32u + succ_nth_bit((uint32_t)(m >> 32), n - c) : succ_nth_bit(lo, n);
+}
 
 // Item r of a state's survivors: r < popc(sub_m) is a substitution, the rest are deletions.
 // Returns false when the substitution penalty exceeds the remaining budget (search.rs:829-834).
 // Written branch-free so substitution and deletion lanes of a warp stay converged.
-FAC_HD bool succ_item2(const SuccConsts &K, const float *sub_pen, const SuccCtx2 &C, uint32_t r, FacState &out) {
-    const uint32_t ns = FAC_POPC(C.sub_m);
+template <bool W>
+FAC_HD bool succ_item2(const SuccConsts &K, const float *sub_pen, const SuccCtx2<W> &C, uint32_t r, FacState &out) {
+    typedef typename SuccW<W>::M M;
+    const uint32_t ns = succ_popc(C.sub_m);
     const uint32_t jr = C.pos >> 10;
     const bool is_sub = r < ns;
     const uint32_t s = succ_nth_bit(is_sub ? C.sub_m : C.del_m, is_sub ? r : r - ns);
     // +inf in the table when similarity < min_symbol_similarity; deletions read a valid slot and ignore it
     const float tp = sub_pen[s * SUCC_SP_STRIDE + (C.packed & 0xFFu)];
     const float pp = is_sub ? tp : K.pen_del;
-    out.node = (C.fc & SUCC_FC_MASK) + FAC_POPC(C.bm & ((1u << s) - 1u));
+    out.node = C.fc + succ_popc((M)(C.bm & succ_below<M>(s)));
     out.pen = FAC_ADD(C.pen, pp);
     out.cnt = C.cnt + (is_sub ? 0x10000u : 0x100u);
     out.pos = is_sub ? succ_make_pos(jr + 1, jr + 1) : C.pos;
@@ -215,16 +251,17 @@ FAC_HD bool succ_item2(const SuccConsts &K, const float *sub_pen, const SuccCtx2
 // Swap (search.rs:935-989: node -text[j+1]-> x -text[j]-> n2, matched_start unchanged) and insertion
 // (search.rs:994-1029: forbidden before anything is consumed, matched_end unchanged, dead-end filter on the
 // current node when this is the last edit).
-template <bool LIM, class Recs>
-FAC_HD bool succ_swap2(const SuccConsts &K, const Recs &R, const SuccCtx2 &C, FacState &out) {
+template <bool LIM, bool W, class Recs>
+FAC_HD bool succ_swap2(const SuccConsts &K, const Recs &R, const SuccCtx2<W> &C, FacState &out) {
+    typedef typename SuccW<W>::M M;
     if ((C.flags & (SUCC_F_IN_TEXT | SUCC_F_HAS_NXT)) != (SUCC_F_IN_TEXT | SUCC_F_HAS_NXT)) return false;
     if (!(K.pen_swap <= FAC_SUB(K.maxpen, C.pen))) return false;
     const uint32_t cur_s = (C.packed >> 8) & 0xFFu, nxt_s = (C.packed >> 16) & 0xFFu;
     if (!((C.bm >> nxt_s) & 1u)) return false;
-    const SuccRec rx = R((C.fc & SUCC_FC_MASK) + FAC_POPC(C.bm & ((1u << nxt_s) - 1u)));
-    if (!succ_has_edge(rx, cur_s)) return false;
+    const SuccRec rx = R(C.fc + succ_popc((M)(C.bm & succ_below<M>(nxt_s))));
+    if (!succ_has_edge<W>(rx, cur_s)) return false;
     const uint32_t jr = C.pos >> 10;
-    out.node = succ_child(rx, cur_s); out.pen = FAC_ADD(C.pen, K.pen_swap); out.cnt = C.cnt + 0x1000000u; out.pos = succ_make_pos(jr + 2, jr + 2);
+    out.node = succ_child<W>(rx, cur_s); out.pen = FAC_ADD(C.pen, K.pen_swap); out.cnt = C.cnt + 0x1000000u; out.pos = succ_make_pos(jr + 2, jr + 2);
     if (LIM) {  // within_limits_swap_ahead of the TARGET node's limits (search.rs:119-130, 962-975)
         FacLimits L;
         if (!succ_pick_limits(K, K.node_lim[out.node], L)) return false;
@@ -232,8 +269,8 @@ FAC_HD bool succ_swap2(const SuccConsts &K, const Recs &R, const SuccCtx2 &C, Fa
     }
     return true;
 }
-template <bool LIM>
-FAC_HD bool succ_ins2(const SuccConsts &K, const SuccCtx2 &C, uint32_t node, bool has_out, FacState &out) {
+template <bool LIM, bool W>
+FAC_HD bool succ_ins2(const SuccConsts &K, const SuccCtx2<W> &C, uint32_t node, bool has_out, FacState &out) {
     if (!(C.flags & SUCC_F_IN_TEXT)) return false;
     const uint32_t jr = C.pos >> 10, mr = C.pos & 1023u;
     if (mr == 0 && jr == 0) return false;

@@ -172,38 +172,45 @@ int emu_search(const fac_config *cfg, const fac_pattern *pats, size_t np, const 
     return 0;
 }
 
+}  // extern "C"
+
 // ---- succinct-trie fast path (csrc/fac_succinct.h) run sequentially: same per-state helpers as the
 // kernel, a plain LIFO stack instead of the warp stack machine, the order-independent reduction with
 // tie detection, and the faithful emulation above for tied ("dirty") windows. ----
 struct EmuRecs { const SuccRec *r; SuccRec operator()(uint32_t n) const { return r[n]; } };
-struct EmuSText {   // first chars / symbols of the haystack graphemes; positions past the end read as (0, SUCC_NOSYM) like the kernel's padded tile
-    const uint8_t *b; const uint32_t *first; const uint8_t *symof; bool ci; uint32_t n;
+struct EmuSText {   // first chars / symbols of the haystack graphemes; positions past the end read as (0, NOSYM) like the kernel's padded tile
+    const uint8_t *b; const uint32_t *first; const uint8_t *symof; bool ci; uint32_t n; uint32_t nosym;
     uint32_t byte(uint32_t j) const {
         if (j >= n) return 0;
         if (first) return first[j] < 128u ? first[j] : SUCC_NONASCII;   // K1 stream: already folded
         const uint32_t c = b[j];
         return (ci && c >= 'A' && c <= 'Z') ? c + 32u : c;
     }
-    uint32_t sym(uint32_t j) const { if (j >= n) return SUCC_NOSYM; const uint32_t c = byte(j); return c < 128u ? symof[c] : SUCC_NOSYM; }
+    uint32_t sym(uint32_t j) const { if (j >= n) return nosym; const uint32_t c = byte(j); return c < 128u ? symof[c] : nosym; }
 };
+template <bool W>
 struct EmuGM {   // grandchild-mask rows: table for the first gm_nodes nodes, recomputed from the children beyond
-    const uint32_t *gm; uint32_t gm_nodes; const SuccRec *r;
-    uint32_t operator()(uint32_t node, uint32_t y) const {
-        if (node < gm_nodes) return gm[(size_t)node * 32 + y];
-        uint32_t bmv = r[node].x, k = 0, m = 0;
+    typedef typename SuccW<W>::M M;
+    const uint64_t *gm; uint32_t gm_nodes; const SuccRec *r;
+    M operator()(uint32_t node, uint32_t y) const {
+        if (node < gm_nodes) return (M)gm[(size_t)node * SuccW<W>::ROW + y];
+        M bmv = succ_bm<W>(r[node]), m = 0;
+        uint32_t k = 0;
         while (bmv) {
-            const uint32_t sy = (uint32_t)__builtin_ctz(bmv);
+            const uint32_t sy = (uint32_t)__builtin_ctzll((uint64_t)bmv);
             bmv &= bmv - 1;
-            const SuccRec &c = r[(r[node].y & SUCC_FC_MASK) + k++];
-            if (y == SUCC_NOSYM ? c.w != FAC_NONE : ((c.x >> y) & 1u)) m |= 1u << sy;
+            const SuccRec &c = r[succ_fc<W>(r[node]) + k++];
+            if (y == SuccW<W>::NOSYM ? succ_has_out<W>(c) : succ_has_edge<W>(c, y)) m |= M(1) << sy;
         }
         return m;
     }
 };
+template <bool W>
 struct EmuGM2 {
-    const uint32_t *gm2; uint32_t gm2_nodes; EmuGM G;
-    uint32_t operator()(uint32_t node, uint32_t y1, uint32_t y2) const {
-        if (node < gm2_nodes) return gm2[((size_t)node * 32 + y1) * 32 + y2];
+    typedef typename SuccW<W>::M M;
+    const uint64_t *gm2; uint32_t gm2_nodes; EmuGM<W> G;
+    M operator()(uint32_t node, uint32_t y1, uint32_t y2) const {
+        if (node < gm2_nodes) return (M)gm2[((size_t)node * SuccW<W>::ROW + y1) * SuccW<W>::ROW + y2];
         return G(node, y1);
     }
 };
@@ -211,6 +218,72 @@ struct EmuEmit {
     std::vector<FacCand> *v;
     void operator()(uint32_t sg, uint32_t eg, uint32_t pat, float sim, uint32_t cnt) { v->push_back(FacCand{sg, eg, pat, sim, cnt, 0, 0, 0}); }
 };
+
+template <bool W, bool LIMM>
+static void emu_succ_expand(const HostAutomaton &HA, const EmuText &ET, const uint8_t *hay, float thr, std::vector<FacCand> &cands, uint64_t &states) {
+    typedef typename SuccW<W>::M M;
+    const HostSuccinct &S = HA.succ;
+    const uint32_t N = (uint32_t)S.bm.size(), n = ET.tv.n, text_end = n, NOSYM = SuccW<W>::NOSYM;
+    std::vector<SuccRec> recs(N);
+    for (uint32_t i = 0; i < N; i++) {
+        union { float f; uint32_t u; } c;
+        c.f = FAC_SUB(S.prune_len[i], FAC_MUL(S.prune_low[i], thr));
+        if (W) recs[i] = SuccRec{(uint32_t)S.bm[i], (uint32_t)(S.bm[i] >> 32) | (S.out_idx[i] != FAC_NONE ? 0x80000000u : 0u),
+                                 S.fc[i] | ((uint32_t)S.insym[i] << SuccW<W>::SYM_SHIFT), c.u};
+        else recs[i] = SuccRec{(uint32_t)S.bm[i], S.fc[i] | ((uint32_t)S.insym[i] << SuccW<W>::SYM_SHIFT), c.u, S.out_idx[i]};
+    }
+    SuccConsts K;
+    K.thr = thr; K.maxpen = succ_ceil<W>(recs[0]); K.pen_ins = HA.pen_ins; K.pen_del = HA.pen_del; K.pen_swap = HA.pen_swap;
+    K.mef = S.limits_mode ? (int32_t)S.edit_bound : HA.mef;
+    K.lim = HA.lim.data(); K.node_lim = S.node_lim.data(); K.has_global = HA.has_global_limits; K.out_idx = S.out_idx.data();
+    const EmuRecs R{recs.data()};
+    const EmuGM<W> G{S.gmask.data(), S.gm_nodes, recs.data()};
+    const EmuGM2<W> G2{S.gmask2.data(), S.gm2_nodes, G};
+    const EmuSText T{hay, ET.tv.ascii ? nullptr : ET.first.data(), S.sym_of, HA.ci, n, NOSYM};
+    const SuccOut *out2 = (const SuccOut *)S.out2.data();
+    EmuEmit emit{&cands};
+    for (uint32_t start = 0; start < n; start++) {
+        if (HA.wskip) {
+            if (T.byte(start) != SUCC_NONASCII && !((S.first_mask >> T.sym(start)) & 1u)) {
+                if (start + 1 >= n) continue;
+                if (T.byte(start + 1) != SUCC_NONASCII && !((S.second_mask >> T.sym(start + 1)) & 1u)) continue;
+            }
+        }
+        if (S.exact_only) {  // engine without FuzzyLimits: only the exact chain from the root can emit
+            states += succ_walk<false, W>(K, R, out2, T, emit, start, text_end, 0u, R(0u), 0.f, 0u, 0u, 0u);
+            continue;
+        }
+        std::vector<FacState> stack;
+        stack.push_back(FacState{0, 0.f, 0, 0});
+        while (!stack.empty()) {
+            const FacState s = stack.back();
+            stack.pop_back();
+            states++;
+            const SuccRec rec = R(s.node);
+            if (s.pen > succ_ceil<W>(rec)) continue;
+            if (succ_has_out<W>(rec)) succ_outputs<LIMM>(K, out2, emit, succ_out_idx<W>(K, rec, s.node), s.pen, s.cnt, start, start + (s.pos & 1023u));
+            SuccCtx2<W> C;
+            succ_make_ctx2<LIMM, W>(K, T, G, G2, start, text_end, s.node, rec, s.pen, s.cnt, s.pos, C);
+            const bool last = (C.flags & SUCC_F_LAST) != 0;
+            const uint32_t jr = s.pos >> 10;
+            auto child = [&](const FacState &c) {
+                if (last) states += succ_walk<LIMM, W>(K, R, out2, T, emit, start, text_end, c.node, R(c.node), c.pen, c.cnt, c.pos >> 10, c.pos & 1023u);
+                else stack.push_back(c);
+            };
+            const uint32_t cur_s = (C.packed >> 8) & 0xFFu;
+            if (succ_has_edge<W>(rec, cur_s)) stack.push_back(FacState{succ_child<W>(rec, cur_s), s.pen, s.cnt, succ_make_pos(jr + 1, jr + 1)});
+            FacState c;
+            if (succ_swap2<LIMM, W>(K, R, C, c)) child(c);
+            if (succ_ins2<LIMM, W>(K, C, s.node, succ_has_out<W>(rec), c)) child(c);
+            const uint32_t n_items = succ_popc(C.sub_m) + succ_popc(C.del_m);
+            for (uint32_t r = 0; r < n_items; r++)
+                if (succ_item2<W>(K, S.sub_pen.data(), C, r, c)) child(c);
+        }
+    }
+    (void)M(0);
+}
+
+extern "C" {
 
 // returns 0 ok, -3 engine/haystack outside the fast kernel's domain.  info[0] = dirty windows, info[1] = states visited
 int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t np, const uint8_t *hay, size_t len, float thr,
@@ -222,75 +295,11 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
     if (!S.ok || HA.beam_width != 0 || HA.has_auto_beam) return -3;
     EmuText ET; segment_host(HA, hay, len, ET);
     if (!ET.tv.ascii && !S.unicode_text_ok) return -3;
-    const uint32_t N = (uint32_t)S.bm.size(), n = ET.tv.n, text_end = n;
-    std::vector<SuccRec> recs(N);
-    for (uint32_t i = 0; i < N; i++) {
-        union { float f; uint32_t u; } c;
-        c.f = FAC_SUB(S.prune_len[i], FAC_MUL(S.prune_low[i], thr));
-        recs[i] = SuccRec{S.bm[i], S.fc_sym[i], c.u, S.out_idx[i]};
-    }
-    SuccConsts K;
-    K.thr = thr; K.maxpen = FAC_AS_FLOAT(recs[0].z); K.pen_ins = HA.pen_ins; K.pen_del = HA.pen_del; K.pen_swap = HA.pen_swap; K.mef = S.limits_mode ? (int32_t)S.edit_bound : HA.mef;
-    K.lim = HA.lim.data(); K.node_lim = S.node_lim.data(); K.has_global = HA.has_global_limits;
-    const bool LIMM = S.limits_mode;
-    const EmuRecs R{recs.data()};
-    const EmuGM G{S.gmask.data(), S.gm_nodes, recs.data()};
-    const EmuGM2 G2{S.gmask2.data(), S.gm2_nodes, G};
-    const EmuSText T{hay, ET.tv.ascii ? nullptr : ET.first.data(), S.sym_of, HA.ci, n};
-    const SuccOut *out2 = (const SuccOut *)S.out2.data();
+    const uint32_t n = ET.tv.n;
     std::vector<FacCand> cands;
-    EmuEmit emit{&cands};
     uint64_t states = 0;
-    const bool warpsim = getenv("EMU_WARPSIM") != nullptr;
-    uint64_t sim_rounds = 0, sim_max = 0, sim_sum = 0;
-    uint64_t st_pop = 0, st_items = 0, st_surv = 0, st_walk = 0, st_deg_hist[33] = {0};
-    for (uint32_t start = 0; start < n; start++) {
-        if (HA.wskip) {
-            if (T.byte(start) != SUCC_NONASCII && !((S.first_mask >> T.sym(start)) & 1u)) {
-                if (start + 1 >= n) continue;
-                if (T.byte(start + 1) != SUCC_NONASCII && !((S.second_mask >> T.sym(start + 1)) & 1u)) continue;
-            }
-        }
-        if (S.exact_only) {  // engine without FuzzyLimits: only the exact chain from the root can emit
-            states += succ_walk<false>(K, R, out2, T, emit, start, text_end, R(0u), 0.f, 0u, 0u, 0u);
-            continue;
-        }
-        std::vector<FacState> stack;
-        stack.push_back(FacState{0, 0.f, 0, 0});
-        while (!stack.empty()) {
-          const size_t npop = warpsim ? std::min<size_t>(32, stack.size()) : 1;
-          std::vector<FacState> popped(stack.end() - npop, stack.end());
-          std::reverse(popped.begin(), popped.end());
-          stack.resize(stack.size() - npop);
-          uint64_t lane_max = 0, lane_sum = 0;
-          for (const FacState &s : popped) {
-            uint64_t lane_work = 0;
-            states++;
-            const SuccRec rec = R(s.node);
-            if (s.pen > FAC_AS_FLOAT(rec.z)) continue;  /*dead*/
-            if (rec.w != FAC_NONE) { if (LIMM) succ_outputs<true>(K, out2, emit, rec.w, s.pen, s.cnt, start, start + (s.pos & 1023u)); else succ_outputs<false>(K, out2, emit, rec.w, s.pen, s.cnt, start, start + (s.pos & 1023u)); }
-            SuccCtx2 C;
-            if (LIMM) succ_make_ctx2<true>(K, T, G, G2, start, text_end, s.node, rec, s.pen, s.cnt, s.pos, C); else succ_make_ctx2<false>(K, T, G, G2, start, text_end, s.node, rec, s.pen, s.cnt, s.pos, C);
-            const bool last = (C.flags & SUCC_F_LAST) != 0;
-            const uint32_t jr = s.pos >> 10;
-            auto child = [&](const FacState &c) {
-                if (last) { const uint32_t w_ = LIMM ? succ_walk<true>(K, R, out2, T, emit, start, text_end, R(c.node), c.pen, c.cnt, c.pos >> 10, c.pos & 1023u) : succ_walk<false>(K, R, out2, T, emit, start, text_end, R(c.node), c.pen, c.cnt, c.pos >> 10, c.pos & 1023u); states += w_; st_walk += w_; st_surv++; lane_work += w_; }
-                else stack.push_back(c);
-            };
-            const uint32_t cur_s = (C.packed >> 8) & 0xFFu;
-            if (succ_has_edge(rec, cur_s)) stack.push_back(FacState{succ_child(rec, cur_s), s.pen, s.cnt, succ_make_pos(jr + 1, jr + 1)});
-            FacState c;
-            if (LIMM ? succ_swap2<true>(K, R, C, c) : succ_swap2<false>(K, R, C, c)) child(c);
-            if (LIMM ? succ_ins2<true>(K, C, s.node, rec.w != FAC_NONE, c) : succ_ins2<false>(K, C, s.node, rec.w != FAC_NONE, c)) child(c);
-            const uint32_t n_items = FAC_POPC(C.sub_m) + FAC_POPC(C.del_m);
-            st_pop++; st_items += n_items; st_deg_hist[std::min<uint32_t>(n_items, 32)]++;
-            for (uint32_t r = 0; r < n_items; r++)
-                if (succ_item2(K, S.sub_pen.data(), C, r, c)) child(c);
-            lane_max = std::max(lane_max, lane_work); lane_sum += lane_work;
-          }
-          sim_rounds++; sim_max += lane_max; sim_sum += lane_sum;
-        }
-    }
+    if (S.wide) { if (S.limits_mode) emu_succ_expand<true, true>(HA, ET, hay, thr, cands, states); else emu_succ_expand<true, false>(HA, ET, hay, thr, cands, states); }
+    else { if (S.limits_mode) emu_succ_expand<false, true>(HA, ET, hay, thr, cands, states); else emu_succ_expand<false, false>(HA, ET, hay, thr, cands, states); }
     typedef std::tuple<uint32_t, uint32_t, uint32_t> Key;
     struct Best { float sim; uint32_t cmin, cmax; };
     std::map<Key, Best> best;
@@ -332,7 +341,6 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
     *n_out = res.size();
     *out = (fac_match *)malloc(sizeof(fac_match) * (res.size() ? res.size() : 1));
     if (!res.empty()) memcpy(*out, res.data(), sizeof(fac_match) * res.size());
-    if (getenv("EMU_STATS")) { fprintf(stderr, "windows %u popped %llu items %llu survivors %llu walk_steps %llu\n deg hist:", n, (unsigned long long)st_pop, (unsigned long long)st_items, (unsigned long long)st_surv, (unsigned long long)st_walk); for (int d = 0; d < 33; d++) fprintf(stderr, " %llu", (unsigned long long)st_deg_hist[d]); fprintf(stderr, "\n warpsim rounds %llu sum(max steps) %llu sum(steps) %llu\n", (unsigned long long)sim_rounds, (unsigned long long)sim_max, (unsigned long long)sim_sum); }
     if (info) { info[0] = n_dirty; info[1] = states; info[2] = cands.size(); info[3] = best.size(); }
     return 0;
 }

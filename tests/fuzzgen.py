@@ -107,7 +107,9 @@ def rand_dense_case(r, backend):
     hundred random patterns over a small alphabet, so that the trie is dense, ties are common and outputs pile
     up -- plus random penalties / similarity / weights / case folding.  Returns (engine, haystack, thr, desc)."""
     from fac_b200 import SearchOptions  # noqa: F401
-    alpha = r.choice(["abcde", "abcdefghij", "etaoinshrdlu", "abcdefghijklmnopqrstuvwxyz", "ab01-_ ."])
+    alpha = r.choice(["abcde", "abcdefghij", "etaoinshrdlu", "abcdefghijklmnopqrstuvwxyz", "ab01-_ .",
+                      "abcdefghijklmnopqrstuvwxyz0123456789-_ .",                    # 40 symbols: wide layout
+                      "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456"])  # 59 symbols (case-sensitive engines)
     npat = r.choice([20, 60, 200, 500])
     lo, hi = r.choice([(2, 6), (3, 9), (5, 12)])
     pats, seen = [], set()
