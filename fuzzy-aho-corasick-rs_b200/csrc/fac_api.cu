@@ -316,8 +316,7 @@ fac_status launch_succinct(const fac_engine *E, Workspace *ws, const TextView &t
     if (d_tiles) { P.tiles = d_tiles; P.n_tiles = n_explicit; }
     // deeper edit budgets push whole sibling sets of non-final states: fewer warps, deeper stacks
     const bool deep = S.limits_mode || E->host.mef > 2;
-    // 64-bit masks need more registers than a 1024-thread CTA leaves per thread
-    const uint32_t nt = deep ? std::min<uint32_t>(E->succ_nt, 512u) : (S.wide ? std::min<uint32_t>(E->succ_nt, 768u) : E->succ_nt);
+    const uint32_t nt = deep ? std::min<uint32_t>(E->succ_nt, 512u) : E->succ_nt;
     const uint32_t nw = nt / 32;
     P.stack_cap = E->succ_stack ? E->succ_stack : (!deep ? 128u : 384u);
     P.text_cap = (P.tile + P.lookahead + 16u + 15u) & ~15u;
