@@ -153,9 +153,10 @@ struct SuccCtx2 {
     uint32_t fc;       // first child
     float pen;
     uint32_t cnt, pos;
-    uint32_t packed;   // cur byte | cur sym << 8 | next sym << 16
+    uint32_t packed;   // cur byte | cur sym << 8 | next sym << 16 | next-next sym << 24
     uint32_t flags;
 };
+template <bool W> FAC_HD uint32_t nxt2_of(const SuccCtx2<W> &C) { return C.packed >> 24; }
 
 //
 // Two-deep refinement for the first gm2_nodes nodes:  gm2[node][y1][y2] = { s : c = child(node, s) has edge y1 and
@@ -205,7 +206,7 @@ FAC_HD void succ_make_ctx2(const SuccConsts &K, const Text &T, const GM &G, cons
     C.sub_m = (in_text && sub_ok) ? (bm & keep_sub & ~(M(1) << cur_s)) : M(0);
     C.del_m = del_ok ? (bm & keep_del) : M(0);
     C.fc = succ_fc<W>(rec); C.pen = pen; C.cnt = cnt; C.pos = pos;
-    C.packed = cur_b | (cur_s << 8) | (nxt_s << 16);
+    C.packed = cur_b | (cur_s << 8) | (nxt_s << 16) | (nxt2_s << 24);
     C.flags = flags;
 }
 
@@ -266,6 +267,12 @@ FAC_HD bool succ_swap2(const SuccConsts &K, const Recs &R, const SuccCtx2<W> &C,
         FacLimits L;
         if (!succ_pick_limits(K, K.node_lim[out.node], L)) return false;
         if (!(fac_none_or_lt(L.edits, (int)fac_edits_of(C.cnt)) && fac_none_or_lt(L.swp, (int)(C.cnt >> 24)))) return false;
+    }
+    if (C.flags & SUCC_F_LAST) {
+        // the exhausted swap child visits n2 at j+2 and then only follows text[j+2]: without an output at n2 and
+        // without that edge it cannot emit -- dropping it is result-neutral
+        const SuccRec r2 = R(out.node);
+        if (!succ_has_out<W>(r2) && !succ_has_edge<W>(r2, nxt2_of(C))) return false;
     }
     return true;
 }
