@@ -929,9 +929,8 @@ fac_status prefilter_slices(const fac_engine *E, Workspace *ws, const uint8_t *d
     {
         size_t tb = 0;
         cub::TransformInputIterator<unsigned long long, CovCountToU64, const uint32_t *> it(ws->covcnt.as<uint32_t>(), CovCountToU64());
-        CK(cub::DeviceScan::ExclusiveSum((void *)nullptr, tb, it, ws->covoff.as<unsigned long long>(), (int64_t)n_words + 1, s));
+        CK(cub::DeviceScan::ExclusiveSum((void *)nullptr, tb, it, ws->covoff.as<unsigned long long>(), (int64_t)n_words, s));
         CKS(ws->cubtmp.ensure(tb));
-        CK(cudaMemsetAsync(ws->covcnt.as<uint32_t>() + n_words - 0, 0, 0, s));
         CK(cub::DeviceScan::ExclusiveSum(ws->cubtmp.p, tb, it, ws->covoff.as<unsigned long long>(), (int64_t)n_words, s));
     }
     // total = off[last] + cnt[last]

@@ -1,8 +1,10 @@
 // fac_kernels.cuh -- hand-written sm_100a kernels of the fuzzy search path.
 //
 //   k_scan_bytes        haystack classification (is_ascii, src/search.rs:196) in one coalesced pass
-//   k_expand            K3: fuzzy frontier expansion, one CTA per tile of start windows
-//                       (search_unsorted_impl, src/search.rs:533-1104)
+//   k_expand            K3, generic / order-faithful variant: fuzzy frontier expansion, one CTA per tile of
+//                       start windows (search_unsorted_impl, src/search.rs:533-1104).  Engines inside the
+//                       fast kernel's domain run k_expand_succinct (fac_succinct.cuh) instead and come here
+//                       only for the windows whose tie-break needs the reference's FIFO order.
 //   k_best_insert/select  best-per-(start,end,pattern) reduction of the raw candidates
 //                       (the `best` map, src/search.rs:705-735 + :1111-1118)
 //
