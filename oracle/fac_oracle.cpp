@@ -519,6 +519,43 @@ struct VKeyHash {
         return (size_t)(h ^ (h >> 29));
     }
 };
+// The reference's `visited` is an FxHashMap pre-sized and cleared per start window (search.rs:456-480, 608-628).
+// Open addressing with an epoch stamp per slot gives the same map semantics with an O(1) clear, so that the
+// CPU baseline timed by bench.py is not handicapped by node-based std::unordered_map allocation.
+struct FlatVisited {
+    struct Slot { VKey k; float pen; uint32_t epoch; };
+    std::vector<Slot> tab;
+    size_t mask = 0, count = 0;
+    uint32_t epoch = 1;
+    FlatVisited() { tab.assign(1024, Slot{VKey{0, 0, 0, 0, 0}, 0.f, 0}); mask = 1023; }
+    void clear() {
+        count = 0;
+        if (++epoch == 0) { for (auto &sl : tab) sl.epoch = 0; epoch = 1; }
+    }
+    void grow() {
+        std::vector<Slot> old;
+        old.swap(tab);
+        tab.assign(old.size() * 2, Slot{VKey{0, 0, 0, 0, 0}, 0.f, 0});
+        mask = tab.size() - 1;
+        for (const Slot &sl : old)
+            if (sl.epoch == epoch) {
+                size_t h = VKeyHash()(sl.k) & mask;
+                while (tab[h].epoch == epoch) h = (h + 1) & mask;
+                tab[h] = sl;
+            }
+    }
+    // the stored minimum of `k` if present, else inserts (k, pen) and returns nullptr
+    float *find_or_insert(const VKey &k, float pen) {
+        if ((count + 1) * 2 > tab.size()) grow();
+        size_t h = VKeyHash()(k) & mask;
+        for (;;) {
+            Slot &sl = tab[h];
+            if (sl.epoch != epoch) { sl.k = k; sl.pen = pen; sl.epoch = epoch; count++; return nullptr; }
+            if (sl.k == k) return &sl.pen;
+            h = (h + 1) & mask;
+        }
+    }
+};
 struct BKey { size_t s, e, p; bool operator<(const BKey &o) const { return s != o.s ? s < o.s : (e != o.e ? e < o.e : p < o.p); } };
 
 static inline int32_t total_key(float f) {  // f32::total_cmp
@@ -582,7 +619,7 @@ static void search_raw(const Engine &E, const uint8_t *s, size_t len, float thr,
     const std::vector<uint32_t> &tc = H.first;
     std::map<BKey, Match> best;
     std::vector<State> queue;
-    std::unordered_map<VKey, float, VKeyHash> visited;
+    FlatVisited visited;
     const Node &root = E.nodes[0];
     const float max_pen = root.prune_len - root.prune_low * thr;  // search.rs:487
     const float min_sym = E.min_symbol_similarity;
@@ -639,9 +676,7 @@ static void search_raw(const Engine &E, const uint8_t *s, size_t len, float thr,
             const uint32_t node = S.node, j = S.j, ms = S.ms, me = S.me, cnt = S.cnt;
             const float pen = S.pen; const int edits = S.edits;
             VKey key{node, j, ms, me, cnt};  // search.rs:608-628
-            auto vit = visited.find(key);
-            if (vit != visited.end()) { if (vit->second <= pen) continue; vit->second = pen; }
-            else visited.emplace(key, pen);
+            if (float *seen = visited.find_or_insert(key, pen)) { if (*seen <= pen) continue; *seen = pen; }
             const Node &nd = E.nodes[node];
             if (pen > nd.prune_len - nd.prune_low * thr) continue;  // search.rs:638-642
             const float remaining = max_pen - pen;                    // search.rs:648
