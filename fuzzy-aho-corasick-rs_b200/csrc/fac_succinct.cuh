@@ -235,34 +235,25 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
             __syncthreads();
             continue;
         }
-        // ---- windows of the tile, one per warp at a time ----
-        for (;;) {
-            uint32_t w = 0;
-            if (lane == 0) w = atomicAdd(&s_next_win, 1u);
-            w = __shfl_sync(0xFFFFFFFFu, w, 0);
-            if (w >= count) break;
-            const uint32_t start = tile_start + w;
-            if (P.wskip) {  // 2-gram window skip (search.rs:535-553); result-neutral
-                // only ASCII first chars take part in the skip test (`c < 128 && !bit`, search.rs:538-551)
-                if (T.byte(start) != SUCC_NONASCII && !((P.first_mask >> T.sym(start)) & 1u)) {
-                    if (start + 1 >= text_end) continue;
-                    if (T.byte(start + 1) != SUCC_NONASCII && !((P.second_mask >> T.sym(start + 1)) & 1u)) continue;
-                }
-            }
-            uint32_t top = 1, wn = 0;      // stack height, walk-queue length (warp-uniform)
+        // ---- windows of the tile: every warp runs ONE stack machine over a stream of start windows ----
+        // A state carries its window (position word bits 20..31), so the next window's root is fed in as soon as
+        // fewer than 32 states are left: pops, item rounds and walk drains stay full across window boundaries.
+        {
+            uint32_t top = 0, wn = 0;      // stack height, walk-queue length (warp-uniform)
             uint32_t b0 = 0, total = 0;    // item rounds of the current pop
             uint32_t off = 0;              // exclusive prefix of the lanes' item counts
+            bool more = true, fed = false; // windows left in the tile; one window fed since the last pop
             SuccCtx2<W> C;
             C.bm = C.sub_m = C.del_m = 0; C.fc = C.cnt = C.pos = C.packed = C.flags = 0; C.pen = 0.f;
-            if (lane == 0) stk[0] = make_uint4(0u, 0u, 0u, 0u);
             for (;;) {
                 __syncwarp();
                 // (1) exhausted children: exact transitions only, walked 32 at a time
-                if (wn >= 32u || (wn && b0 >= total && top == 0)) {
+                if (wn >= 32u || (wn && b0 >= total && top == 0 && !more)) {
                     const uint32_t n = min(wn, 32u);
                     if (lane < n) {
                         const uint4 q = wq[wn - n + lane];
-                        n_states += succ_walk<LIM, W>(K, R, out2, T, emit, start, text_end, q.x, R(q.x), __uint_as_float(q.y), q.z, q.w >> 10, q.w & 1023u);
+                        n_states += succ_walk<LIM, W>(K, R, out2, T, emit, tile_start + (q.w >> 20), text_end, q.x, R(q.x), __uint_as_float(q.y), q.z,
+                                                      succ_jr(q.w), succ_mr(q.w));
                     }
                     wn -= n;
                     continue;
@@ -298,13 +289,39 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                     if (__any_sync(0xFFFFFFFFu, to_stack)) succ_warp_push(stk, top, to_stack, c);
                     continue;
                 }
-                if (top == 0) break;
-                // (3) pop up to 32 states
+                // (3) feed: one more start window when the stack runs low
+                if (more && !fed && top < 32u) {
+                    uint32_t w = 0;
+                    if (lane == 0) w = atomicAdd(&s_next_win, 1u);
+                    w = __shfl_sync(0xFFFFFFFFu, w, 0);
+                    if (w >= count) { more = false; continue; }
+                    const uint32_t start = tile_start + w;
+                    bool skip = false;
+                    if (P.wskip) {  // 2-gram window skip (search.rs:535-553); result-neutral.  Only ASCII first chars take part
+                        if (T.byte(start) != SUCC_NONASCII && !((P.first_mask >> T.sym(start)) & 1u))
+                            skip = start + 1 >= text_end || (T.byte(start + 1) != SUCC_NONASCII && !((P.second_mask >> T.sym(start + 1)) & 1u));
+                    }
+                    if (!skip) {
+                        if (lane == 0) stk[top] = make_uint4(0u, 0u, 0u, w << 20);
+                        top++;
+                        fed = true;
+                    }
+                    continue;
+                }
+                if (top == 0) {
+                    if (!more && wn == 0) break;
+                    fed = false;   // nothing to pop: allow the next feed (or fall into the final drain)
+                    if (!more) continue;
+                    continue;
+                }
+                // (4) pop up to 32 states
+                fed = false;
                 const uint32_t navail = min(top, 32u);
                 const bool has = lane < navail;
                 uint4 sv = make_uint4(0, 0, 0, 0);
                 SuccRec rec; rec.x = rec.y = rec.z = 0; rec.w = FAC_NONE;
                 if (has) { sv = stk[top - 1u - lane]; rec = R(sv.x); }
+                const uint32_t start = tile_start + (sv.w >> 20);
                 const float pen = __uint_as_float(sv.y);
                 const bool dead = !has || pen > succ_ceil<W>(rec);   // node ceiling, search.rs:638-642
                 const bool last = (int)fac_edits_of(sv.z) + 1 >= K.mef;
@@ -321,12 +338,14 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                     const uint32_t viol = __ballot_sync(0xFFFFFFFFu, has && (incl > cap - top + lane + 1u));
                     if (viol) n_pop = (uint32_t)(__ffs(viol) - 1);
                 }
-                if (n_pop == 0) {  // the top state alone does not fit: give the window to the faithful kernel
+                if (n_pop == 0) {  // the top state alone does not fit: its window goes to the faithful kernel, the state is dropped
                     if (lane == 0) {
-                        atomicOr(&P.dirty[(start - P.seg_begin) >> 5], 1u << ((start - P.seg_begin) & 31u));
+                        const uint32_t wabs = start - P.seg_begin;
+                        atomicOr(&P.dirty[wabs >> 5], 1u << (wabs & 31u));
                         atomicAdd(&P.counters[7], 1ull);
                     }
-                    break;
+                    top -= 1u;
+                    continue;
                 }
                 const bool active = lane < n_pop && !dead;
                 top -= n_pop;
@@ -339,13 +358,13 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                 C.sub_m = C.del_m = 0;
                 if (active) {
                     n_states++;
-                    if (succ_has_out<W>(rec)) succ_outputs<LIM>(K, out2, emit, succ_out_idx<W>(K, rec, sv.x), pen, sv.z, start, start + (sv.w & 1023u));
+                    if (succ_has_out<W>(rec)) succ_outputs<LIM>(K, out2, emit, succ_out_idx<W>(K, rec, sv.x), pen, sv.z, start, start + succ_mr(sv.w));
                     succ_make_ctx2<LIM, W>(K, T, G, G2, start, text_end, sv.x, rec, pen, sv.z, sv.w, C);
-                    const uint32_t jr = sv.w >> 10;
+                    const uint32_t jr = succ_jr(sv.w);
                     const uint32_t cur_s = (C.packed >> 8) & 0xFFu;
                     if (succ_has_edge<W>(rec, cur_s)) {   // exact transition, search.rs:776-798
                         p_ex = true;
-                        c_ex.node = succ_child<W>(rec, cur_s); c_ex.pen = pen; c_ex.cnt = sv.z; c_ex.pos = succ_make_pos(jr + 1, jr + 1);
+                        c_ex.node = succ_child<W>(rec, cur_s); c_ex.pen = pen; c_ex.cnt = sv.z; c_ex.pos = succ_repos(sv.w, jr + 1, jr + 1);
                     }
                     p_sw = succ_swap2<LIM, W>(K, R, C, c_sw);
                     p_in = succ_ins2<LIM, W>(K, C, sv.x, succ_has_out<W>(rec), c_in);

@@ -88,7 +88,12 @@ template <bool W> FAC_HD uint32_t succ_child(const SuccRec &r, uint32_t sym) {
     return succ_fc<W>(r) + succ_popc((M)(succ_bm<W>(r) & succ_below<M>(sym)));
 }
 template <bool W> FAC_HD bool succ_has_edge(const SuccRec &r, uint32_t sym) { return (succ_bm<W>(r) >> sym) & 1u; }
-FAC_HD uint32_t succ_make_pos(uint32_t jr, uint32_t mr) { return (jr << 10) | mr; }
+// State position word: window-in-tile << 20 | (j - start) << 10 | (matched_end - start).  The window field lets one
+// warp keep states of several start windows on its stack (the kernel feeds the next window before the current
+// one has drained); the emulator always uses window 0.
+FAC_HD uint32_t succ_jr(uint32_t pos) { return (pos >> 10) & 1023u; }
+FAC_HD uint32_t succ_mr(uint32_t pos) { return pos & 1023u; }
+FAC_HD uint32_t succ_repos(uint32_t pos, uint32_t jr, uint32_t mr) { return (pos & 0xFFF00000u) | (jr << 10) | mr; }
 
 // Outputs of one node visit (search.rs:659-737): fast-path limit check is `edits > MAX_EDITS_FAST`,
 // never true here because no state exceeds the budget.
@@ -176,7 +181,7 @@ FAC_HD void succ_make_ctx2(const SuccConsts &K, const Text &T, const GM &G, cons
     const uint32_t NOSYM = SuccW<W>::NOSYM;
     // Text contract: T.sym(j) == NOSYM and T.byte(j) == 0 for text_end <= j <= start + look-ahead, so the
     // three look-ahead symbols are read unconditionally (few branches: the kernel is issue-bound).
-    const uint32_t jr = pos >> 10;
+    const uint32_t jr = succ_jr(pos);
     const uint32_t j = start + jr;
     const bool last = (int)fac_edits_of(cnt) + 1 >= K.mef;
     const bool in_text = j < text_end;
@@ -236,7 +241,7 @@ template <bool W>
 FAC_HD bool succ_item2(const SuccConsts &K, const float *sub_pen, const SuccCtx2<W> &C, uint32_t r, FacState &out) {
     typedef typename SuccW<W>::M M;
     const uint32_t ns = succ_popc(C.sub_m);
-    const uint32_t jr = C.pos >> 10;
+    const uint32_t jr = succ_jr(C.pos);
     const bool is_sub = r < ns;
     const uint32_t s = succ_nth_bit(is_sub ? C.sub_m : C.del_m, is_sub ? r : r - ns);
     // +inf in the table when similarity < min_symbol_similarity; deletions read a valid slot and ignore it
@@ -245,7 +250,7 @@ FAC_HD bool succ_item2(const SuccConsts &K, const float *sub_pen, const SuccCtx2
     out.node = C.fc + succ_popc((M)(C.bm & succ_below<M>(s)));
     out.pen = FAC_ADD(C.pen, pp);
     out.cnt = C.cnt + (is_sub ? 0x10000u : 0x100u);
-    out.pos = is_sub ? succ_make_pos(jr + 1, jr + 1) : C.pos;
+    out.pos = is_sub ? succ_repos(C.pos, jr + 1, jr + 1) : C.pos;
     return !(is_sub && pp > FAC_SUB(K.maxpen, C.pen));
 }
 
@@ -261,8 +266,8 @@ FAC_HD bool succ_swap2(const SuccConsts &K, const Recs &R, const SuccCtx2<W> &C,
     if (!((C.bm >> nxt_s) & 1u)) return false;
     const SuccRec rx = R(C.fc + succ_popc((M)(C.bm & succ_below<M>(nxt_s))));
     if (!succ_has_edge<W>(rx, cur_s)) return false;
-    const uint32_t jr = C.pos >> 10;
-    out.node = succ_child<W>(rx, cur_s); out.pen = FAC_ADD(C.pen, K.pen_swap); out.cnt = C.cnt + 0x1000000u; out.pos = succ_make_pos(jr + 2, jr + 2);
+    const uint32_t jr = succ_jr(C.pos);
+    out.node = succ_child<W>(rx, cur_s); out.pen = FAC_ADD(C.pen, K.pen_swap); out.cnt = C.cnt + 0x1000000u; out.pos = succ_repos(C.pos, jr + 2, jr + 2);
     if (LIM) {  // within_limits_swap_ahead of the TARGET node's limits (search.rs:119-130, 962-975)
         FacLimits L;
         if (!succ_pick_limits(K, K.node_lim[out.node], L)) return false;
@@ -279,13 +284,13 @@ FAC_HD bool succ_swap2(const SuccConsts &K, const Recs &R, const SuccCtx2<W> &C,
 template <bool LIM, bool W>
 FAC_HD bool succ_ins2(const SuccConsts &K, const SuccCtx2<W> &C, uint32_t node, bool has_out, FacState &out) {
     if (!(C.flags & SUCC_F_IN_TEXT)) return false;
-    const uint32_t jr = C.pos >> 10, mr = C.pos & 1023u;
+    const uint32_t jr = succ_jr(C.pos), mr = succ_mr(C.pos);
     if (mr == 0 && jr == 0) return false;
     if (!(K.pen_ins <= FAC_SUB(K.maxpen, C.pen))) return false;
     if (!(C.flags & SUCC_F_INS)) return false;
     if (!LIM && (C.flags & SUCC_F_LAST) && !has_out) {
         if (!(C.flags & SUCC_F_HAS_NXT) || !((C.bm >> ((C.packed >> 16) & 0xFFu)) & 1u)) return false;
     }
-    out.node = node; out.pen = FAC_ADD(C.pen, K.pen_ins); out.cnt = C.cnt + 1u; out.pos = succ_make_pos(jr + 1, mr);
+    out.node = node; out.pen = FAC_ADD(C.pen, K.pen_ins); out.cnt = C.cnt + 1u; out.pos = succ_repos(C.pos, jr + 1, mr);
     return true;
 }

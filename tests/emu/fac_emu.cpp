@@ -261,17 +261,17 @@ static void emu_succ_expand(const HostAutomaton &HA, const EmuText &ET, const ui
             states++;
             const SuccRec rec = R(s.node);
             if (s.pen > succ_ceil<W>(rec)) continue;
-            if (succ_has_out<W>(rec)) succ_outputs<LIMM>(K, out2, emit, succ_out_idx<W>(K, rec, s.node), s.pen, s.cnt, start, start + (s.pos & 1023u));
+            if (succ_has_out<W>(rec)) succ_outputs<LIMM>(K, out2, emit, succ_out_idx<W>(K, rec, s.node), s.pen, s.cnt, start, start + succ_mr(s.pos));
             SuccCtx2<W> C;
             succ_make_ctx2<LIMM, W>(K, T, G, G2, start, text_end, s.node, rec, s.pen, s.cnt, s.pos, C);
             const bool last = (C.flags & SUCC_F_LAST) != 0;
-            const uint32_t jr = s.pos >> 10;
+            const uint32_t jr = succ_jr(s.pos);
             auto child = [&](const FacState &c) {
-                if (last) states += succ_walk<LIMM, W>(K, R, out2, T, emit, start, text_end, c.node, R(c.node), c.pen, c.cnt, c.pos >> 10, c.pos & 1023u);
+                if (last) states += succ_walk<LIMM, W>(K, R, out2, T, emit, start, text_end, c.node, R(c.node), c.pen, c.cnt, succ_jr(c.pos), succ_mr(c.pos));
                 else stack.push_back(c);
             };
             const uint32_t cur_s = (C.packed >> 8) & 0xFFu;
-            if (succ_has_edge<W>(rec, cur_s)) stack.push_back(FacState{succ_child<W>(rec, cur_s), s.pen, s.cnt, succ_make_pos(jr + 1, jr + 1)});
+            if (succ_has_edge<W>(rec, cur_s)) stack.push_back(FacState{succ_child<W>(rec, cur_s), s.pen, s.cnt, succ_repos(s.pos, jr + 1, jr + 1)});
             FacState c;
             if (succ_swap2<LIMM, W>(K, R, C, c)) child(c);
             if (succ_ins2<LIMM, W>(K, C, s.node, succ_has_out<W>(rec), c)) child(c);
