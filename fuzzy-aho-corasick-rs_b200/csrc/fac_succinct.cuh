@@ -289,29 +289,31 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                     if (__any_sync(0xFFFFFFFFu, to_stack)) succ_warp_push(stk, top, to_stack, c);
                     continue;
                 }
-                // (3) feed: one more start window when the stack runs low
+                // (3) feed more start windows when the stack runs low: one root at a time when a root fans out into
+                //     dozens of children, a whole warp's worth when the root is already on its last edit (edits(1))
                 if (more && !fed && top < 32u) {
-                    uint32_t w = 0;
-                    if (lane == 0) w = atomicAdd(&s_next_win, 1u);
-                    w = __shfl_sync(0xFFFFFFFFu, w, 0);
-                    if (w >= count) { more = false; continue; }
-                    const uint32_t start = tile_start + w;
-                    bool skip = false;
-                    if (P.wskip) {  // 2-gram window skip (search.rs:535-553); result-neutral.  Only ASCII first chars take part
+                    const uint32_t nf = K.mef <= 1 ? 32u - top : 1u;
+                    uint32_t w0 = 0;
+                    if (lane == 0) w0 = atomicAdd(&s_next_win, nf);
+                    w0 = __shfl_sync(0xFFFFFFFFu, w0, 0);
+                    if (w0 >= count) { more = false; continue; }
+                    if (w0 + nf >= count) more = false;   // this fetch takes the tail of the tile
+                    const uint32_t w = w0 + lane;
+                    bool push = lane < nf && w < count;
+                    if (push && P.wskip) {  // 2-gram window skip (search.rs:535-553); result-neutral.  Only ASCII first chars take part
+                        const uint32_t start = tile_start + w;
                         if (T.byte(start) != SUCC_NONASCII && !((P.first_mask >> T.sym(start)) & 1u))
-                            skip = start + 1 >= text_end || (T.byte(start + 1) != SUCC_NONASCII && !((P.second_mask >> T.sym(start + 1)) & 1u));
+                            push = !(start + 1 >= text_end || (T.byte(start + 1) != SUCC_NONASCII && !((P.second_mask >> T.sym(start + 1)) & 1u)));
                     }
-                    if (!skip) {
-                        if (lane == 0) stk[top] = make_uint4(0u, 0u, 0u, w << 20);
-                        top++;
-                        fed = true;
-                    }
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, push);
+                    if (push) stk[top + __popc(bal & succ_lanemask_lt())] = make_uint4(0u, 0u, 0u, w << 20);
+                    top += __popc(bal);
+                    fed = bal != 0u;
                     continue;
                 }
                 if (top == 0) {
                     if (!more && wn == 0) break;
-                    fed = false;   // nothing to pop: allow the next feed (or fall into the final drain)
-                    if (!more) continue;
+                    fed = false;   // nothing to pop: feed again, or fall into the final walk drain
                     continue;
                 }
                 // (4) pop up to 32 states
