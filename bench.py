@@ -31,7 +31,7 @@ DEFAULT_BYTES = int(os.environ.get("FAC_BENCH_BYTES", 128 << 20))  # haystack by
 DEFAULT_PATTERNS = int(os.environ.get("FAC_BENCH_PATTERNS", 10000))
 THRESHOLD = 0.8
 # dram bytes of one k_expand_succinct launch from the ncu --set full capture under profiles/ (None until measured)
-TRAFFIC_NOTE = 407134208  # profiles/r1_k_expand_succinct_raw_selected.txt: 68.5 MB read + 338.6 MB written (raw candidates, ~0.37 per start window) per 2^25-window launch
+TRAFFIC_NOTE = 404099584  # profiles/r1_k_expand_succinct_raw_selected.txt: 65.5 MB read + 338.6 MB written (raw candidates, ~0.37 per start window) per 2^25-window launch
 METRIC = "haystack GB/s (fuzzy, edits=2)"
 
 
