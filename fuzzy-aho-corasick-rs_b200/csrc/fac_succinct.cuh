@@ -1,18 +1,21 @@
 // fac_succinct.cuh -- K3 fast kernel: fuzzy frontier expansion over the succinct BFS-ordered trie.
 //
-// search_unsorted_impl<MAPPINGS=false, WINDOW_SKIP, MAX_EDITS_FAST=1..6> (src/search.rs:418-1119)
-// for ASCII haystacks and single-byte pattern alphabets of at most 31 symbols.  Per-state logic is
-// in fac_succinct.h (shared with the CPU emulator); this file is the SIMT orchestration:
+// search_unsorted_impl (src/search.rs:418-1119) for engines without mappings whose trie edges are single ASCII
+// bytes over at most 63 symbols: the fast monomorphisations <MAPPINGS=false, _, MAX_EDITS_FAST=1..6>, the generic
+// MAX_EDITS_FAST=255 path with per-pattern / per-type limits (template LIM) and engines without limits
+// (exact-only).  Haystacks are ASCII bytes or the K1 stream of folded first chars.  Per-state logic is in
+// fac_succinct.h (shared with the CPU emulator); this file is the SIMT orchestration:
 //
 //   * one persistent CTA per SM, tiles of start windows fetched with one atomicAdd per tile;
-//   * the tile's haystack bytes (+ look-ahead) staged into shared memory by one TMA bulk copy,
+//   * the tile's haystack elements (+ look-ahead) staged into shared memory by one TMA bulk copy,
 //     then case-folded and translated to dense symbols in place;
 //   * the first `n_smem_nodes` node records (BFS order == shallow levels first, where most visits
-//     land) copied to shared memory once per CTA; deeper records come through L1/L2 as 128-bit loads;
-//   * each warp owns one start window at a time and runs a depth-first stack machine in shared
-//     memory: pop <= 32 states (one per lane), push exact/swap/insertion children by ballot/popc
+//     land) copied to shared memory once per CTA; deeper records are 128-bit loads that hit L2;
+//   * each warp runs ONE depth-first stack machine in shared memory over a stream of start windows
+//     (a state carries its window; the next root is fed when fewer than 32 states are left):
+//     pop <= 32 states (one per lane), push exact/swap/insertion children by ballot/popc
 //     compaction; the children that survive the last-edit dead-end filter are read off the
-//     precomputed grandchild masks (two 4-byte loads per state instead of one record per child),
+//     precomputed grandchild masks (two loads per state instead of one record per child),
 //     flattened over the warp with a prefix sum and turned into child states 32 per round;
 //   * children that exhausted the edit budget can only follow exact transitions: they are queued in
 //     a per-warp shared-memory walk queue and walked 32 at a time, so the divergent chain walk runs
@@ -29,7 +32,7 @@
 struct SuccParams {
     const uint4 *rec;        // [n_nodes] per-call node records (SuccRec)
     const uint4 *out2;       // SuccOut entries
-    const float *sub_pen;    // [32][SUCC_SP_STRIDE]
+    const float *sub_pen;    // [ROW][SUCC_SP_STRIDE]
     const uint8_t *sym_of;   // [256]
     const uint8_t *text;     // ASCII haystack bytes, or
     const uint32_t *first;   // non-ASCII haystack: first char of every folded grapheme (K1 stream); null for ASCII
@@ -45,11 +48,11 @@ struct SuccParams {
     const void *gm2;         // [gm2_nodes * ROW * ROW] two-deep masks
     uint32_t gm2_nodes;
     uint32_t stack_cap;      // states per warp stack
-    uint32_t text_cap;       // bytes of the shared text tile (multiple of 16)
+    uint32_t text_cap;       // elements of the shared text tile (multiple of 16)
     FacCand *cands;
     uint32_t cand_cap;
     unsigned long long *counters;  // [0] next tile, [1] candidates, [2] states visited, [7] overflowed windows
-    uint32_t *dirty;         // bitmap over start windows (bit sg - seg_begin): set when a window's stack overflowed
+    uint32_t *dirty;         // bitmap over start windows (bit sg - seg_begin): set when a state of the window did not fit the stack
 };
 
 // per-call records: ceiling = prune_len - prune_low * thr (search.rs:638-642), exact f32 ops.
