@@ -1214,7 +1214,7 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
     E->succ_generic_ok = H.succ.ok && (H.succ.exact_only || H.succ.limits_mode) && H.beam_width == 0 && !H.has_auto_beam && env_int("FAC_FAITHFUL", 0) == 0 &&
                     env_int("FAC_SUCCINCT", 1) != 0;
     E->succ_nt = (uint32_t)env_int("FAC_SUCC_THREADS", 1024);
-    E->succ_tile = (uint32_t)std::max(32, env_int("FAC_SUCC_TILE", 1024));
+    E->succ_tile = (uint32_t)std::min(4096, std::max(32, env_int("FAC_SUCC_TILE", 1024)));  // 12-bit window field of a state
     E->succ_stack = (uint32_t)env_int("FAC_SUCC_STACK", 0);
     *out = E;
     return FAC_OK;

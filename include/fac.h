@@ -195,8 +195,11 @@ fac_status fac_search_windows(const fac_engine *engine, const fac_window *window
 
 const fac_match *fac_matches_data(const fac_matches *m);
 size_t fac_matches_len(const fac_matches *m);
-/* Sum over start windows of the reference's `queue.len()` (src/search.rs:1099): the number
- * of search states pushed.  Used for the states/s figure. */
+/* Number of search states of the call.  On the order-faithful kernels (engines with a beam,
+ * mappings, ... or FAC_FAITHFUL=1) this is exactly the sum over start windows of the
+ * reference's `queue.len()` (src/search.rs:1099); on the fast kernel it is the number of states
+ * that kernel visited, which is smaller (it skips children that cannot emit).  A statistic for
+ * the states/s figure, never part of the result. */
 uint64_t fac_matches_states_pushed(const fac_matches *m);
 /* Device time (ms, CUDA events on the library's stream) of the whole call and of the
  * frontier-expansion kernel launches inside it, and the number of kernel launches. */
