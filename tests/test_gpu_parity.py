@@ -13,6 +13,9 @@ from fuzzgen import rand_case, rand_dense_case
 
 pytestmark = pytest.mark.gpu
 
+# FAC_TEST_SEED shifts the seeds of the randomized differentials so that extra GPU runs cover fresh cases
+SEED = int(__import__("os").environ.get("FAC_TEST_SEED", "0"))
+
 ALL_OPTS = [(o, v) for o in (Order.Unsorted, Order.Default, Order.Greedy, Order.CoverageWeighted)
             for v in (Overlap.Keep, Overlap.NonOverlapping, Overlap.NonOverlappingUnique)]
 
@@ -37,12 +40,12 @@ def _fuzz(oracle, gpu, seed, unicode_, trials, faithful, monkeypatch):
 
 @pytest.mark.parametrize("faithful", [True, False])
 def test_fuzz_ascii(oracle, gpu, faithful, monkeypatch):
-    _fuzz(oracle, gpu, 11, False, 400, faithful, monkeypatch)
+    _fuzz(oracle, gpu, 11 + SEED, False, 400, faithful, monkeypatch)
 
 
 @pytest.mark.parametrize("faithful", [True, False])
 def test_fuzz_unicode(oracle, gpu, faithful, monkeypatch):
-    _fuzz(oracle, gpu, 12, True, 400, faithful, monkeypatch)
+    _fuzz(oracle, gpu, 12 + SEED, True, 400, faithful, monkeypatch)
 
 
 def test_fast_kernel_on_non_ascii_haystack(oracle, gpu, monkeypatch):
@@ -135,8 +138,8 @@ def test_exact_engine_fast_path(oracle, gpu, monkeypatch):
 def test_fast_kernel_dense_tries(oracle, gpu, monkeypatch):
     # dense random tries over small alphabets: survivor masks, two-deep masks, walk queue, ties, many outputs
     monkeypatch.setenv("FAC_FAITHFUL", "0")
-    r1, r2 = random.Random(77), random.Random(77)
-    ropt = random.Random(78)
+    r1, r2 = random.Random(77 + SEED), random.Random(77 + SEED)
+    ropt = random.Random(78 + SEED)
     for t in range(60):
         eo, hay, thr, desc = rand_dense_case(r1, oracle)
         eg, _, _, _ = rand_dense_case(r2, gpu)
@@ -149,7 +152,7 @@ def test_fast_kernel_dense_tries(oracle, gpu, monkeypatch):
 def test_fast_kernel_tie_redo(oracle, gpu, monkeypatch):
     # patterns / texts built to tie: sub(sim 0) == ins + del == del + swap at default penalties
     monkeypatch.setenv("FAC_FAITHFUL", "0")
-    r = random.Random(99)
+    r = random.Random(99 + SEED)
     letters = "ab"
     for t in range(300):
         pats = ["".join(r.choice(letters) for _ in range(r.randrange(3, 7))) for _ in range(r.randrange(1, 5))]
@@ -299,8 +302,8 @@ def test_succinct_other_edit_budgets(oracle, gpu, edits, monkeypatch):
 
 def test_prefilter_fuzz_ascii(oracle, gpu, monkeypatch):
     # Prefiltered::search (prefilter.rs:135): GPU bitap scan + slices vs the oracle's restatement
-    r1, r2 = random.Random(41), random.Random(41)
-    ropt = random.Random(48)
+    r1, r2 = random.Random(41 + SEED), random.Random(41 + SEED)
+    ropt = random.Random(48 + SEED)
     used = 0
     for t in range(400):
         eo, hay, thr, desc = rand_case(r1, oracle, False)
