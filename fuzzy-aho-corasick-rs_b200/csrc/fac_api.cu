@@ -207,7 +207,7 @@ struct fac_engine {
     const uint8_t *d_s_symof = nullptr;
     const void *d_s_gm = nullptr, *d_s_gm2 = nullptr;
     const uint32_t *d_s_node_lim = nullptr;
-    uint32_t succ_nt = 1024, succ_tile = 1024, succ_stack = 0;
+    uint32_t succ_nt = 1024, succ_tile = 4096, succ_stack = 0;
     int smem_optin = 0;
     bool fast_ok = false;  // FAST kernel allowed (fast-path edit ceiling, no beam); FAC_FAITHFUL=1 forces the order-faithful kernel
     mutable std::mutex mu;
@@ -1214,7 +1214,7 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
     E->succ_generic_ok = H.succ.ok && (H.succ.exact_only || H.succ.limits_mode) && H.beam_width == 0 && !H.has_auto_beam && env_int("FAC_FAITHFUL", 0) == 0 &&
                     env_int("FAC_SUCCINCT", 1) != 0;
     E->succ_nt = (uint32_t)env_int("FAC_SUCC_THREADS", 1024);
-    E->succ_tile = (uint32_t)std::min(4096, std::max(32, env_int("FAC_SUCC_TILE", 1024)));  // 12-bit window field of a state
+    E->succ_tile = (uint32_t)std::min(4096, std::max(32, env_int("FAC_SUCC_TILE", 4096)));  // 12-bit window field of a state
     E->succ_stack = (uint32_t)env_int("FAC_SUCC_STACK", 0);
     *out = E;
     return FAC_OK;
