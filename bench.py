@@ -88,6 +88,7 @@ def make_shard(rank, nbytes, npat):
 
 
 def cpu_arm(args, cfg, cores, seconds_target=20.0):
+    seconds_target = float(os.environ.get("FAC_BENCH_CPU_SECONDS", seconds_target))  # tests shorten the sample
     """The reference's algorithm on the host cores: C++ restatement (oracle), all cores, bounded sample."""
     from oracle_backend import OracleBackend
     from fac_b200 import workload
