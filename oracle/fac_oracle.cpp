@@ -9,7 +9,7 @@
 //
 // The reference is Rust and cannot be compiled in this image (no cargo/rustc), so the
 // oracle is pinned by the reference's own known-answer tests (src/tests.rs, doc examples),
-// transcribed in tests/test_oracle_kat.py.  Items that no reference test pins are called
+// transcribed in tests/test_reference_kat.py and tests/test_oracle_pins.py.  Items that no reference test pins are called
 // out below as "parity unpinned" and listed in DESIGN.md:
 //   (U1) edge order of a node = first-insertion order here; the reference uses hashbrown
 //        iteration order under its FxHasher (src/builder.rs:331-342).
