@@ -89,6 +89,10 @@ def test_sharded_search_world2_gloo():
     _run(2, "oracle")
 
 
+def test_sharded_search_world3_gloo():
+    _run(3, "oracle")   # uneven cuts
+
+
 @pytest.mark.gpu
 def test_sharded_search_world2_nccl_single_device():
     # two ranks over NCCL; with one visible GPU both ranks share it (NCCL refuses that), so this needs >= 2 GPUs

@@ -67,6 +67,32 @@ def main():
     with open(os.path.join(out_dir, "unicode_mappings.json"), "w") as f:
         json.dump(doc, f, ensure_ascii=True, separators=(",", ":"))
     print("unicode_mappings", {k: len(v) for k, v in doc["results"].items()})
+    fast_domain_cases(ob, out_dir)
+
+
+def fast_domain_cases(ob, out_dir):
+    """Engines inside the fast kernel's extended domain: wide alphabet (> 31 symbols), per-pattern limits, no limits
+    at all, and a non-ASCII haystack under an ASCII-alphabet engine."""
+    import random
+    from fac_b200 import Pattern
+    r = random.Random(4242)
+    alpha = "abcdefghijklmnopqrstuvwxyz0123456789-_ ."
+    pats = sorted({"".join(r.choice(alpha) for _ in range(r.randrange(3, 9))) for _ in range(150)})
+    hay = "".join(r.choice(alpha) if r.random() > 0.1 else r.choice(pats) for _ in range(900))
+    hay_u = "".join(ch + ("\u00e9" if i % 37 == 5 else "\r\n" if i % 53 == 7 else "") for i, ch in enumerate(hay[:500]))
+    kinds = [FuzzyLimits.new().edits(1), FuzzyLimits.new().edits(2).swaps(0), FuzzyLimits.new().substitutions(1).deletions(1)]
+    engines = {
+        "wide_edits2": FuzzyAhoCorasickBuilder.new(ob).fuzzy(FuzzyLimits.new().edits(2)).build(pats),
+        "wide_pattern_limits": FuzzyAhoCorasickBuilder.new(ob).build([Pattern.from_(p).fuzzy(kinds[i % 3]) for i, p in enumerate(pats)]),
+        "wide_no_limits": FuzzyAhoCorasickBuilder.new(ob).build(pats),
+    }
+    doc = {"patterns": pats, "hay": hay, "hay_unicode": hay_u, "threshold": 0.7, "results": {}}
+    for name, eng in engines.items():
+        for hname, h in (("ascii", hay), ("unicode", hay_u)):
+            doc["results"][name + "/" + hname] = tuples(eng.search(h, SearchOptions.new().threshold(0.7)))
+    with open(os.path.join(out_dir, "fast_domain.json"), "w") as f:
+        json.dump(doc, f, ensure_ascii=True, separators=(",", ":"))
+    print("fast_domain", {k: len(v) for k, v in doc["results"].items()})
 
 
 if __name__ == "__main__":
