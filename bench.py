@@ -1,21 +1,30 @@
 #!/usr/bin/env python3
 """bench.py -- haystack GB/s of the fuzzy search path (BASELINE.json metric) on N B200s of one node.
 
-A step is ONE pass of the hot path (`engine.search(hay, &SearchOptions)` through the C ABI) over one
-synthetic haystack shard per GPU: cfg2 of BASELINE.json -- 10k ASCII patterns, edits(2), default
-penalties, threshold 0.8, English-like text with planted fuzzy hits (fac_b200/workload.py).  The
-haystack shards naturally: every rank searches its own shard (+halo) with no data-path
-collective; the only exchange is the final gather of the match counts / lists.
+Headline workload (`--config cfg2`, the configuration BASELINE.json's metric is quoted on): ONE 1 GiB synthetic
+haystack, 10k ASCII patterns, edits(2), default penalties, threshold 0.8, Order::Unsorted / Overlap::Keep
+(fac_b200/workload.py, seed 0xFAC00002).  A step is one `engine.search(hay, &SearchOptions)` over that haystack:
 
-  value : whole-job throughput, shards already resident in HBM when the timed region starts
-  e2e   : same metric through fac_search() on HOST (pinned) buffers -- H2D of the shard and D2H of
-          the match list inside the timed region
-  roofline / cpu_baseline : see DESIGN.md ("Measurement")
+  N = 1   one call over the whole haystack;
+  N > 1   STRONG scaling: the haystack is cut by fac_plan_shards into N shards (+ right halo); rank g searches its
+          shard with fac_search_ex (match list ranked locally, kept in device memory), the lists are gathered to
+          rank 0 over NCCL (all_gather of the counts + point-to-point sends of exactly count * 32 bytes into rank 0's
+          device buffer) and rank 0 finishes with the global fac_matches_apply_device -- all inside the timed region.
 
-  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
-  python bench.py --impl reference ...                     (CPU arm: the C++ restatement of the reference)
+  value : haystack bytes / step time, haystack (shards) resident in HBM when the timed region starts and the final
+          list resident in rank 0's HBM when it ends
+  e2e   : same step from HOST buffers: every rank copies its shard H2D from pinned memory, rank 0 copies the final
+          list D2H (both inside the timed region); `e2e_pageable` repeats it from ordinary (pageable) host memory
+  roofline / cpu_baseline : DESIGN.md "Measurement"
+
+On step 0 (untimed) the result is verified: N > 1: the gathered sharded result equals rank 0's own whole-haystack
+search byte for byte; every N: sampled regions (incl. the shard cuts) equal the CPU oracle (tests/ infrastructure).
+
+  python bench.py --gpus N --steps K --warmup W [--config cfg1|cfg2|cfg3|cfg4|cfg5]   (N>1: launched by torchrun)
+  python bench.py --impl reference ...       (CPU arm: the C++ restatement of the reference on all host cores)
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -27,12 +36,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "fuzzy-aho-corasick-rs_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-DEFAULT_BYTES = int(os.environ.get("FAC_BENCH_BYTES", 128 << 20))  # haystack bytes per GPU per step
-DEFAULT_PATTERNS = int(os.environ.get("FAC_BENCH_PATTERNS", 10000))
-THRESHOLD = 0.8
-# dram bytes of one k_expand_succinct launch from the ncu --set full capture under profiles/ (None until measured)
-TRAFFIC_NOTE = 404099584  # profiles/r1_k_expand_succinct_raw_selected.txt: 65.5 MB read + 338.6 MB written (raw candidates, ~0.37 per start window) per 2^25-window launch
 METRIC = "haystack GB/s (fuzzy, edits=2)"
+# dram bytes of one k_expand_succinct launch from the ncu --set full capture under profiles/ (per 2^25-window launch)
+TRAFFIC_NOTE = 404099584
 
 
 def peaks():
@@ -76,32 +82,86 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
 
 
-def make_shard(rank, nbytes, npat):
+# ---------------------------------------------------------------------------------------------------------------
+# workloads: BASELINE.json configs.  Each returns the engine recipe and a generator for a byte range of the haystack.
+# ---------------------------------------------------------------------------------------------------------------
+CONFIG_BYTES = {"cfg1": 64 << 20, "cfg2": 1 << 30, "cfg3": 256 << 20, "cfg4": 4_000_000_000, "cfg5": 16 << 30}
+
+
+def config_text(name, args, a, b, procs):
+    """Bytes [a, b) of the config's haystack + the engine recipe (patterns, limits ...)."""
     from fac_b200 import workload
-    cfg = workload.cfg2(nbytes, npat, seed=0xFAC00002)
-    if rank:  # same patterns, a different text stream per rank (weak scaling: per-GPU work is fixed)
-        import numpy as np
-        vocab = workload.make_vocab(0xFAC00002)
-        text = workload.make_text(0xFAC00002 + 7919 * rank, nbytes, vocab)
-        cfg["text"] = workload.plant(text, [p.encode() for p in cfg["patterns"]], 0xFAC00002 + rank)
-    return cfg
+    total = args.bytes
+    if name == "cfg2":
+        return workload.cfg2(total, args.patterns, procs=procs, text_range=(a, b))
+    if name == "cfg1":
+        cfg = workload.cfg1(min(b, total))   # a prefix of the stream is the same text (workload.make_text)
+        cfg["text"] = cfg["text"][a:b]
+        return cfg
+    raise SystemExit("unknown config " + name)
 
 
-def cpu_arm(args, cfg, cores, seconds_target=20.0):
+def describe(name, args):
+    if name == "cfg2":
+        return ("cfg2: %d ASCII patterns (len 5-16), FuzzyLimits edits(2), default penalties, threshold 0.8, Order::Unsorted / "
+                "Overlap::Keep, ONE synthetic English-like haystack with planted fuzzy hits (seed 0xFAC00002)" % args.patterns)
+    if name == "cfg1":
+        return ("cfg1: 100 ASCII patterns, FuzzyLimits edits(1), case-insensitive, threshold 0.8, Order::Unsorted / Overlap::Keep, "
+                "mixed-case synthetic English-like text (seed 0xFAC00001)")
+    return name
+
+
+def workload_config(args, world, extra=None):
+    c = {"workload": describe(args.config, args), "config": args.config, "haystack_bytes_total": int(args.bytes),
+         "haystack_bytes_per_gpu": int(args.bytes // max(world, 1)), "patterns": args.patterns, "threshold": args.threshold,
+         "sharding": ("one fac_search call over the whole haystack" if world == 1 else
+                      "strong scaling: fac_plan_shards cuts the haystack into %d shards + halo; fac_search_ex per rank, match lists "
+                      "gathered to rank 0 over NCCL (exact-size send/recv of device-resident records), global "
+                      "fac_matches_apply_device on rank 0, all inside the timed region" % world),
+         "cache": "the haystack shard (>= 128 MiB) plus the candidate / reduction buffers written every step (> 1 GB per GPU) "
+                  "exceed the 126 MB L2: inputs larger than L2, no explicit flush"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (C++ restatement, oracle/) on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_arm(cfg, cores, seconds_target):
+    """Calibrate on a small slice and size a prefix sample for ~seconds_target of wall time on all cores.
+    orc_search_parallel cuts the sample into one contiguous shard of start positions per thread (+ halo) -- the
+    same decomposition the GPU ranks use."""
     seconds_target = float(os.environ.get("FAC_BENCH_CPU_SECONDS", seconds_target))  # tests shorten the sample
-    """The reference's algorithm on the host cores: C++ restatement (oracle), all cores, bounded sample."""
     from oracle_backend import OracleBackend
     from fac_b200 import workload
     ob = OracleBackend()
     eng = workload.build_engine(cfg, ob)
     text = cfg["text"]
-    # calibrate on a tiny slice, then size the sample for ~seconds_target of wall time on all cores
     probe = min(len(text), 4096 * cores)
     t0 = time.time()
-    ob.search_parallel(eng._h, text.ctypes.data, probe, THRESHOLD, cores)
+    ob.search_parallel(eng._h, text.ctypes.data, probe, cfg["threshold"], cores)
     rate = probe / max(time.time() - t0, 1e-6)
     sample = int(min(len(text), max(probe, rate * seconds_target)))
     return ob, eng, sample
+
+
+def cpu_baseline_block(cfg, cores, seconds_target=15.0):
+    ob, oeng, sample = cpu_arm(cfg, cores, seconds_target)
+    text = cfg["text"]
+    t2 = time.time()
+    ob.search_parallel(oeng._h, text.ctypes.data, sample, cfg["threshold"], cores)
+    dt = time.time() - t2
+    # mode (i) of SURVEY 8d: single-thread whole-input search, on a smaller prefix (~1/4 of the time budget)
+    one = max(4096, int(sample / cores / 4))
+    t3 = time.time()
+    ob.search_parallel(oeng._h, text.ctypes.data, min(one, len(text)), cfg["threshold"], 1)
+    dt1 = time.time() - t3
+    return {"value": sample / dt / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
+            "single_thread_value": min(one, len(text)) / dt1 / 1e9,
+            "sample": "%d-byte prefix of the haystack on %d threads (one contiguous shard of start positions per thread); single-thread "
+                      "figure on a %d-byte prefix; C++ restatement of the reference (the Rust crate cannot be built in this image)"
+                      % (sample, cores, min(one, len(text)))}
 
 
 def run_reference(args):
@@ -109,34 +169,58 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    cfg = make_shard(0, min(args.bytes, 8 << 20), args.patterns)
-    ob, eng, sample = cpu_arm(args, cfg, cores, seconds_target=15.0)
+    cfg = config_text(args.config, args, 0, min(args.bytes, 8 << 20), 1)
+    ob, eng, sample = cpu_arm(cfg, cores, seconds_target=15.0)
     text = cfg["text"]
     for _ in range(args.warmup):
-        ob.search_parallel(eng._h, text.ctypes.data, min(sample, 4096 * cores), THRESHOLD, cores)
+        ob.search_parallel(eng._h, text.ctypes.data, min(sample, 4096 * cores), cfg["threshold"], cores)
     t0 = time.time()
     for _ in range(args.steps):
-        ob.search_parallel(eng._h, text.ctypes.data, sample, THRESHOLD, cores)
+        ob.search_parallel(eng._h, text.ctypes.data, sample, cfg["threshold"], cores)
     dt = (time.time() - t0) / args.steps
     val = sample / dt / 1e9
+    world = int(os.environ.get("WORLD_SIZE", 1))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, sample),
+            "config": workload_config(args, world, {"sample_bytes_per_step": sample}),
             "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "port",
-                             "sample": "%d-byte prefix of the rank-0 shard per step, %d threads" % (sample, cores)},
+                             "sample": "each step searches a %d-byte prefix of the same haystack on %d threads (one contiguous shard of "
+                                       "start positions per thread); C++ restatement of the reference" % (sample, cores)},
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
     return 0
 
 
-def workload_config(args, nbytes):
-    return {"workload": "cfg2: %d ASCII patterns (len 5-16), FuzzyLimits edits(2), default penalties, threshold 0.8, "
-                        "Order::Unsorted / Overlap::Keep, synthetic English-like haystack with planted fuzzy hits" % args.patterns,
-            "haystack_bytes_per_gpu": int(nbytes), "patterns": args.patterns, "threshold": THRESHOLD,
-            "sharding": "one shard per GPU, no data-path collective; match lists gathered to rank 0",
-            "cache": "haystack shard (128 MiB default) plus the candidate / reduction buffers written every step (> 1 GB) exceed the "
-                     "126 MB L2, so no step finds its input cached"}
+# ---------------------------------------------------------------------------------------------------------------
+# verification helpers (step 0, untimed)
+# ---------------------------------------------------------------------------------------------------------------
+def oracle_sample_check(cfg_small, text, final_np, regions, region_len, halo):
+    """Compare the final list with the CPU oracle on `regions` (start offsets) of `text` (numpy uint8, whole haystack or
+    None-safe slices).  final_np: structured numpy view of the final fac_match list, ascending (start, end, pattern)."""
+    import numpy as np
+    from oracle_backend import OracleBackend
+    from fac_b200 import workload
+    ob = OracleBackend()
+    oeng = workload.build_engine(cfg_small, ob)
+    starts = final_np["start"]
+    checked = 0
+    for p in regions:
+        sl = bytes(text[p:p + region_len + halo])
+        arr, _ = ob.search(oeng._h, sl, cfg_small["threshold"], 0, 0, False)
+        want = sorted((m.start + p, m.end + p, m.pattern_index, C.c_uint32.from_buffer(C.c_float(m.similarity)).value,
+                       m.insertions, m.deletions, m.substitutions, m.swaps) for m in arr if m.start < region_len)
+        lo, hi = np.searchsorted(starts, p, "left"), np.searchsorted(starts, p + region_len, "left")
+        got = sorted((int(r["start"]), int(r["end"]), int(r["pat"]), int(r["simbits"]), int(r["ins"]), int(r["del"]), int(r["sub"]),
+                      int(r["swap"])) for r in final_np[lo:hi])
+        if got != want:
+            raise SystemExit("PARITY FAILURE vs oracle in region [%d, %d): %d GPU records vs %d oracle records" % (p, p + region_len, len(got), len(want)))
+        checked += len(want)
+    return checked
+
+
+MATCH_DTYPE = [("start", "<u8"), ("end", "<u8"), ("pat", "<u4"), ("simbits", "<u4"), ("ins", "u1"), ("del", "u1"), ("sub", "u1"),
+               ("swap", "u1"), ("edits", "u1"), ("pad", "u1", (3,))]
 
 
 def main():
@@ -145,17 +229,28 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--bytes", type=int, default=DEFAULT_BYTES, help="haystack bytes per GPU per step")
-    ap.add_argument("--patterns", type=int, default=DEFAULT_PATTERNS)
+    ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--bytes", type=int, default=0, help="total haystack bytes (default: the size BASELINE.md names for the config)")
+    ap.add_argument("--patterns", type=int, default=int(os.environ.get("FAC_BENCH_PATTERNS", 10000)))
+    ap.add_argument("--threshold", type=float, default=0.8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if not args.bytes:
+        args.bytes = int(os.environ.get("FAC_BENCH_BYTES", CONFIG_BYTES[args.config]))
+    if args.config == "cfg1":
+        args.patterns = 100
     if args.impl == "reference":
         return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+    if args.config in ("cfg3", "cfg4", "cfg5"):
+        import bench_configs
+        return bench_configs.run(args, sys.modules[__name__])
 
+    import numpy as np
     import torch
     import torch.distributed as dist
-    from fac_b200 import GpuBackend, workload
+    from fac_b200 import GpuBackend, _abi, sharding, workload
 
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
@@ -173,64 +268,123 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    thr = args.threshold
+    ORDER, OVERLAP = 0, 0
     gpu = GpuBackend()
-    cfg = make_shard(rank, args.bytes, args.patterns)
-    eng = workload.build_engine(cfg, gpu, device=local)
-    text = cfg["text"]
+    total = args.bytes
+    procs = max(1, min(16, (os.cpu_count() or 1) // max(world, 1)))
+    verify = not args.no_verify
+    # engine first (the shard plan needs max_match_graphemes), then this rank's slice of the haystack
+    recipe = config_text(args.config, args, 0, 0, 1)
+    eng = workload.build_engine(recipe, gpu, device=local)
+    plan = sharding.plan_shards(eng.max_match_graphemes(), None, world, n_bytes=total)
+    own_a, own_b, read_end = plan[rank]
+    whole_text = None
+    if rank == 0 and (world == 1 or verify):
+        whole_text = config_text(args.config, args, 0, total, procs)["text"]   # rank 0 keeps the whole haystack for the step-0 check
+        text = whole_text[own_a:read_end]
+    else:
+        text = config_text(args.config, args, own_a, read_end, procs)["text"]
     n = len(text)
-    host = torch.from_numpy(text).pin_memory()
+    own_len = own_b - own_a
+    host = torch.from_numpy(np.ascontiguousarray(text)).pin_memory()
+    pageable = np.ascontiguousarray(text).copy()
     dev = host.cuda(non_blocking=False)
+    gather_buf = [None]
+    F_DEV, F_RES = _abi.FAC_HAYSTACK_ON_DEVICE, _abi.FAC_RESULT_ON_DEVICE
 
-    def step_resident():
-        arr, st = gpu.search_device(eng._h, dev.data_ptr(), n, THRESHOLD, 0, 0, False)
-        return len(arr), st
-
-    def step_e2e():
-        arr, st = gpu.search_host_ptr(eng._h, host.data_ptr(), n, THRESHOLD, 0, 0, False)
-        return len(arr), st
-
-    def gather_counts(cnt):
-        # the only exchange on the path: the final gather of the per-shard match lists (here their sizes;
-        # bench.py does not need the records on rank 0, tests/test_multi_gpu.py gathers the records)
+    def step(src_ptr, on_device, final_on_device):
+        """One engine.search over the whole haystack.  Returns (final list or None, per-step stats)."""
+        t0 = time.perf_counter()
         if world == 1:
-            return cnt
-        t = torch.tensor([cnt], device="cuda", dtype=torch.int64)
-        out = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(out, t)
-        return int(sum(int(x.item()) for x in out))
+            flags = (F_DEV if on_device else 0) | (F_RES if final_on_device else 0)
+            final, st = gpu.search_ex(eng._h, src_ptr, n, 0, n, 0, thr, ORDER, OVERLAP, flags)
+            t1 = time.perf_counter()
+            st.update(search_ms=(t1 - t0) * 1e3, gather_ms=0.0, apply_ms=0.0, local_matches=len(final))
+            return final, st
+        dm, st = gpu.search_ex(eng._h, src_ptr, n, 0, own_len, own_a, thr, ORDER, 0, (F_DEV if on_device else 0) | F_RES)
+        t1 = time.perf_counter()
+        buf, counts = sharding.gather_records(dm.as_tensor("cuda"), dist, "cuda", out=gather_buf[0])
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        final = None
+        if rank == 0:
+            gather_buf[0] = buf
+            flags = _abi.FAC_APPLY_PRESORTED | (F_RES if final_on_device else 0)
+            final, st2 = gpu.apply_device(eng._h, buf.data_ptr(), sum(counts), ORDER, OVERLAP, flags)
+            st["kernel_launches"] += st2["kernel_launches"]
+        t3 = time.perf_counter()
+        st.update(search_ms=(t1 - t0) * 1e3, gather_ms=(t2 - t1) * 1e3, apply_ms=(t3 - t2) * 1e3, local_matches=len(dm))
+        return final, st
 
-    for _ in range(args.warmup):
-        c, _ = step_resident()
-        gather_counts(c)
+    # ---- step 0 (untimed): verification ----
+    verified = {}
+    final, st0 = step(host.data_ptr(), False, False)       # host flavour: rank 0 gets the final list on the host
+    if verify and rank == 0:
+        final_np = np.frombuffer(final, dtype=MATCH_DTYPE, count=len(final)) if len(final) else np.zeros(0, dtype=MATCH_DTYPE)
+        if world > 1:
+            whole_dev = torch.from_numpy(whole_text).cuda()
+            whole, _ = gpu.search_ex(eng._h, whole_dev.data_ptr(), total, 0, total, 0, thr, ORDER, OVERLAP, F_DEV)
+            same = len(whole) == len(final) and (len(final) == 0 or
+                                                 np.array_equal(np.frombuffer(whole, dtype=np.uint8, count=len(whole) * 32),
+                                                                np.frombuffer(final, dtype=np.uint8, count=len(final) * 32)))
+            if not same:
+                raise SystemExit("PARITY FAILURE: sharded result (%d matches) != whole-haystack search on rank 0 (%d matches)" % (len(final), len(whole)))
+            verified["sharded_equals_whole"] = True
+            del whole, whole_dev
+        rng = np.random.default_rng(12345)
+        region_len, halo = 192, eng.max_match_graphemes() + 3
+        regions = [int(x) for x in rng.integers(0, max(1, total - region_len - halo), 40)]
+        regions += [max(0, c[0] - region_len // 2) for c in plan[1:]] + [0, max(0, total - region_len)]
+        verified["oracle_sample_records"] = oracle_sample_check(recipe, whole_text, final_np, regions, region_len, halo)
+        verified["oracle_sample_regions"] = len(regions)
+        del final_np
+    n_final = len(final) if final is not None else 0
+    del final
+    barrier()
+
+    # ---- resident: W warm-up + K timed steps ----
+    for _ in range(args.warmup - 1):
+        step(dev.data_ptr(), True, True)
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
     t0 = time.perf_counter()
-    dev_ms = expand_ms = 0.0
-    launches = states = 0
-    matches = 0
+    per_step = []
     for _ in range(args.steps):
-        c, st = step_resident()
-        matches = gather_counts(c)
-        dev_ms += st["device_ms"]
-        expand_ms += st["expand_ms"]
-        launches += st["kernel_launches"]
-        states += st["states_pushed"]
+        f, st = step(dev.data_ptr(), True, True)
+        per_step.append(st)
+        del f
+    ev1.record()
     barrier()
     wall = time.perf_counter() - t0
-    my_matches = c
-    # end to end: host buffers, H2D + D2H inside the timed region
-    step_e2e()
+    ev_ms = ev0.elapsed_time(ev1)
+
+    # ---- end to end: pinned host shards in, final list on rank 0's host out ----
+    step(host.data_ptr(), False, False)
     barrier()
     t1 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 2))
     d2h = 0
-    for _ in range(e2e_steps):
-        c2, _ = step_e2e()
-        d2h = c2 * 32
-        gather_counts(c2)
+    e2e_steps = []
+    for _ in range(args.steps):
+        f, st = step(host.data_ptr(), False, False)
+        e2e_steps.append(st)
+        if f is not None:
+            d2h = len(f) * 32
+        del f
     barrier()
     wall_e2e = time.perf_counter() - t1
+    # pageable input: a few steps (the copy runs at a few GB/s)
+    pg_steps = max(1, min(args.steps, 3))
+    barrier()
+    t2 = time.perf_counter()
+    for _ in range(pg_steps):
+        f, _ = step(pageable.ctypes.data, False, False)
+        del f
+    barrier()
+    wall_pg = time.perf_counter() - t2
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -248,44 +402,71 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    ms_step_dev = maxr(dev_ms / args.steps)          # CUDA events on the library's stream, max over ranks
-    ms_step_wall = maxr(wall * 1e3 / args.steps)
-    ms_step = max(ms_step_dev, 1e-9)
-    ms_e2e = maxr(wall_e2e * 1e3 / e2e_steps)
-    total_bytes = sumr(float(n))
-    ms_expand = maxr(expand_ms / args.steps)
-    total_states = sumr(float(states) / args.steps)
-    total_launches = int(sumr(float(launches)))
+    K = args.steps
+    mean = lambda key, rows=per_step: sum(r[key] for r in rows) / len(rows)
+    mine = {"rank": rank, "own_bytes": own_len, "device_ms": mean("device_ms"), "expand_ms": mean("expand_ms"), "search_ms": mean("search_ms"),
+            "gather_ms": mean("gather_ms"), "apply_ms": mean("apply_ms"), "matches": per_step[-1]["local_matches"],
+            "e2e_search_ms": mean("search_ms", e2e_steps), "e2e_gather_ms": mean("gather_ms", e2e_steps), "e2e_apply_d2h_ms": mean("apply_ms", e2e_steps)}
+    per_rank = [mine]
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+    ms_step = maxr(max(ev_ms, wall * 1e3) / K)        # CUDA events on the current stream bracket host-synchronous steps: == wall
+    ms_e2e = maxr(wall_e2e * 1e3 / K)
+    ms_pg = maxr(wall_pg * 1e3 / pg_steps)
+    states = sumr(float(mean("states_pushed")))
+    launches = int(sumr(float(sum(r["kernel_launches"] for r in per_step))))
     clocks = sampler.summary()
 
     if rank == 0:
         peak, which = peaks()
-        # dominant kernel: k_expand.  algorithmic bytes per launch = haystack bytes + 32 B per raw match
-        n_exp_launches = max(1, round((launches / args.steps - 8) / 1))  # informative only
-        alg_bytes = n + 32.0 * my_matches
-        achieved = alg_bytes / (expand_ms / args.steps) / 1e6 if expand_ms > 0 else 0.0
-        line = {"metric": METRIC, "value": total_bytes / ms_step / 1e6, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "wall_ms_per_step": ms_step_wall, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(args, n),
-                "states_per_s": total_states / (ms_expand / 1e3) if ms_expand > 0 else None,
-                "matches_per_step": matches,
-                "e2e": {"value": total_bytes / ms_e2e / 1e6, "unit": "GB/s", "h2d_bytes_per_step": int(n), "d2h_bytes_per_step": int(d2h)},
-                "gpu_launches": total_launches,
+        exp_ms_max = max(r["expand_ms"] for r in per_rank)
+        alg_rank0 = own_len + 32.0 * mine["matches"]
+        alg_total = total + 32.0 * sum(r["matches"] for r in per_rank)
+        achieved = alg_rank0 / mine["expand_ms"] / 1e6 if mine["expand_ms"] > 0 else 0.0
+        achieved_all = alg_total / exp_ms_max / 1e6 if exp_ms_max > 0 else 0.0
+        # the reference counts pushed states (queue.len(), src/search.rs:1099); the fast kernel visits fewer (it never
+        # pushes children that cannot emit).  The ratio is measured on a 1 MiB sample with the order-faithful kernel.
+        ref_states_per_byte = None
+        if not args.no_verify:
+            try:
+                os.environ["FAC_FAITHFUL"] = "1"
+                feng = workload.build_engine(recipe, gpu, device=local)
+                os.environ.pop("FAC_FAITHFUL")
+                sb = min(n, 1 << 20)
+                _, fst = gpu.search_ex(feng._h, dev.data_ptr(), sb, 0, sb, 0, thr, 0, 0, F_DEV | F_RES)
+                ref_states_per_byte = fst["states_pushed"] / sb
+            except Exception as e:  # a statistic, never fatal
+                sys.stderr.write("queue.len() sample failed: %r\n" % (e,))
+                os.environ.pop("FAC_FAITHFUL", None)
+        line = {"metric": METRIC, "value": total / ms_step / 1e6, "unit": "GB/s", "n_gpus": world, "steps": K,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(args, world),
+                "states_per_s": {"visited_by_kernel": states / (exp_ms_max / 1e3) if exp_ms_max > 0 else None,
+                                 "reference_queue_len_equivalent": (ref_states_per_byte * total / (exp_ms_max / 1e3)) if ref_states_per_byte else None,
+                                 "reference_queue_len_per_byte": ref_states_per_byte,
+                                 "note": "visited = states the fast kernel popped or walked; reference equivalent = the reference's pushed-state "
+                                         "count (sum of queue.len(), measured by the order-faithful kernel on a 1 MiB sample) per second of "
+                                         "k_expand time"},
+                "matches_per_step": n_final,
+                "e2e": {"value": total / ms_e2e / 1e6, "unit": "GB/s", "h2d_bytes_per_step": int(sum(r["own_bytes"] for r in per_rank) + sum(p[2] - p[1] for p in plan)),
+                        "d2h_bytes_per_step": int(d2h), "steps": K, "input": "pinned host memory"},
+                "e2e_pageable": {"value": total / ms_pg / 1e6, "unit": "GB/s", "steps": pg_steps, "input": "pageable host memory"},
+                "gpu_launches": launches,
+                "per_rank": per_rank,
+                "verified": verified,
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": TRAFFIC_NOTE, "peak_source": which, "kernel": "k_expand_succinct",
-                             "note": "algorithmic bytes = haystack bytes + 32 B x raw matches per step, divided by the CUDA-event time of the "
-                                     "k_expand_succinct launches of the step; the kernel is instruction-issue bound (~2400 trie states per "
-                                     "input byte, ncu: IPC 3.1 of 4, DRAM < 0.1 %), see DESIGN.md and profiles/"}}
-        if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            ob, oeng, sample = cpu_arm(args, cfg, cores, seconds_target=15.0)
-            t2 = time.time()
-            ob.search_parallel(oeng._h, text.ctypes.data, sample, THRESHOLD, cores)
-            dt = time.time() - t2
-            line["cpu_baseline"] = {"value": sample / dt / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
-                                    "sample": "%d-byte prefix of the rank-0 shard, %d threads (C++ restatement of the reference)" % (sample, cores)}
+                             "achieved_all_gpus": achieved_all, "frac_of_%dx" % world: achieved_all / (peak * world),
+                             "note": "algorithmic bytes = owned haystack bytes + 32 B x raw matches, divided by the CUDA-event time of the "
+                                     "k_expand_succinct launches of the step (rank 0; all-GPU figure: total bytes / slowest rank); the kernel is "
+                                     "instruction-issue bound (hundreds of trie states per input byte), see DESIGN.md and profiles/"}}
+        if not args.no_cpu_baseline and world == 1:
+            cfg_cpu = dict(recipe)
+            cfg_cpu["text"] = whole_text[: min(total, 8 << 20)]
+            line["cpu_baseline"] = cpu_baseline_block(cfg_cpu, os.cpu_count() or 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

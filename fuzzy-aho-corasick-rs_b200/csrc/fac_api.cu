@@ -175,6 +175,42 @@ struct PinnedAlloc {
 };
 using MatchVec = std::vector<fac_match, PinnedAlloc<fac_match>>;
 
+// Device-resident result lists (FAC_RESULT_ON_DEVICE) are handed to the caller as whole buffers; freed lists go back
+// to a small per-process pool so that a multi-GB list is not cudaMalloc'ed / cudaFree'd on every call.
+struct DevicePool {
+    struct Item { int device; void *p; size_t cap; };
+    std::mutex mu;
+    std::vector<Item> free_;
+    static constexpr size_t kMaxItems = 6;
+    bool get(int device, size_t bytes, DBuf &out) {
+        std::lock_guard<std::mutex> g(mu);
+        size_t best = free_.size();
+        for (size_t i = 0; i < free_.size(); i++)
+            if (free_[i].device == device && free_[i].cap >= bytes && (best == free_.size() || free_[i].cap < free_[best].cap)) best = i;
+        if (best == free_.size()) return false;
+        out.p = free_[best].p; out.cap = free_[best].cap;
+        free_.erase(free_.begin() + best);
+        return true;
+    }
+    void put(int device, DBuf &b) {
+        if (!b.p) return;
+        Item victim{device, b.p, b.cap};
+        b.p = nullptr; b.cap = 0;
+        bool drop = false;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            free_.push_back(victim);
+            if (free_.size() > kMaxItems) {  // drop the smallest
+                size_t k = 0;
+                for (size_t i = 1; i < free_.size(); i++) if (free_[i].cap < free_[k].cap) k = i;
+                victim = free_[k]; free_.erase(free_.begin() + k); drop = true;
+            }
+        }
+        if (drop) { int cur = 0; cudaGetDevice(&cur); cudaSetDevice(victim.device); cudaFree(victim.p); cudaSetDevice(cur); }
+    }
+};
+DevicePool &device_pool() { static DevicePool *p = new DevicePool(); return *p; }
+
 }  // namespace
 
 struct fac_engine {
@@ -207,7 +243,7 @@ struct fac_engine {
     const uint8_t *d_s_symof = nullptr;
     const void *d_s_gm = nullptr, *d_s_gm2 = nullptr;
     const uint32_t *d_s_node_lim = nullptr;
-    uint32_t succ_nt = 1024, succ_tile = 4096, succ_stack = 0;
+    uint32_t succ_nt = 1024, succ_tile = 4096, succ_stack = 0, succ_min_stack = 64;
     int smem_optin = 0;
     bool fast_ok = false;  // FAST kernel allowed (fast-path edit ceiling, no beam); FAC_FAITHFUL=1 forces the order-faithful kernel
     mutable std::mutex mu;
@@ -217,6 +253,12 @@ struct fac_engine {
 struct fac_matches {
     MatchVec v;
     SearchStats stats;
+    // FAC_RESULT_ON_DEVICE: the list stays in device memory (d_out[0..n_dev))
+    bool on_device = false;
+    int device = 0;
+    DBuf d_out;
+    size_t n_dev = 0;
+    ~fac_matches() { if (d_out.p) device_pool().put(device, d_out); }
 };
 
 namespace {
@@ -250,6 +292,14 @@ Workspace *acquire_ws(const fac_engine *E, fac_status &st) {
 void release_ws(const fac_engine *E, Workspace *w) {
     std::lock_guard<std::mutex> g(E->mu);
     E->pool.push_back(w);
+}
+
+inline bool host_is_ascii(const uint8_t *p, size_t n) {
+    size_t i = 0;
+    uint64_t acc = 0;
+    for (; i + 8 <= n; i += 8) { uint64_t v; memcpy(&v, p + i, 8); acc |= v; }
+    for (; i < n; i++) acc |= p[i];
+    return (acc & 0x8080808080808080ull) == 0;
 }
 
 int env_int(const char *name, int dflt) {
@@ -318,7 +368,7 @@ fac_status launch_succinct(const fac_engine *E, Workspace *ws, const TextView &t
     const bool deep = S.limits_mode || E->host.mef > 2;
     const uint32_t nt = deep ? std::min<uint32_t>(E->succ_nt, 512u) : E->succ_nt;
     const uint32_t nw = nt / 32;
-    P.stack_cap = E->succ_stack ? E->succ_stack : (!deep ? 128u : 384u);
+    P.stack_cap = E->succ_stack ? E->succ_stack : std::max(!deep ? 128u : 384u, E->succ_min_stack);
     P.text_cap = (P.tile + P.lookahead + 16u + 15u) & ~15u;
     P.gm = E->d_s_gm; P.gm_nodes = S.gm_nodes; P.gm2 = E->d_s_gm2; P.gm2_nodes = S.gm2_nodes;
     const size_t fixed = (size_t)nw * (P.stack_cap + SUCC_WQ_CAP) * 16 + (S.wide ? 64u : 32u) * SUCC_SP_STRIDE * 4 + (size_t)P.text_cap * (tv.ascii ? 3 : 6) + 256;
@@ -647,14 +697,16 @@ fac_status merge_sort(Workspace *ws, T *d, uint32_t n, Cmp cmp) {
 
 // FuzzyMatches::apply on the device.  In: ws->m_a[0..n) (any order).  Out: ws->m_a[0..*n_out) in final order.
 fac_status apply_device(const fac_engine *E, Workspace *ws, uint32_t n, int order, int overlap, uint32_t n_windows, uint32_t *n_out,
-                        SearchStats &stats) {
+                        SearchStats &stats, bool presorted = false) {
     cudaStream_t s = ws->stream;
     *n_out = n;
     if (n == 0) return FAC_OK;
     WMatch *R = ws->m_a.as<WMatch>();
     RankLess rl{order, E->d_pat_bytes};
-    CKS(merge_sort(ws, R, n, rl));
-    stats.launches += 2;
+    if (!presorted) {
+        CKS(merge_sort(ws, R, n, rl));
+        stats.launches += 2;
+    }
     if (overlap == FAC_OVERLAP_KEEP) return FAC_OK;
     // position order
     CKS(ws->idx_a.ensure((size_t)n * 4));
@@ -730,9 +782,21 @@ fac_status apply_device(const fac_engine *E, Workspace *ws, uint32_t n, int orde
 
 // WMatch list -> fac_match on the host (optionally dropping matches a stream window does not own).
 fac_status finalize_and_fetch(Workspace *ws, uint32_t n, const FacWindow *d_windows, bool filter_commit, MatchVec &out,
-                              SearchStats &stats) {
+                              SearchStats &stats, fac_matches *dev_sink = nullptr) {
     cudaStream_t s = ws->stream;
     if (n == 0) return FAC_OK;
+    if (dev_sink && !filter_commit) {
+        // the finalised list is written straight into a buffer the result handle owns (recycled through the pool)
+        const size_t bytes = (size_t)n * sizeof(fac_match);
+        if (!device_pool().get(dev_sink->device, bytes, dev_sink->d_out)) CKS(dev_sink->d_out.ensure(bytes));
+        CKS(ws->keep8.ensure(n));
+        k_finalize<<<cdiv(n, 256), 256, 0, s>>>(ws->m_a.as<WMatch>(), n, d_windows, dev_sink->d_out.as<fac_match>(), ws->keep8.as<uint8_t>());
+        CK(cudaGetLastError());
+        stats.launches++;
+        dev_sink->n_dev = n; dev_sink->on_device = true;
+        CK(cudaStreamSynchronize(s));
+        return FAC_OK;
+    }
     CKS(ws->outm.ensure((size_t)n * sizeof(fac_match)));
     CKS(ws->keep8.ensure(n));
     k_finalize<<<cdiv(n, 256), 256, 0, s>>>(ws->m_a.as<WMatch>(), n, d_windows, ws->outm.as<fac_match>(), ws->keep8.as<uint8_t>());
@@ -751,6 +815,14 @@ fac_status finalize_and_fetch(Workspace *ws, uint32_t n, const FacWindow *d_wind
         cnt = ws->h_flags[0];
         src = ws->m_b.as<fac_match>();
         stats.launches += 2;
+    }
+    if (dev_sink) {  // filtered list (stream windows): copy the kept records into the handle's buffer
+        const size_t bytes = (size_t)std::max<uint32_t>(cnt, 1) * sizeof(fac_match);
+        if (!device_pool().get(dev_sink->device, bytes, dev_sink->d_out)) CKS(dev_sink->d_out.ensure(bytes));
+        if (cnt) CK(cudaMemcpyAsync(dev_sink->d_out.p, src, (size_t)cnt * sizeof(fac_match), cudaMemcpyDeviceToDevice, s));
+        dev_sink->n_dev = cnt; dev_sink->on_device = true;
+        CK(cudaStreamSynchronize(s));
+        return FAC_OK;
     }
     const size_t old = out.size();
     out.resize(old + cnt);
@@ -964,16 +1036,19 @@ fac_status prefilter_slices(const fac_engine *E, Workspace *ws, const uint8_t *d
 // start windows, reduction, apply.  Restricts start windows to the byte range [own_begin, own_end).
 fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_text, uint64_t len, float thr, int order, int overlap,
                            uint64_t own_begin, uint64_t own_end, uint64_t base, uint64_t commit, bool apply, MatchVec &out, SearchStats &stats,
-                           bool use_prefilter = false) {
+                           bool use_prefilter = false, fac_matches *dev_sink = nullptr, bool force_unicode = false) {
     cudaStream_t s = ws->stream;
     if (len == 0) return FAC_OK;
     CKS(ws->misc.ensure(64));
-    CK(cudaMemsetAsync(ws->misc.p, 0, 4, s));
-    k_scan_bytes<<<(unsigned)std::min<uint64_t>(cdiv(len, 256 * 64), 148 * 8), 256, 0, s>>>(d_text, len, ws->misc.as<uint32_t>());
-    CK(cudaMemcpyAsync(ws->h_flags, ws->misc.p, 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    stats.launches++;
-    const bool ascii = ws->h_flags[0] == 0;
+    bool ascii = false;
+    if (!force_unicode) {
+        CK(cudaMemsetAsync(ws->misc.p, 0, 4, s));
+        k_scan_bytes<<<(unsigned)std::min<uint64_t>(cdiv(len, 256 * 64), 148 * 8), 256, 0, s>>>(d_text, len, ws->misc.as<uint32_t>());
+        CK(cudaMemcpyAsync(ws->h_flags, ws->misc.p, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        stats.launches++;
+        ascii = ws->h_flags[0] == 0;
+    }
     TextView tv;
     memset(&tv, 0, sizeof(tv));
     tv.n_bytes = len; tv.ascii = ascii;
@@ -1014,7 +1089,7 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
         CKS(search_beamed(E, ws, tv, g_begin, g_end, thr, &n_matches, stats));
         uint32_t n_fin = (uint32_t)n_matches;
         if (apply) CKS(apply_device(E, ws, (uint32_t)n_matches, order, overlap, 1, &n_fin, stats));
-        CKS(finalize_and_fetch(ws, n_fin, ws->windows.as<FacWindow>(), commit != ~0ull, out, stats));
+        CKS(finalize_and_fetch(ws, n_fin, ws->windows.as<FacWindow>(), commit != ~0ull, out, stats, dev_sink));
         return FAC_OK;
     }
     // Prefiltered::search (src/prefilter.rs:135-155, 304-374): bitap scan -> merged slices -> the engine on every
@@ -1044,7 +1119,7 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
             }
             uint32_t n_final = (uint32_t)n_matches;
             if (apply) CKS(apply_device(E, ws, (uint32_t)n_matches, order, overlap, 1, &n_final, stats));
-            CKS(finalize_and_fetch(ws, n_final, ws->windows.as<FacWindow>(), commit != ~0ull, out, stats));
+            CKS(finalize_and_fetch(ws, n_final, ws->windows.as<FacWindow>(), commit != ~0ull, out, stats, dev_sink));
             return FAC_OK;
         }
     }
@@ -1078,7 +1153,7 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
     }
     uint32_t n_final = (uint32_t)n_matches;
     if (apply) CKS(apply_device(E, ws, (uint32_t)n_matches, order, overlap, 1, &n_final, stats));
-    CKS(finalize_and_fetch(ws, n_final, ws->windows.as<FacWindow>(), commit != ~0ull, out, stats));
+    CKS(finalize_and_fetch(ws, n_final, ws->windows.as<FacWindow>(), commit != ~0ull, out, stats, dev_sink));
     return FAC_OK;
 }
 
@@ -1091,6 +1166,11 @@ extern "C" {
 
 const char *fac_last_error_string(void) { return g_err.c_str(); }
 int fac_abi_version(void) { return FAC_ABI_VERSION; }
+#ifndef FAC_SOURCE_HASH
+#define FAC_SOURCE_HASH "unstamped"
+#endif
+static const char fac_source_stamp[] = "FAC_SOURCE_STAMP:" FAC_SOURCE_HASH;   // also read straight from the file by build()
+const char *fac_build_source_hash(void) { return fac_source_stamp + 17; }
 uint64_t fac_last_haystack_graphemes(void) { return g_last_graphemes; }
 
 fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pattern *patterns, size_t n_patterns, fac_engine **out) {
@@ -1216,6 +1296,22 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
     E->succ_nt = (uint32_t)env_int("FAC_SUCC_THREADS", 1024);
     E->succ_tile = (uint32_t)std::min(4096, std::max(32, env_int("FAC_SUCC_TILE", 4096)));  // 12-bit window field of a state
     E->succ_stack = (uint32_t)env_int("FAC_SUCC_STACK", 0);
+    if (H.succ.ok) {
+        // a popped state that is not on its last edit reserves 2 * children + 3 stack slots and roots are fed while
+        // fewer than 32 states are stacked: the stack must hold the widest node on top of those 32
+        uint32_t maxdeg = 0;
+        for (uint64_t b : H.succ.bm) maxdeg = std::max<uint32_t>(maxdeg, (uint32_t)__builtin_popcountll(b & 0x7FFFFFFFFFFFFFFFull));
+        E->succ_min_stack = (2 * maxdeg + 3 + 32 + 7) & ~7u;
+    }
+    if (E->succ_nt != 512 && E->succ_nt != 768 && E->succ_nt != 1024) {
+        set_err("FAC_SUCC_THREADS must be 512, 768 or 1024"); fac_engine_free(E); return FAC_INVALID_ARGUMENT;
+    }
+    // memory safety needs room for the 32-root feed on top of < 32 stacked states; below succ_min_stack results stay
+    // exact but windows whose widest state does not fit are redone by the order-faithful kernel (tests use that)
+    if (E->succ_stack != 0 && (E->succ_stack < 40 || E->succ_stack > 4096)) {
+        set_err("FAC_SUCC_STACK must be 0 (automatic) or between 40 and 4096");
+        fac_engine_free(E); return FAC_INVALID_ARGUMENT;
+    }
     *out = E;
     return FAC_OK;
 }
@@ -1239,14 +1335,29 @@ size_t fac_engine_num_patterns(const fac_engine *E) { return E ? E->host.pattern
 int fac_engine_device(const fac_engine *E) { return E ? E->device : -1; }
 
 static fac_status search_common(const fac_engine *E, const uint8_t *hay, size_t len, bool on_device, float thr, int order, int overlap,
-                                int use_prefilter, size_t own_begin, size_t own_end, uint64_t base, bool apply, fac_matches **out) {
+                                int use_prefilter, size_t own_begin, size_t own_end, uint64_t base, bool apply, fac_matches **out,
+                                uint32_t flags = 0) {
     if (!E || !out || (len && !hay)) { set_err("null argument"); return FAC_INVALID_ARGUMENT; }
     *out = nullptr;
+    if (own_end > len) own_end = len;
+    if (own_begin > own_end) { set_err("own_begin lies behind own_end"); return FAC_INVALID_ARGUMENT; }
+    const bool partial = own_begin > 0 || own_end < len;
+    if (partial && E->host.has_auto_beam) {
+        // the auto_beam budget accumulates over ALL start windows of the haystack (src/search.rs:1096-1103): a shard
+        // cannot know where the running total stands, so a sharded call would switch to the beam at other windows
+        set_err("auto_beam engines cannot search a shard of a haystack: the state budget is cumulative over the whole call");
+        return FAC_UNSUPPORTED;
+    }
+    if (partial && overlap != FAC_OVERLAP_KEEP) {
+        set_err("overlap resolution is global: gather the shard lists and call fac_matches_apply[_device]");
+        return FAC_INVALID_ARGUMENT;
+    }
     CK(cudaSetDevice(E->device));
     fac_status st;
     Workspace *ws = acquire_ws(E, st);
     if (!ws) return st;
     fac_matches *M = new fac_matches();
+    M->device = E->device;
     auto body = [&]() -> fac_status {
         CK(cudaEventRecord(ws->ev_begin, ws->stream));
         const uint8_t *d_text = hay;
@@ -1256,7 +1367,9 @@ static fac_status search_common(const fac_engine *E, const uint8_t *hay, size_t 
             CK(cudaMemsetAsync((uint8_t *)ws->hay.p + len, 0, 64, ws->stream));
             d_text = ws->hay.as<uint8_t>();
         }
-        CKS(search_resident(E, ws, d_text, len, thr, order, overlap, own_begin, own_end, base, ~0ull, apply, M->v, M->stats, use_prefilter != 0));
+        CKS(search_resident(E, ws, d_text, len, thr, order, overlap, own_begin, own_end, base, ~0ull, apply, M->v, M->stats, use_prefilter != 0,
+                            (flags & FAC_RESULT_ON_DEVICE) ? M : nullptr, (flags & FAC_TEXT_IS_UNICODE) != 0));
+        if (flags & FAC_RESULT_ON_DEVICE) M->on_device = true;
         CK(cudaEventRecord(ws->ev_end, ws->stream));
         CK(cudaEventSynchronize(ws->ev_end));
         float ms = 0;
@@ -1282,6 +1395,41 @@ fac_status fac_search_device(const fac_engine *E, const uint8_t *d_haystack, siz
 fac_status fac_search_shard(const fac_engine *E, const uint8_t *haystack, size_t len, size_t own_begin, size_t own_end, uint64_t base,
                             float threshold, int on_device, fac_matches **out) {
     return search_common(E, haystack, len, on_device != 0, threshold, FAC_ORDER_UNSORTED, FAC_OVERLAP_KEEP, 0, own_begin, own_end, base, true, out);
+}
+fac_status fac_search_ex(const fac_engine *E, const fac_search_args *a, fac_matches **out) {
+    if (!a) { set_err("null argument"); return FAC_INVALID_ARGUMENT; }
+    if ((unsigned)a->order > FAC_ORDER_COVERAGE_WEIGHTED || (unsigned)a->overlap > FAC_OVERLAP_NON_OVERLAPPING_UNIQUE) {
+        set_err("invalid order / overlap"); return FAC_INVALID_ARGUMENT;
+    }
+    return search_common(E, a->haystack, a->len, (a->flags & FAC_HAYSTACK_ON_DEVICE) != 0, a->threshold, a->order, a->overlap, a->use_prefilter,
+                         a->own_begin, a->own_end, a->base, true, out, a->flags);
+}
+
+// Shard plan: cuts on extended-grapheme-cluster boundaries of the WHOLE haystack (a cut inside a cluster would give
+// the next shard a start window the whole-haystack search never has), halo counted in clusters.
+fac_status fac_plan_shards(size_t max_match_graphemes, const uint8_t *hay, size_t len, size_t n_shards, fac_shard *out) {
+    if (!out || n_shards == 0) { set_err("null argument"); return FAC_INVALID_ARGUMENT; }
+    const size_t halo = max_match_graphemes + 3;
+    const bool ascii = hay == nullptr || host_is_ascii(hay, len);
+    const UnicodeTables &U = fac::host_unicode_tables();
+    auto snap = [&](size_t c) -> size_t {  // first cluster boundary at or after c
+        if (ascii || c >= len) return std::min(c, len);
+        while (c < len && (fac_is_cont(hay[c]) || !fac_break_before(U, hay, 0, c))) c++;
+        return c;
+    };
+    auto advance = [&](size_t c, size_t clusters) -> size_t {  // `clusters` boundaries further right
+        if (ascii) return std::min(len, c + clusters);
+        for (size_t k = 0; k < clusters && c < len; k++) c = snap(c + 1);
+        return c;
+    };
+    size_t prev = 0;
+    for (size_t r = 0; r < n_shards; r++) {
+        size_t end = r + 1 == n_shards ? len : snap((size_t)(((unsigned __int128)len * (r + 1)) / n_shards));
+        if (end < prev) end = prev;
+        out[r].own_begin = prev; out[r].own_end = end; out[r].read_end = advance(end, halo);
+        prev = end;
+    }
+    return FAC_OK;
 }
 
 fac_status fac_matches_apply(const fac_engine *E, const fac_match *in, size_t n, fac_order order, fac_overlap overlap, fac_matches **out) {
@@ -1320,8 +1468,70 @@ fac_status fac_matches_apply(const fac_engine *E, const fac_match *in, size_t n,
     return FAC_OK;
 }
 
-const fac_match *fac_matches_data(const fac_matches *m) { return m && !m->v.empty() ? m->v.data() : nullptr; }
-size_t fac_matches_len(const fac_matches *m) { return m ? m->v.size() : 0; }
+fac_status fac_matches_apply_device(const fac_engine *E, const fac_match *d_in, size_t n, fac_order order, fac_overlap overlap, uint32_t flags,
+                                    fac_matches **out) {
+    if (!E || !out || (n && !d_in)) { set_err("null argument"); return FAC_INVALID_ARGUMENT; }
+    *out = nullptr;
+    if (n > 0xFFFFFFF0ull) { set_err("match list exceeds the 32-bit rank space"); return FAC_UNSUPPORTED; }
+    CK(cudaSetDevice(E->device));
+    fac_status st;
+    Workspace *ws = acquire_ws(E, st);
+    if (!ws) return st;
+    fac_matches *M = new fac_matches();
+    M->device = E->device;
+    const bool to_device = (flags & FAC_RESULT_ON_DEVICE) != 0;
+    auto body = [&]() -> fac_status {
+        cudaStream_t s = ws->stream;
+        CK(cudaEventRecord(ws->ev_begin, s));
+        if (to_device) M->on_device = true;
+        if (n) {
+            if ((flags & FAC_APPLY_PRESORTED) && overlap == FAC_OVERLAP_KEEP) {
+                // nothing to rank or select: the answer is the input list
+                if (to_device) {
+                    const size_t bytes = n * sizeof(fac_match);
+                    if (!device_pool().get(M->device, bytes, M->d_out)) CKS(M->d_out.ensure(bytes));
+                    CK(cudaMemcpyAsync(M->d_out.p, d_in, bytes, cudaMemcpyDeviceToDevice, s));
+                    M->n_dev = n;
+                } else {
+                    M->v.resize(n);
+                    CK(cudaMemcpyAsync(M->v.data(), d_in, n * sizeof(fac_match), cudaMemcpyDeviceToHost, s));
+                }
+            } else {
+                CKS(ws->m_a.ensure(n * sizeof(WMatch)));
+                CKS(ws->misc.ensure(64));
+                CK(cudaMemsetAsync(ws->misc.p, 0, 4, s));
+                k_unfinalize<<<cdiv(n, 256), 256, 0, s>>>(d_in, (uint32_t)n, (uint32_t)E->host.patterns.size(), ws->m_a.as<WMatch>(), ws->misc.as<uint32_t>());
+                CK(cudaGetLastError());
+                FacWindow fw;
+                memset(&fw, 0, sizeof(fw));
+                fw.commit = ~0ull;
+                CKS(ws->windows.ensure(sizeof(FacWindow)));
+                CK(cudaMemcpyAsync(ws->windows.p, &fw, sizeof(fw), cudaMemcpyHostToDevice, s));
+                CK(cudaMemcpyAsync(ws->h_flags, ws->misc.p, 4, cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                if (ws->h_flags[0]) { set_err("pattern index out of range"); return FAC_INVALID_ARGUMENT; }
+                uint32_t kept = 0;
+                CKS(apply_device(E, ws, (uint32_t)n, order, overlap, 1, &kept, M->stats, (flags & FAC_APPLY_PRESORTED) != 0));
+                CKS(finalize_and_fetch(ws, kept, ws->windows.as<FacWindow>(), false, M->v, M->stats, to_device ? M : nullptr));
+            }
+        }
+        CK(cudaEventRecord(ws->ev_end, s));
+        CK(cudaEventSynchronize(ws->ev_end));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ws->ev_begin, ws->ev_end));
+        M->stats.device_ms = ms;
+        return FAC_OK;
+    };
+    st = body();
+    release_ws(E, ws);
+    if (st != FAC_OK) { delete M; return st; }
+    *out = M;
+    return FAC_OK;
+}
+
+const fac_match *fac_matches_data(const fac_matches *m) { return m && !m->on_device && !m->v.empty() ? m->v.data() : nullptr; }
+const fac_match *fac_matches_device_data(const fac_matches *m) { return m && m->on_device && m->n_dev ? m->d_out.as<fac_match>() : nullptr; }
+size_t fac_matches_len(const fac_matches *m) { return m ? (m->on_device ? m->n_dev : m->v.size()) : 0; }
 uint64_t fac_matches_states_pushed(const fac_matches *m) { return m ? m->stats.states : 0; }
 double fac_matches_device_ms(const fac_matches *m) { return m ? m->stats.device_ms : 0; }
 double fac_matches_expand_ms(const fac_matches *m) { return m ? m->stats.expand_ms : 0; }

@@ -260,3 +260,16 @@ __global__ void k_finalize(const WMatch *in, uint32_t n, const FacWindow *window
     out[i] = o;
     keep[i] = m.start < w.commit;
 }
+
+// fac_match (absolute offsets) -> WMatch of a single window with base 0: the inverse of k_finalize, for
+// fac_matches_apply_device.  *bad is set when a pattern index is out of range.
+__global__ void k_unfinalize(const fac_match *in, uint32_t n, uint32_t n_patterns, WMatch *out, uint32_t *bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const fac_match m = in[i];
+    if (m.pattern_index >= n_patterns) atomicOr(bad, 1u);
+    WMatch w;
+    w.start = m.start; w.end = m.end; w.pat = m.pattern_index; w.sim = m.similarity; w.win = 0;
+    w.cnt = (uint32_t)m.insertions | ((uint32_t)m.deletions << 8) | ((uint32_t)m.substitutions << 16) | ((uint32_t)m.swaps << 24);
+    out[i] = w;
+}

@@ -54,6 +54,18 @@ class fac_window(C.Structure):
     _fields_ = [("text", C.c_void_p), ("len", C.c_size_t), ("base", C.c_uint64), ("commit", C.c_size_t)]
 
 
+class fac_shard(C.Structure):
+    _fields_ = [("own_begin", C.c_size_t), ("own_end", C.c_size_t), ("read_end", C.c_size_t)]
+
+
+class fac_search_args(C.Structure):
+    _fields_ = [("haystack", C.c_void_p), ("len", C.c_size_t), ("own_begin", C.c_size_t), ("own_end", C.c_size_t),
+                ("base", C.c_uint64), ("threshold", C.c_float), ("order", C.c_int), ("overlap", C.c_int),
+                ("use_prefilter", C.c_int32), ("flags", C.c_uint32)]
+
+
+FAC_HAYSTACK_ON_DEVICE, FAC_RESULT_ON_DEVICE, FAC_TEXT_IS_UNICODE, FAC_APPLY_PRESORTED = 1, 2, 4, 8
+
 assert C.sizeof(fac_match) == 32
 
 READ_FN = C.CFUNCTYPE(C.c_int64, C.c_void_p, C.POINTER(C.c_uint8), C.c_size_t)
@@ -66,6 +78,7 @@ REPLACE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(fac_match), C.c_uint64, 
 SYMBOLS = [
     ("fac_last_error_string", C.c_char_p, []),
     ("fac_abi_version", C.c_int, []),
+    ("fac_build_source_hash", C.c_char_p, []),
     ("fac_engine_create", C.c_int, [C.POINTER(fac_config), C.POINTER(fac_pattern), C.c_size_t, C.POINTER(C.c_void_p)]),
     ("fac_engine_create_on", C.c_int, [C.c_int, C.POINTER(fac_config), C.POINTER(fac_pattern), C.c_size_t, C.POINTER(C.c_void_p)]),
     ("fac_engine_free", None, [C.c_void_p]),
@@ -79,6 +92,10 @@ SYMBOLS = [
     ("fac_last_haystack_graphemes", C.c_uint64, []),
     ("fac_search_shard", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint64, C.c_float, C.c_int, C.POINTER(C.c_void_p)]),
     ("fac_matches_apply", C.c_int, [C.c_void_p, C.POINTER(fac_match), C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    ("fac_plan_shards", C.c_int, [C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(fac_shard)]),
+    ("fac_search_ex", C.c_int, [C.c_void_p, C.POINTER(fac_search_args), C.POINTER(C.c_void_p)]),
+    ("fac_matches_apply_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]),
+    ("fac_matches_device_data", C.c_void_p, [C.c_void_p]),
     ("fac_search_windows", C.c_int, [C.c_void_p, C.POINTER(fac_window), C.c_size_t, C.c_float, C.POINTER(C.c_void_p)]),
     ("fac_matches_data", C.POINTER(fac_match), [C.c_void_p]),
     ("fac_matches_len", C.c_size_t, [C.c_void_p]),
@@ -93,6 +110,19 @@ SYMBOLS = [
 ]
 
 _lib = None
+CSRC_DIR = os.path.join(os.path.dirname(_HERE), "csrc")
+HEADER = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "fac.h")
+
+
+def source_hash():
+    """SHA-256 over the library's sources (csrc/*.{cu,cuh,h,cpp,inc} + include/fac.h), the stamp build() compiles in."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(f for f in os.listdir(CSRC_DIR) if f.endswith((".cu", ".cuh", ".h", ".cpp", ".inc")))
+    for f in [os.path.join(CSRC_DIR, f) for f in files] + [HEADER]:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
 
 
 def load_library(path=None):
@@ -110,6 +140,11 @@ def load_library(path=None):
         fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
         fn.restype = res
         fn.argtypes = args
+    if path is None and os.path.isdir(CSRC_DIR) and os.environ.get("FAC_ALLOW_STALE_LIB") != "1":
+        built, want = lib.fac_build_source_hash().decode(), source_hash()
+        if built != want:
+            raise RuntimeError("libfacgpu.so was built from other sources (stamp %s..., tree %s...): rebuild with "
+                               "`python __graft_entry__.py`" % (built[:12], want[:12]))
     if path is None:
         _lib = lib
     return lib

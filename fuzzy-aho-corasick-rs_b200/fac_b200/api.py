@@ -391,6 +391,32 @@ class _MatchesOwner:
             pass
 
 
+class DeviceMatches:
+    """A match list that stayed in device memory (FAC_RESULT_ON_DEVICE): `ptr` / `n` describe n fac_match records
+    (32 bytes each) on the engine's device; the buffer lives until this object is collected."""
+
+    def __init__(self, lib, mh):
+        self._owner = _MatchesOwner(lib, mh)
+        self.n = int(lib.fac_matches_len(mh))
+        self.ptr = int(lib.fac_matches_device_data(mh) or 0)
+
+    def __len__(self):
+        return self.n
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.n * 32,), "typestr": "|u1", "data": (self.ptr, False), "version": 3, "strides": None}
+
+    def as_tensor(self, device):
+        """Zero-copy torch uint8 view [n * 32] (keeps this object alive through the tensor)."""
+        import torch
+        if self.n == 0:
+            return torch.empty(0, dtype=torch.uint8, device=device)
+        t = torch.as_tensor(self, device=device)
+        t._fac_owner = self
+        return t
+
+
 class GpuBackend:
     name = "libfacgpu"
 
@@ -477,6 +503,34 @@ class GpuBackend:
         st = self.lib.fac_search_shard(h, p, n, own_begin, own_end, base, thr, int(on_device), C.byref(mh))
         if st != 0:
             raise self._err(st)
+        return self._take(mh)
+
+    def _stats(self, mh):
+        return {"states_pushed": int(self.lib.fac_matches_states_pushed(mh)),
+                "device_ms": float(self.lib.fac_matches_device_ms(mh)),
+                "expand_ms": float(self.lib.fac_matches_expand_ms(mh)),
+                "kernel_launches": int(self.lib.fac_matches_kernel_launches(mh))}
+
+    def search_ex(self, h, ptr, n, own_begin, own_end, base, thr, order, overlap, flags, use_prefilter=False):
+        """fac_search_ex on a raw host / device address.  With FAC_RESULT_ON_DEVICE returns a DeviceMatches."""
+        a = _abi.fac_search_args(C.c_void_p(ptr), n, own_begin, own_end, base, thr, order, overlap, int(use_prefilter), flags)
+        mh = C.c_void_p()
+        st = self.lib.fac_search_ex(h, C.byref(a), C.byref(mh))
+        if st != 0:
+            raise self._err(st)
+        if flags & _abi.FAC_RESULT_ON_DEVICE:
+            return DeviceMatches(self.lib, mh), self._stats(mh)
+        return self._take(mh)
+
+    def apply_device(self, h, dptr, n, order, overlap, flags):
+        """fac_matches_apply_device: device-resident fac_match records in, final list out (host array, or a
+        DeviceMatches with FAC_RESULT_ON_DEVICE)."""
+        mh = C.c_void_p()
+        st = self.lib.fac_matches_apply_device(h, C.c_void_p(dptr), n, order, overlap, flags, C.byref(mh))
+        if st != 0:
+            raise self._err(st)
+        if flags & _abi.FAC_RESULT_ON_DEVICE:
+            return DeviceMatches(self.lib, mh), self._stats(mh)
         return self._take(mh)
 
     def apply(self, h, arr, n, order, overlap):
@@ -694,7 +748,9 @@ class FuzzyAhoCorasickBuilder:
             handle = backend.create(cfg, parr, len(pats), self._device)
         else:
             handle = backend.create(cfg, parr, len(pats))
-        return FuzzyAhoCorasick(backend, handle, pats)
+        eng = FuzzyAhoCorasick(backend, handle, pats)
+        eng._has_auto_beam = self._auto_beam is not None
+        return eng
 
     def build_replacer(self, pairs):
         pairs = list(pairs)

@@ -45,11 +45,12 @@ def vocab_words(vocab):
     return [bytes(arr[i, :lengths[i]]) for i in range(len(lengths))]
 
 
-def make_text(seed, nbytes, vocab, mixed_case=False, chunk_words=1 << 20):
-    """English-like text of exactly `nbytes` bytes (ASCII)."""
+def make_text(seed, nbytes, vocab, mixed_case=False, chunk_words=1 << 20, stream=0):
+    """English-like text of exactly `nbytes` bytes (ASCII).  `stream` selects an independent PCG64 stream of the
+    same seed (block k of a blocked haystack, see cfg2_range)."""
     arr, lengths = vocab
     V = len(lengths)
-    rng = np.random.default_rng([seed, 2])
+    rng = np.random.default_rng([seed, 2] + ([stream] if stream else []))
     p = 1.0 / np.arange(1, V + 1)
     cdf = np.cumsum(p / p.sum())
     out = np.empty(nbytes, dtype=np.uint8)
@@ -106,9 +107,9 @@ def mutate(word, rng, max_edits=2):
     return bytes(w)
 
 
-def plant(text, patterns, seed, every=4096):
+def plant(text, patterns, seed, every=4096, stream=0):
     """Overwrite a mutated pattern roughly every `every` bytes (keeps the length of `text`)."""
-    rng = np.random.default_rng([seed, 3])
+    rng = np.random.default_rng([seed, 3] + ([stream] if stream else []))
     n = len(text)
     pos = every // 2
     while pos + 64 < n:
@@ -140,16 +141,60 @@ def cfg1(nbytes=64 << 20, seed=0xFAC00001):
             "text": text, "name": "cfg1: 100 ASCII patterns, edits(1), ci, thr 0.8"}
 
 
-def cfg2(nbytes=1 << 30, n_patterns=10000, seed=0xFAC00002):
-    """10k ASCII patterns (len 5-16), edits(2), default penalties, threshold 0.8, planted hits every ~4 KiB."""
-    vocab = make_vocab(seed)
+CFG2_BLOCK = 32 << 20   # haystacks larger than this are generated block-wise (independent streams per block)
+
+
+def cfg2_patterns(n_patterns=10000, seed=0xFAC00002, vocab=None):
+    vocab = vocab or make_vocab(seed)
     words = vocab_words(vocab)
     half = n_patterns // 2
     from_vocab = [w for w in words[1000:] if 5 <= len(w) <= 16][:half]
     rnd = random_words(seed, n_patterns - len(from_vocab), 5, 16)
-    pats = from_vocab + rnd
-    text = make_text(seed, nbytes, vocab, mixed_case=False)
-    text = plant(text, pats, seed)
+    return from_vocab + rnd
+
+
+def _cfg2_block(args):
+    seed, k, size, n_patterns = args
+    vocab = make_vocab(seed)
+    pats = cfg2_patterns(n_patterns, seed, vocab)
+    return plant(make_text(seed, size, vocab, mixed_case=False, stream=k), pats, seed, stream=k)
+
+
+def cfg2_range(a, b, total=1 << 30, n_patterns=10000, seed=0xFAC00002, procs=1):
+    """Bytes [a, b) of the cfg2 haystack of `total` bytes.  A haystack of at most CFG2_BLOCK bytes is one
+    make_text + plant stream; a larger one is the concatenation of CFG2_BLOCK-sized blocks, block k drawn from
+    stream k of the same seed (block 0 = the unblocked stream), so that a rank can produce its own shard (+ halo)
+    without generating the whole haystack and blocks can be produced by a process pool."""
+    b = min(b, total)
+    if b <= a:
+        return np.empty(0, dtype=np.uint8)
+    if total <= CFG2_BLOCK:
+        blocks = [(seed, 0, total, n_patterns)]
+    else:
+        blocks = [(seed, k, min(CFG2_BLOCK, total - k * CFG2_BLOCK), n_patterns) for k in range(a // CFG2_BLOCK, (max(b, a + 1) - 1) // CFG2_BLOCK + 1)]
+    if procs > 1 and len(blocks) > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(procs, len(blocks))) as pool:
+            parts = pool.map(_cfg2_block, blocks)
+    else:
+        parts = [_cfg2_block(x) for x in blocks]
+    first = blocks[0][1] * CFG2_BLOCK
+    out = np.empty(b - a, dtype=np.uint8)
+    pos = first
+    for part in parts:
+        lo, hi = max(a, pos), min(b, pos + len(part))
+        if hi > lo:
+            out[lo - a:hi - a] = part[lo - pos:hi - pos]
+        pos += len(part)
+    return out
+
+
+def cfg2(nbytes=1 << 30, n_patterns=10000, seed=0xFAC00002, procs=1, text_range=None):
+    """10k ASCII patterns (len 5-16), edits(2), default penalties, threshold 0.8, planted hits every ~4 KiB.
+    text_range = (a, b): only bytes [a, b) of the nbytes-byte haystack are generated (a rank's shard + halo)."""
+    pats = cfg2_patterns(n_patterns, seed)
+    a, b = text_range if text_range else (0, nbytes)
+    text = cfg2_range(a, b, nbytes, n_patterns, seed, procs)
     return {"patterns": [p.decode() for p in pats], "edits": 2, "case_insensitive": False, "threshold": 0.8,
             "text": text, "name": "cfg2: %d ASCII patterns, edits(2), thr 0.8" % n_patterns}
 

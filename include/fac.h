@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FAC_ABI_VERSION 1
+#define FAC_ABI_VERSION 2
 
 typedef enum fac_status {
     FAC_OK = 0,
@@ -134,6 +134,9 @@ typedef struct fac_matches fac_matches;
 /* Thread-local description of the last failure on this thread ("" if none). */
 const char *fac_last_error_string(void);
 int fac_abi_version(void);
+/* SHA-256 (hex) of the library's source files at build time; the loaders compare it with the sources in the tree
+ * and refuse a stale binary. */
+const char *fac_build_source_hash(void);
 
 /* FuzzyAhoCorasickBuilder::build (src/builder.rs:181-484).  Builds the trie on the host,
  * flattens it and uploads the automaton to CUDA device `device` (fac_engine_create uses
@@ -178,6 +181,58 @@ fac_status fac_search_shard(const fac_engine *engine, const uint8_t *haystack, s
  * shards): sorts + overlap resolution run on the engine's device. */
 fac_status fac_matches_apply(const fac_engine *engine, const fac_match *in, size_t n, fac_order order,
                              fac_overlap overlap, fac_matches **out);
+
+/* ---- multi-GPU sharding of ONE haystack (ownership rule of src/stream.rs:262-297) ---- */
+
+/* Flags of fac_search_args.flags / fac_matches_apply_device. */
+#define FAC_HAYSTACK_ON_DEVICE 1u /* `haystack` is device memory on the engine's device */
+#define FAC_RESULT_ON_DEVICE 2u   /* keep the match list in device memory (fac_matches_device_data); no D2H copy */
+#define FAC_TEXT_IS_UNICODE 4u    /* the slice belongs to a non-ASCII haystack: use the Unicode grapheme storage even
+                                     when the slice itself is ASCII (`\r\n` is one grapheme there, src/search.rs:196,
+                                     src/grapheme.rs:92-98) */
+#define FAC_APPLY_PRESORTED 8u    /* fac_matches_apply_device: the input already is in `order` (e.g. Order::Unsorted
+                                     shard lists concatenated in shard order) */
+
+/* One shard of a haystack: the rank searches haystack[own_begin, read_end) and owns the matches that start in
+ * [own_begin, own_end).  Cuts lie on extended-grapheme-cluster boundaries; read_end - own_end covers
+ * max_match_graphemes() + 3 clusters (the reference's streaming overlap, src/stream.rs:213-258, plus the
+ * look-ahead of the dead-end filter). */
+typedef struct fac_shard {
+    size_t own_begin;
+    size_t own_end;
+    size_t read_end;
+} fac_shard;
+
+/* Cut `haystack` (host memory, valid UTF-8; NULL = the caller guarantees an ASCII haystack of `len` bytes)
+ * into n_shards contiguous shards of about equal byte length.  Pure host function (no device needed):
+ * `max_match_graphemes` is fac_engine_max_match_graphemes() of the engine that will search the shards. */
+fac_status fac_plan_shards(size_t max_match_graphemes, const uint8_t *haystack, size_t len, size_t n_shards,
+                           fac_shard *out);
+
+/* The general search entry point: engine.search / Prefiltered::search restricted to the start positions in
+ * [own_begin, own_end) of `haystack` (own_end > len means len), offsets reported as `base` + slice offset.
+ * `order` is applied to the shard's own list (with overlap == FAC_OVERLAP_KEEP a global ranking is then a merge of
+ * the shard lists; for Order::Unsorted -- ascending (start, end, pattern) -- it is their concatenation); overlap
+ * modes other than KEEP are only meaningful when the owned range is the whole haystack. */
+typedef struct fac_search_args {
+    const uint8_t *haystack;
+    size_t len;
+    size_t own_begin;
+    size_t own_end;
+    uint64_t base;
+    float threshold;
+    fac_order order;
+    fac_overlap overlap;
+    int32_t use_prefilter;
+    uint32_t flags;
+} fac_search_args;
+fac_status fac_search_ex(const fac_engine *engine, const fac_search_args *args, fac_matches **out);
+
+/* FuzzyMatches::apply on a device-resident list of fac_match records (the NCCL-gathered shard lists on rank 0). */
+fac_status fac_matches_apply_device(const fac_engine *engine, const fac_match *d_in, size_t n, fac_order order,
+                                    fac_overlap overlap, uint32_t flags, fac_matches **out);
+/* Device pointer of a list produced with FAC_RESULT_ON_DEVICE (NULL otherwise); valid until fac_matches_free. */
+const fac_match *fac_matches_device_data(const fac_matches *m);
 
 /* One reader-cut streaming window (StreamWindow, src/stream.rs:67-73). */
 typedef struct fac_window {

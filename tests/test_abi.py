@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version(lib):
-    assert lib.fac_abi_version() == 1
+    assert lib.fac_abi_version() == 2
 
 
 def test_struct_layouts():
