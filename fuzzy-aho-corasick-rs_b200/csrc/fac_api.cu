@@ -241,7 +241,8 @@ struct fac_engine {
     const uint32_t *d_s_fc = nullptr, *d_s_out_idx = nullptr, *d_s_out2 = nullptr;
     const float *d_s_plen = nullptr, *d_s_plow = nullptr, *d_s_subpen = nullptr;
     const uint8_t *d_s_symof = nullptr;
-    const void *d_s_gm = nullptr, *d_s_gm2 = nullptr;
+    const void *d_s_masks = nullptr;   // transposed survivor masks (SuccGMDev): gmT then gm2T
+    uint32_t succ_gm2_off = 0;
     const uint32_t *d_s_node_lim = nullptr;
     uint32_t succ_nt = 1024, succ_tile = 4096, succ_stack = 0, succ_min_stack = 64;
     int smem_optin = 0;
@@ -369,9 +370,9 @@ fac_status launch_succinct(const fac_engine *E, Workspace *ws, const TextView &t
     const uint32_t nt = deep ? std::min<uint32_t>(E->succ_nt, 512u) : E->succ_nt;
     const uint32_t nw = nt / 32;
     P.stack_cap = E->succ_stack ? E->succ_stack : std::max(!deep ? 128u : 384u, E->succ_min_stack);
-    P.text_cap = (P.tile + P.lookahead + 16u + 15u) & ~15u;
-    P.gm = E->d_s_gm; P.gm_nodes = S.gm_nodes; P.gm2 = E->d_s_gm2; P.gm2_nodes = S.gm2_nodes;
-    const size_t fixed = (size_t)nw * (P.stack_cap + SUCC_WQ_CAP) * 16 + (S.wide ? 64u : 32u) * SUCC_SP_STRIDE * 4 + (size_t)P.text_cap * (tv.ascii ? 3 : 6) + 256;
+    P.text_cap = (P.tile + P.lookahead + 32u + 15u) & ~15u;   // + alignment lead (< 16) + 3 positions of context look-ahead
+    P.masks = E->d_s_masks; P.gm_nodes = S.gm_nodes; P.gm2_nodes = S.gm2_nodes; P.gm2_off = E->succ_gm2_off;
+    const size_t fixed = (size_t)nw * (P.stack_cap + SUCC_WQ_CAP) * 16 + (S.wide ? 64u : 32u) * SUCC_SP_STRIDE * 4 + (size_t)P.text_cap * (tv.ascii ? 5 : 8) + 256;   // context words + raw tile
     const size_t budget = (size_t)E->smem_optin - 1024;  // static shared + reserve
     if (fixed + 16 * 64 > budget) { set_err("succinct kernel: shared-memory budget too small for the configured stack / tile"); return FAC_UNSUPPORTED; }
     P.n_smem_nodes = (uint32_t)std::min<size_t>(N, (budget - fixed) / 16);
@@ -1245,28 +1246,38 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
         std::vector<uint8_t> symof(S.sym_of, S.sym_of + 256);
         std::vector<uint32_t> fcsym(Nn);
         for (size_t i = 0; i < Nn; i++) fcsym[i] = S.fc[i] | ((uint32_t)S.insym[i] << (S.wide ? 26 : 27));
+        // survivor masks, transposed so that the node index is fastest (SuccGMDev): gmT[y][node], then gm2T[y1][y2][node]
+        const uint32_t ROWS = S.wide ? 64u : 32u, n1 = S.gm_nodes, n2 = S.gm2_nodes;
+        const size_t off2 = (size_t)ROWS * n1, total = off2 + (size_t)ROWS * ROWS * n2;
+        if (total >= 0xFFFFFFFFull) { set_err("survivor-mask tables exceed the 32-bit entry index"); return fail(FAC_UNSUPPORTED); }
+        E->succ_gm2_off = (uint32_t)off2;
+        auto fill_masks = [&](auto *dst) {
+            typedef typename std::remove_pointer<decltype(dst)>::type T;
+            for (uint32_t h = 0; h < n1; h++)
+                for (uint32_t y = 0; y < ROWS; y++) dst[(size_t)y * n1 + h] = (T)S.gmask[(size_t)h * ROWS + y];
+            for (uint32_t h = 0; h < n2; h++)
+                for (uint32_t y1 = 0; y1 < ROWS; y1++)
+                    for (uint32_t y2 = 0; y2 < ROWS; y2++)
+                        dst[off2 + ((size_t)y1 * ROWS + y2) * n2 + h] = (T)S.gmask2[((size_t)h * ROWS + y1) * ROWS + y2];
+        };
         if (S.wide) {
-            std::vector<uint64_t> bm(Nn);
+            std::vector<uint64_t> bm(Nn), masks(std::max<size_t>(total, 1));
             for (size_t i = 0; i < Nn; i++) bm[i] = S.bm[i] | (S.out_idx[i] != FAC_NONE ? 1ull << 63 : 0ull);
+            fill_masks(masks.data());
             const uint64_t *p64;
             if ((st = upload(E, bm, &p64)) != FAC_OK) return fail(st);
             E->d_s_bm = p64;
-            if ((st = upload(E, S.gmask, &p64)) != FAC_OK) return fail(st);
-            E->d_s_gm = p64;
-            if ((st = upload(E, S.gmask2, &p64)) != FAC_OK) return fail(st);
-            E->d_s_gm2 = p64;
+            if ((st = upload(E, masks, &p64)) != FAC_OK) return fail(st);
+            E->d_s_masks = p64;
         } else {
-            std::vector<uint32_t> bm(Nn), gm(S.gmask.size()), gm2(S.gmask2.size());
+            std::vector<uint32_t> bm(Nn), masks(std::max<size_t>(total, 1));
             for (size_t i = 0; i < Nn; i++) bm[i] = (uint32_t)S.bm[i];
-            for (size_t i = 0; i < gm.size(); i++) gm[i] = (uint32_t)S.gmask[i];
-            for (size_t i = 0; i < gm2.size(); i++) gm2[i] = (uint32_t)S.gmask2[i];
+            fill_masks(masks.data());
             const uint32_t *p32;
             if ((st = upload(E, bm, &p32)) != FAC_OK) return fail(st);
             E->d_s_bm = p32;
-            if ((st = upload(E, gm, &p32)) != FAC_OK) return fail(st);
-            E->d_s_gm = p32;
-            if ((st = upload(E, gm2, &p32)) != FAC_OK) return fail(st);
-            E->d_s_gm2 = p32;
+            if ((st = upload(E, masks, &p32)) != FAC_OK) return fail(st);
+            E->d_s_masks = p32;
         }
         if ((st = upload(E, fcsym, &E->d_s_fc)) != FAC_OK) return fail(st);
         if ((st = upload(E, S.out_idx, &E->d_s_out_idx)) != FAC_OK) return fail(st);

@@ -543,7 +543,7 @@ fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_
             };
             {   // grandchild masks: gm[n][y] = symbols s with child(n, s) having edge y; gm[n][NOSYM] = children with an output
                 const char *ev = getenv("FAC_GM_NODES");
-                const size_t lim = ev && *ev ? (size_t)atoll(ev) : 65536;
+                const size_t lim = ev && *ev ? (size_t)atoll(ev) : ((size_t)4 << 20);   // every node of any realistic trie
                 S.gm_nodes = (uint32_t)std::min<size_t>(N, lim);
                 S.gmask.assign((size_t)std::max<uint32_t>(S.gm_nodes, 1) * ROW, 0);
                 for (uint32_t h = 0; h < S.gm_nodes; h++)

@@ -43,10 +43,10 @@ struct SuccParams {
     unsigned long long first_mask, second_mask;
     uint32_t seg_begin, seg_end, text_end, tile, n_tiles, lookahead;
     const uint4 *tiles;      // optional explicit tiles {start, count (<= tile), text_end, window id} (pre-filter slices, stream batches); null = uniform tiling
-    const void *gm;          // [gm_nodes * ROW] grandchild masks (fac_succinct.h): u32 (narrow) or u64 (wide) entries
-    uint32_t gm_nodes;
-    const void *gm2;         // [gm2_nodes * ROW * ROW] two-deep masks
-    uint32_t gm2_nodes;
+    const void *masks;       // survivor masks (SuccGMDev layout): u32 (narrow) or u64 (wide) entries
+    uint32_t gm_nodes;       // nodes covered by the one-deep table
+    uint32_t gm2_nodes;      // nodes covered by the two-deep table
+    uint32_t gm2_off;        // entry offset of the two-deep table inside `masks`
     uint32_t stack_cap;      // states per warp stack
     uint32_t text_cap;       // elements of the shared text tile (multiple of 16)
     FacCand *cands;
@@ -82,43 +82,31 @@ struct SuccRecsDev {
         return r;
     }
 };
+// Survivor-mask tables (fac_succinct.h) in ONE buffer, node index fastest:
+//     gmT[y][node]  (n1 nodes)   followed at `off2` by   gm2T[y1][y2][node]  (the first n2 nodes).
+// Siblings are numbered consecutively and sit next to each other on the warp stack with the same text context, so the
+// lanes of a pop that hold a sibling group read consecutive words (one or two 128-byte lines instead of one per lane).
+// One 4- or 8-byte load per question; the index (32-bit) is selected, the load is shared between the two tables.
 template <bool W>
 struct SuccGMDev {
     typedef typename SuccW<W>::M M;
-    const M *gm;
-    uint32_t gm_nodes;
-    SuccRecsDev R;
-    __device__ __forceinline__ M operator()(uint32_t node, uint32_t y) const {
-        if (node < gm_nodes) return __ldg(&gm[(size_t)node * SuccW<W>::ROW + y]);
-        // beyond the table: recompute the row entry from the children's records
-        const SuccRec r = R(node);
-        M bmv = succ_bm<W>(r), m = 0;
-        uint32_t k = 0;
-        while (bmv) {
-            const uint32_t sy = W ? (uint32_t)(__ffsll((long long)bmv) - 1) : (uint32_t)(__ffs((int)bmv) - 1);
-            bmv &= bmv - 1;
-            const SuccRec c = R(succ_fc<W>(r) + k++);
-            if (y == SuccW<W>::NOSYM ? succ_has_out<W>(c) : succ_has_edge<W>(c, y)) m |= M(1) << sy;
-        }
-        return m;
+    const M *buf;
+    uint32_t n1, n2, off2;
+    __device__ __forceinline__ bool two_deep(uint32_t node) const { return node < n2; }
+    __device__ __forceinline__ M row(uint32_t node, uint32_t y) const {
+        return node < n1 ? __ldg(buf + (y * n1 + node)) : ~M(0);
     }
-};
-template <bool W>
-struct SuccGM2Dev {
-    typedef typename SuccW<W>::M M;
-    const M *gm2;
-    uint32_t gm2_nodes;
-    SuccGMDev<W> G;
-    __device__ __forceinline__ M operator()(uint32_t node, uint32_t y1, uint32_t y2) const {
-        if (node < gm2_nodes) return __ldg(&gm2[((size_t)node * SuccW<W>::ROW + y1) * SuccW<W>::ROW + y2]);
-        return G(node, y1);
+    __device__ __forceinline__ M row2(uint32_t node, uint32_t y1, uint32_t y2) const {
+        const uint32_t idx = node < n2 ? off2 + (y1 * SuccW<W>::ROW + y2) * n2 + node : y1 * n1 + node;
+        return node < n1 ? __ldg(buf + idx) : ~M(0);
     }
 };
 struct SuccTextDev {
-    const uint8_t *sb, *ss;  // folded bytes / symbols of the tile
+    const uint32_t *ctxw;  // text context words of the tile (succ_ctx_pack)
     uint32_t base;
-    __device__ __forceinline__ uint32_t byte(uint32_t j) const { return sb[j - base]; }
-    __device__ __forceinline__ uint32_t sym(uint32_t j) const { return ss[j - base]; }
+    __device__ __forceinline__ uint32_t ctx(uint32_t j) const { return ctxw[j - base]; }
+    __device__ __forceinline__ uint32_t byte(uint32_t j) const { return succ_ctx_byte(ctxw[j - base]); }
+    __device__ __forceinline__ uint32_t sym(uint32_t j) const { return succ_ctx_s0(ctxw[j - base]); }
 };
 struct SuccEmitDev {
     FacCand *cands;
@@ -137,12 +125,6 @@ struct SuccEmitDev {
 
 __device__ __forceinline__ uint32_t succ_lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
-__device__ __forceinline__ void succ_warp_push(uint4 *stk, uint32_t &top, bool p, const FacState &c) {
-    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, p);
-    if (p) stk[top + __popc(bal & succ_lanemask_lt())] = make_uint4(c.node, __float_as_uint(c.pen), c.cnt, c.pos);
-    top += __popc(bal);
-}
-
 #define SUCC_WQ_CAP 96u
 
 // LIM = limits mode: per-pattern / per-type FuzzyLimits evaluated per state (the reference's MAX_EDITS_FAST = 255 path).
@@ -155,17 +137,16 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
     constexpr int NW = NT / 32;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
-    // carve-up: [node records][warp stacks][walk queues][sub_pen][raw tile][folded bytes][symbols][sym_of]
+    // carve-up: [node records][warp stacks][walk queues][sub_pen][text context words][raw tile][sym_of]
     uint4 *s_rec = reinterpret_cast<uint4 *>(dyn_smem);
     uint4 *s_stack = s_rec + P.n_smem_nodes;
     uint4 *s_wq = s_stack + (size_t)NW * P.stack_cap;
     float *s_subpen = reinterpret_cast<float *>(s_wq + (size_t)NW * SUCC_WQ_CAP);
     typedef typename SuccW<W>::M M;
     constexpr uint32_t NOSYM = SuccW<W>::NOSYM;
-    uint8_t *s_raw = reinterpret_cast<uint8_t *>(s_subpen + SuccW<W>::ROW * SUCC_SP_STRIDE);
-    uint8_t *s_byte = s_raw + (size_t)P.text_cap * (P.first ? 4u : 1u);
-    uint8_t *s_sym = s_byte + P.text_cap;
-    uint8_t *s_symof = s_sym + P.text_cap;
+    uint32_t *s_ctx = reinterpret_cast<uint32_t *>(s_subpen + SuccW<W>::ROW * SUCC_SP_STRIDE);
+    uint8_t *s_raw = reinterpret_cast<uint8_t *>(s_ctx + P.text_cap);
+    uint8_t *s_symof = s_raw + (size_t)P.text_cap * (P.first ? 4u : 1u);
 
     for (uint32_t k = tid; k < P.n_smem_nodes; k += NT) s_rec[k] = P.rec[k];
     for (uint32_t k = tid; k < SuccW<W>::ROW * SUCC_SP_STRIDE; k += NT) s_subpen[k] = P.sub_pen[k];
@@ -175,13 +156,13 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
 
     const SuccConsts K = P.K;
     const SuccRecsDev R{s_rec, P.rec, P.n_smem_nodes};
-    const SuccGMDev<W> G{reinterpret_cast<const M *>(P.gm), P.gm_nodes, R};
-    const SuccGM2Dev<W> G2{reinterpret_cast<const M *>(P.gm2), P.gm2_nodes, G};
+    const SuccGMDev<W> G{reinterpret_cast<const M *>(P.masks), P.gm_nodes, P.gm2_nodes, P.gm2_off};
     const SuccOut *out2 = reinterpret_cast<const SuccOut *>(P.out2);
     SuccEmitDev emit{P.cands, P.cand_cap, &P.counters[1], 0u};
     uint4 *const stk = s_stack + (size_t)warp * P.stack_cap;
     uint4 *const wq = s_wq + (size_t)warp * SUCC_WQ_CAP;
     const uint32_t cap = P.stack_cap;
+    const uint32_t lt_mask = succ_lanemask_lt();
     uint32_t mbar_phase = 0;
     uint32_t n_states = 0;  // per-lane count of visited states (summed at the end)
 
@@ -202,7 +183,7 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
         if (lead > tile_start) lead = 0;
         const uint32_t base = tile_start - lead;
         const uint32_t span = count + P.lookahead + lead;                 // positions the tile must answer
-        const uint32_t avail = min(span, text_end - base);                // elements that exist
+        const uint32_t avail = min(span + 3u, text_end - base);           // elements that exist (a context word looks 3 ahead)
         const bool aligned = ((((uintptr_t)(src + (size_t)base * esz)) & 15u) == 0u);
         const uint32_t bulk = aligned ? ((avail * esz) & ~15u) : 0u;      // bytes
         if (bulk && tid == 0) {
@@ -213,23 +194,30 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
         for (uint32_t k = bulk + tid; k < avail * esz; k += NT) s_raw[k] = src[(size_t)base * esz + k];
         if (bulk) { fac_mbar_wait(&s_mbar, mbar_phase & 1u); mbar_phase++; }
         __syncthreads();
+        // text context words: folded first char + the dense symbols of positions k .. k+3 (fac_succinct.h)
         for (uint32_t k = tid; k < span; k += NT) {
-            uint32_t b = 0, s = NOSYM;
-            if (k < avail) {
-                if (P.first) {   // already folded by K1; non-ASCII first chars match no edge and have similarity 0
-                    const uint32_t c = reinterpret_cast<const uint32_t *>(s_raw)[k];
-                    b = c < 128u ? c : SUCC_NONASCII;
-                    s = c < 128u ? s_symof[c] : NOSYM;
-                } else {
-                    b = s_raw[k];
-                    if (P.ci && b >= 'A' && b <= 'Z') b += 32u;   // to_ascii_lowercase, grapheme.rs:110-117
-                    s = s_symof[b];
+            uint32_t b0 = 0, sy[4];
+#pragma unroll
+            for (uint32_t q = 0; q < 4; q++) {
+                uint32_t b = 0, sq = NOSYM;
+                if (k + q < avail) {
+                    if (P.first) {   // already folded by K1; non-ASCII first chars match no edge and have similarity 0
+                        const uint32_t c = reinterpret_cast<const uint32_t *>(s_raw)[k + q];
+                        b = c < 128u ? c : SUCC_NONASCII;
+                        sq = c < 128u ? s_symof[c] : NOSYM;
+                    } else {
+                        b = s_raw[k + q];
+                        if (P.ci && b >= 'A' && b <= 'Z') b += 32u;   // to_ascii_lowercase, grapheme.rs:110-117
+                        sq = s_symof[b];
+                    }
                 }
+                if (q == 0) b0 = b;
+                sy[q] = sq;
             }
-            s_byte[k] = (uint8_t)b; s_sym[k] = (uint8_t)s;
+            s_ctx[k] = succ_ctx_pack(b0, sy[0], sy[1], sy[2], sy[3]);
         }
         __syncthreads();
-        const SuccTextDev T{s_byte, s_sym, base};
+        const SuccTextDev T{s_ctx, base};
 
         if (P.exact_only) {
             // no edit is ever accepted (search.rs:166-168): one LANE per start window walks the exact chain
@@ -288,8 +276,11 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                     const bool ok = it < total && succ_item2<W>(K, s_subpen, O, r, c);
                     const bool to_walk = ok && (O.flags & SUCC_F_LAST);
                     const bool to_stack = ok && !(O.flags & SUCC_F_LAST);
-                    if (__any_sync(0xFFFFFFFFu, to_walk)) succ_warp_push(wq, wn, to_walk, c);
-                    if (__any_sync(0xFFFFFFFFu, to_stack)) succ_warp_push(stk, top, to_stack, c);
+                    const uint32_t bw = __ballot_sync(0xFFFFFFFFu, to_walk), bs = __ballot_sync(0xFFFFFFFFu, to_stack);
+                    const uint4 cv = make_uint4(c.node, __float_as_uint(c.pen), c.cnt, c.pos);
+                    if (to_walk) wq[wn + __popc(bw & lt_mask)] = cv;
+                    if (to_stack) stk[top + __popc(bs & lt_mask)] = cv;
+                    wn += __popc(bw); top += __popc(bs);
                     continue;
                 }
                 // (3) feed more start windows when the stack runs low: one root at a time when a root fans out into
@@ -305,11 +296,12 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                     bool push = lane < nf && w < count;
                     if (push && P.wskip) {  // 2-gram window skip (search.rs:535-553); result-neutral.  Only ASCII first chars take part
                         const uint32_t start = tile_start + w;
-                        if (T.byte(start) != SUCC_NONASCII && !((P.first_mask >> T.sym(start)) & 1u))
-                            push = !(start + 1 >= text_end || (T.byte(start + 1) != SUCC_NONASCII && !((P.second_mask >> T.sym(start + 1)) & 1u)));
+                        const uint32_t cw = T.ctx(start);
+                        if (succ_ctx_byte(cw) != SUCC_NONASCII && !((P.first_mask >> succ_ctx_s0(cw)) & 1u))
+                            push = !(start + 1 >= text_end || (T.byte(start + 1) != SUCC_NONASCII && !((P.second_mask >> succ_ctx_s1(cw)) & 1u)));
                     }
                     const uint32_t bal = __ballot_sync(0xFFFFFFFFu, push);
-                    if (push) stk[top + __popc(bal & succ_lanemask_lt())] = make_uint4(0u, 0u, 0u, w << 20);
+                    if (push) stk[top + __popc(bal & lt_mask)] = make_uint4(0u, 0u, 0u, w << 20);
                     top += __popc(bal);
                     fed = bal != 0u;
                     continue;
@@ -364,23 +356,37 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                 if (active) {
                     n_states++;
                     if (succ_has_out<W>(rec)) succ_outputs<LIM>(K, out2, emit, succ_out_idx<W>(K, rec, sv.x), pen, sv.z, start, start + succ_mr(sv.w));
-                    succ_make_ctx2<LIM, W>(K, T, G, G2, start, text_end, sv.x, rec, pen, sv.z, sv.w, C);
+                    succ_make_ctx2<LIM, W>(K, T, G, start, text_end, sv.x, rec, pen, sv.z, sv.w, C);
                     const uint32_t jr = succ_jr(sv.w);
-                    const uint32_t cur_s = (C.packed >> 8) & 0xFFu;
+                    const uint32_t cur_s = succ_ctx_s0(C.packed);
                     if (succ_has_edge<W>(rec, cur_s)) {   // exact transition, search.rs:776-798
                         p_ex = true;
                         c_ex.node = succ_child<W>(rec, cur_s); c_ex.pen = pen; c_ex.cnt = sv.z; c_ex.pos = succ_repos(sv.w, jr + 1, jr + 1);
                     }
                     p_sw = succ_swap2<LIM, W>(K, R, C, c_sw);
-                    p_in = succ_ins2<LIM, W>(K, C, sv.x, succ_has_out<W>(rec), c_in);
+                    p_in = succ_ins2<LIM, W>(K, C, sv.x, c_in);
                 }
-                succ_warp_push(stk, top, p_ex, c_ex);
                 {
+                    // exact children and the swap / insertion children of states with budget left go back on the stack,
+                    // the exhausted swap / insertion children into the walk queue: five ballots, no branches
                     const bool lw = active && last;
-                    if (__any_sync(0xFFFFFFFFu, p_sw && lw)) succ_warp_push(wq, wn, p_sw && lw, c_sw);
-                    if (__any_sync(0xFFFFFFFFu, p_sw && !lw)) succ_warp_push(stk, top, p_sw && !lw, c_sw);
-                    if (__any_sync(0xFFFFFFFFu, p_in && lw)) succ_warp_push(wq, wn, p_in && lw, c_in);
-                    if (__any_sync(0xFFFFFFFFu, p_in && !lw)) succ_warp_push(stk, top, p_in && !lw, c_in);
+                    const uint32_t b_ex = __ballot_sync(0xFFFFFFFFu, p_ex);
+                    const uint32_t b_sw_w = __ballot_sync(0xFFFFFFFFu, p_sw && lw), b_in_w = __ballot_sync(0xFFFFFFFFu, p_in && lw);
+                    const uint32_t b_sw_s = __ballot_sync(0xFFFFFFFFu, p_sw && !lw), b_in_s = __ballot_sync(0xFFFFFFFFu, p_in && !lw);
+                    if (p_ex) stk[top + __popc(b_ex & lt_mask)] = make_uint4(c_ex.node, __float_as_uint(c_ex.pen), c_ex.cnt, c_ex.pos);
+                    top += __popc(b_ex);
+                    const uint4 v_sw = make_uint4(c_sw.node, __float_as_uint(c_sw.pen), c_sw.cnt, c_sw.pos);
+                    const uint4 v_in = make_uint4(c_in.node, __float_as_uint(c_in.pen), c_in.cnt, c_in.pos);
+                    if (p_sw && lw) wq[wn + __popc(b_sw_w & lt_mask)] = v_sw;
+                    wn += __popc(b_sw_w);
+                    if (p_in && lw) wq[wn + __popc(b_in_w & lt_mask)] = v_in;
+                    wn += __popc(b_in_w);
+                    if (b_sw_s | b_in_s) {
+                        if (p_sw && !lw) stk[top + __popc(b_sw_s & lt_mask)] = v_sw;
+                        top += __popc(b_sw_s);
+                        if (p_in && !lw) stk[top + __popc(b_in_s & lt_mask)] = v_in;
+                        top += __popc(b_in_s);
+                    }
                 }
                 const uint32_t n_items = succ_popc(C.sub_m) + succ_popc(C.del_m);
                 off = n_items;

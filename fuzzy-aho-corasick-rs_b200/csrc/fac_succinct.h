@@ -31,7 +31,7 @@
 #define SUCC_MAX_NODES 0x03FFFFFFu
 // sub_pen is [ROW][SUCC_SP_STRIDE]: column b < 128 = text first char b, column 128 = any non-ASCII text first char
 // (similarity 0: only offered when the engine has no similarity entry with a non-ASCII member)
-#define SUCC_SP_STRIDE 132u
+#define SUCC_SP_STRIDE 129u
 #define SUCC_NONASCII 128u
 
 #if defined(__CUDA_ARCH__)
@@ -95,6 +95,19 @@ FAC_HD uint32_t succ_jr(uint32_t pos) { return (pos >> 10) & 1023u; }
 FAC_HD uint32_t succ_mr(uint32_t pos) { return pos & 1023u; }
 FAC_HD uint32_t succ_repos(uint32_t pos, uint32_t jr, uint32_t mr) { return (pos & 0xFFF00000u) | (jr << 10) | mr; }
 
+// Text context word of position j (one 32-bit load answers everything a state needs to know about the text):
+//     folded first char of grapheme j (0..127, SUCC_NONASCII = any non-ASCII char) | sym(j) << 8 | sym(j+1) << 14 |
+//     sym(j+2) << 20 | sym(j+3) << 26          (6-bit dense symbols; NOSYM of the layout when there is no such symbol)
+// Text contract: positions at or beyond text_end read as byte 0 / NOSYM (up to start + look-ahead).
+FAC_HD uint32_t succ_ctx_pack(uint32_t byte, uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3) {
+    return byte | (s0 << 8) | (s1 << 14) | (s2 << 20) | (s3 << 26);
+}
+FAC_HD uint32_t succ_ctx_byte(uint32_t p) { return p & 0xFFu; }
+FAC_HD uint32_t succ_ctx_s0(uint32_t p) { return (p >> 8) & 63u; }
+FAC_HD uint32_t succ_ctx_s1(uint32_t p) { return (p >> 14) & 63u; }
+FAC_HD uint32_t succ_ctx_s2(uint32_t p) { return (p >> 20) & 63u; }
+FAC_HD uint32_t succ_ctx_s3(uint32_t p) { return p >> 26; }
+
 // Outputs of one node visit (search.rs:659-737): fast-path limit check is `edits > MAX_EDITS_FAST`,
 // never true here because no state exceeds the budget.
 // In limits mode every pattern is checked against its own (or the global) limits: within_limits,
@@ -142,7 +155,11 @@ FAC_HD uint32_t succ_walk(const SuccConsts &K, const Recs &R, const SuccOut *out
     return steps;
 }
 
-enum : uint32_t { SUCC_F_IN_TEXT = 1u, SUCC_F_LAST = 2u, SUCC_F_DEL = 4u, SUCC_F_HAS_NXT = 8u, SUCC_F_INS = 16u };
+enum : uint32_t { SUCC_F_IN_TEXT = 1u, SUCC_F_LAST = 2u, SUCC_F_DEL = 4u, SUCC_F_HAS_NXT = 8u, SUCC_F_INS = 16u,
+                  SUCC_F_SWAP_MASK = 32u,   // the masks do not rule the swap child out
+                  SUCC_F_INS_MASK = 64u,    // the masks do not rule the insertion child out
+                  SUCC_F_SWAP_SURE = 128u   // ... and already prove that an exhausted swap child can reach an output
+};
 
 // ---- survivor masks -------------------------------------------------------------------------------
 // For a state on its last edit the dead-end filter keeps a child c iff
@@ -158,39 +175,48 @@ struct SuccCtx2 {
     uint32_t fc;       // first child
     float pen;
     uint32_t cnt, pos;
-    uint32_t packed;   // cur byte | cur sym << 8 | next sym << 16 | next-next sym << 24
+    uint32_t packed;   // text context word of the state's position (succ_ctx_pack)
     uint32_t flags;
 };
-template <bool W> FAC_HD uint32_t nxt2_of(const SuccCtx2<W> &C) { return C.packed >> 24; }
 
 //
 // Two-deep refinement for the first gm2_nodes nodes:  gm2[node][y1][y2] = { s : c = child(node, s) has edge y1 and
-// g = child(c, y1) has an output or an edge y2 } and gm2[node][y1][NOSYM] = { s : ... g has an output }.  A child
-// outside  outm | gm2[node][y1][y2]  walks c -> g and stops there without visiting an output node, i.e. it
-// cannot emit a candidate: dropping it is result-neutral (only the visited-state statistic changes).
-// `G2(node, y1, y2)` returns that set, or the one-deep set gm[node][y1] for nodes beyond the table.
+// g = child(c, y1) has an output or an edge y2 } and gm2[node][y1][NOSYM] = { s : ... g has an output };
+// gm2[node][NOSYM][*] = 0.  A child outside  outm | gm2[node][y1][y2]  walks c -> g and stops there without visiting
+// an output node, i.e. it cannot emit a candidate: dropping it is result-neutral (only the visited-state statistic
+// changes).  The mask accessor `G` offers
+//     G.row(node, y)        gm[node][y]                                    (~0 = "unknown" beyond the table)
+//     G.row2(node, y1, y2)  gm2[node][y1][y2], or gm[node][y1] for nodes beyond the two-deep table
+// The same two tables answer two more questions without touching a node record:
+//   * swap (search.rs:935-989: node -text[j+1]-> x -text[j]-> n2): bit text[j+1] of gm[node][text[j]] says whether x has
+//     the edge text[j]; bit text[j+1] of gm2[node][text[j]][text[j+2]] additionally says that n2 has an output or the edge
+//     text[j+2], i.e. that an exhausted swap child can still emit;
+//   * insertion on the last edit (search.rs:994-1029: same node, j+1): the child walks node -text[j+1]-> g -text[j+2]-> h;
+//     bit text[j+1] of  outm | gm2[node][text[j+2]][text[j+3]]  says that g has an output, or the edge text[j+2] to a
+//     node with an output or the edge text[j+3].  Without that (and without an output at the node itself) the
+//     insertion child cannot emit.
 // Limits mode: the per-state permissions follow within_limits_*_ahead of the limits of the pattern that created
 // the node (src/search.rs:66-148); with neither pattern nor global limits only a fresh state may substitute
 // (:143-145).  The dead-end filter does not exist on that path, but dropping exhausted children whose exact walk
 // cannot reach an output stays result-neutral, so the same masks are applied once `last` (no limits of the engine
 // admit another edit after this one).
-template <bool LIM, bool W, class Text, class GM, class GM2>
-FAC_HD void succ_make_ctx2(const SuccConsts &K, const Text &T, const GM &G, const GM2 &G2, uint32_t start, uint32_t text_end, uint32_t node,
+template <bool LIM, bool W, class Text, class GM>
+FAC_HD void succ_make_ctx2(const SuccConsts &K, const Text &T, const GM &G, uint32_t start, uint32_t text_end, uint32_t node,
                            const SuccRec &rec, float pen, uint32_t cnt, uint32_t pos, SuccCtx2<W> &C) {
     typedef typename SuccW<W>::M M;
     const uint32_t NOSYM = SuccW<W>::NOSYM;
-    // Text contract: T.sym(j) == NOSYM and T.byte(j) == 0 for text_end <= j <= start + look-ahead, so the
-    // three look-ahead symbols are read unconditionally (few branches: the kernel is issue-bound).
-    const uint32_t jr = succ_jr(pos);
+    const uint32_t jr = succ_jr(pos), mr = succ_mr(pos);
     const uint32_t j = start + jr;
-    const bool last = (int)fac_edits_of(cnt) + 1 >= K.mef;
-    const bool in_text = j < text_end;
-    const uint32_t cur_b = T.byte(j), cur_s = T.sym(j), nxt_s = T.sym(j + 1), nxt2_s = T.sym(j + 2);
-    bool del_ok = K.pen_del <= FAC_SUB(K.maxpen, pen);  // search.rs:1035
+    const int edits = (int)fac_edits_of(cnt);
+    const bool last = edits + 1 >= K.mef;
+    const bool in_text = j < text_end, has_nxt = j + 1 < text_end;
+    const uint32_t p = T.ctx(j);
+    const uint32_t cur_s = succ_ctx_s0(p), nxt_s = succ_ctx_s1(p), nxt2_s = succ_ctx_s2(p), nxt3_s = succ_ctx_s3(p);
+    const float remaining = FAC_SUB(K.maxpen, pen);
+    bool del_ok = K.pen_del <= remaining;  // search.rs:1035
     bool sub_ok = true, ins_ok = true;
     if (LIM) {
         FacLimits L;
-        const int edits = (int)fac_edits_of(cnt);
         if (succ_pick_limits(K, K.node_lim[node], L)) {
             const bool e_ok = fac_none_or_lt(L.edits, edits);
             sub_ok = e_ok && fac_none_or_lt(L.sub, (int)((cnt >> 16) & 0xFF));
@@ -198,20 +224,32 @@ FAC_HD void succ_make_ctx2(const SuccConsts &K, const Text &T, const GM &G, cons
             del_ok = del_ok && e_ok && fac_none_or_lt(L.del, (int)((cnt >> 8) & 0xFF));
         } else { sub_ok = edits == 0 && ((cnt >> 16) & 0xFF) == 0; ins_ok = false; del_ok = false; }
     }
-    const uint32_t flags = (last ? SUCC_F_LAST : 0u) | (in_text ? SUCC_F_IN_TEXT : 0u) | (j + 1 < text_end ? SUCC_F_HAS_NXT : 0u) |
-                           (del_ok ? SUCC_F_DEL : 0u) | (ins_ok ? SUCC_F_INS : 0u);
     const M bm = succ_bm<W>(rec);
-    M keep_sub = ~M(0), keep_del = ~M(0);  // states not on their last edit keep every child
+    const bool has_nxt_edge = (bm >> nxt_s) & 1u;   // NOSYM is never an edge
+    const bool has_out = succ_has_out<W>(rec);
+    // everything the swap / insertion children need besides the masks (search.rs:935-937, 994-1003); the mask rows are
+    // only fetched for the states that get this far (the loads are independent and issued together)
+    const bool sw_pre = in_text && has_nxt && has_nxt_edge && cur_s != NOSYM && K.pen_swap <= remaining;
+    const bool ins_pre = in_text && ins_ok && !(mr == 0 && jr == 0) && K.pen_ins <= remaining;
+    const bool ins_need = ins_pre && last && !has_out;    // the masks decide
+    M outm = 0, m_sub = ~M(0), m_del = ~M(0), m_sw = 0, m_ins = 0;  // states not on their last edit keep every child
     if (last) {
-        const M outm = G(node, NOSYM);
-        keep_sub = outm | (nxt_s != NOSYM ? G2(node, nxt_s, nxt2_s) : M(0));
-        keep_del = outm | (cur_s != NOSYM ? G2(node, cur_s, nxt_s) : M(0));
+        outm = G.row(node, NOSYM);
+        m_sub = G.row2(node, nxt_s, nxt2_s);
+        m_del = G.row2(node, cur_s, nxt_s);
     }
+    m_sw = sw_pre ? (last ? G.row2(node, cur_s, nxt2_s) : G.row(node, cur_s)) : M(0);
+    m_ins = (ins_need && has_nxt_edge) ? G.row2(node, nxt2_s, nxt3_s) : M(0);
+    const bool swap_m = (m_sw >> nxt_s) & 1u;
+    const bool ins_m = ins_pre && (!ins_need || (((outm | m_ins) >> nxt_s) & (M)has_nxt_edge & 1u));
+    const uint32_t flags = (last ? SUCC_F_LAST : 0u) | (in_text ? SUCC_F_IN_TEXT : 0u) | (has_nxt ? SUCC_F_HAS_NXT : 0u) |
+                           (del_ok ? SUCC_F_DEL : 0u) | (ins_ok ? SUCC_F_INS : 0u) | (swap_m ? SUCC_F_SWAP_MASK : 0u) |
+                           (ins_m ? SUCC_F_INS_MASK : 0u) | ((last && G.two_deep(node)) ? SUCC_F_SWAP_SURE : 0u);
     C.bm = bm;
-    C.sub_m = (in_text && sub_ok) ? (bm & keep_sub & ~(M(1) << cur_s)) : M(0);
-    C.del_m = del_ok ? (bm & keep_del) : M(0);
+    C.sub_m = (in_text && sub_ok) ? (bm & (outm | m_sub) & ~(M(1) << cur_s)) : M(0);
+    C.del_m = del_ok ? (bm & (outm | m_del)) : M(0);
     C.fc = succ_fc<W>(rec); C.pen = pen; C.cnt = cnt; C.pos = pos;
-    C.packed = cur_b | (cur_s << 8) | (nxt_s << 16) | (nxt2_s << 24);
+    C.packed = p;
     C.flags = flags;
 }
 
@@ -245,7 +283,7 @@ FAC_HD bool succ_item2(const SuccConsts &K, const float *sub_pen, const SuccCtx2
     const bool is_sub = r < ns;
     const uint32_t s = succ_nth_bit(is_sub ? C.sub_m : C.del_m, is_sub ? r : r - ns);
     // +inf in the table when similarity < min_symbol_similarity; deletions read a valid slot and ignore it
-    const float tp = sub_pen[s * SUCC_SP_STRIDE + (C.packed & 0xFFu)];
+    const float tp = sub_pen[s * SUCC_SP_STRIDE + succ_ctx_byte(C.packed)];
     const float pp = is_sub ? tp : K.pen_del;
     out.node = C.fc + succ_popc((M)(C.bm & succ_below<M>(s)));
     out.pen = FAC_ADD(C.pen, pp);
@@ -260,12 +298,12 @@ FAC_HD bool succ_item2(const SuccConsts &K, const float *sub_pen, const SuccCtx2
 template <bool LIM, bool W, class Recs>
 FAC_HD bool succ_swap2(const SuccConsts &K, const Recs &R, const SuccCtx2<W> &C, FacState &out) {
     typedef typename SuccW<W>::M M;
-    if ((C.flags & (SUCC_F_IN_TEXT | SUCC_F_HAS_NXT)) != (SUCC_F_IN_TEXT | SUCC_F_HAS_NXT)) return false;
-    if (!(K.pen_swap <= FAC_SUB(K.maxpen, C.pen))) return false;
-    const uint32_t cur_s = (C.packed >> 8) & 0xFFu, nxt_s = (C.packed >> 16) & 0xFFu;
-    if (!((C.bm >> nxt_s) & 1u)) return false;
+    // SUCC_F_SWAP_MASK: in the text with a next grapheme, penalty affordable, edge text[j+1] present and the mask row does
+    // not rule out the second edge -- almost every state ends here, before a record is touched
+    if (!(C.flags & SUCC_F_SWAP_MASK)) return false;
+    const uint32_t cur_s = succ_ctx_s0(C.packed), nxt_s = succ_ctx_s1(C.packed);
     const SuccRec rx = R(C.fc + succ_popc((M)(C.bm & succ_below<M>(nxt_s))));
-    if (!succ_has_edge<W>(rx, cur_s)) return false;
+    if (!succ_has_edge<W>(rx, cur_s)) return false;   // only reachable when the mask row was not available ("unknown")
     const uint32_t jr = succ_jr(C.pos);
     out.node = succ_child<W>(rx, cur_s); out.pen = FAC_ADD(C.pen, K.pen_swap); out.cnt = C.cnt + 0x1000000u; out.pos = succ_repos(C.pos, jr + 2, jr + 2);
     if (LIM) {  // within_limits_swap_ahead of the TARGET node's limits (search.rs:119-130, 962-975)
@@ -273,24 +311,21 @@ FAC_HD bool succ_swap2(const SuccConsts &K, const Recs &R, const SuccCtx2<W> &C,
         if (!succ_pick_limits(K, K.node_lim[out.node], L)) return false;
         if (!(fac_none_or_lt(L.edits, (int)fac_edits_of(C.cnt)) && fac_none_or_lt(L.swp, (int)(C.cnt >> 24)))) return false;
     }
-    if (C.flags & SUCC_F_LAST) {
-        // the exhausted swap child visits n2 at j+2 and then only follows text[j+2]: without an output at n2 and
-        // without that edge it cannot emit -- dropping it is result-neutral
+    if ((C.flags & (SUCC_F_LAST | SUCC_F_SWAP_SURE)) == SUCC_F_LAST) {
+        // beyond the two-deep table: the exhausted swap child visits n2 at j+2 and then only follows text[j+2]; without
+        // an output at n2 and without that edge it cannot emit -- dropping it is result-neutral
         const SuccRec r2 = R(out.node);
-        if (!succ_has_out<W>(r2) && !succ_has_edge<W>(r2, nxt2_of(C))) return false;
+        if (!succ_has_out<W>(r2) && !succ_has_edge<W>(r2, succ_ctx_s2(C.packed))) return false;
     }
     return true;
 }
 template <bool LIM, bool W>
-FAC_HD bool succ_ins2(const SuccConsts &K, const SuccCtx2<W> &C, uint32_t node, bool has_out, FacState &out) {
-    if (!(C.flags & SUCC_F_IN_TEXT)) return false;
+FAC_HD bool succ_ins2(const SuccConsts &K, const SuccCtx2<W> &C, uint32_t node, FacState &out) {
+    // SUCC_F_INS_MASK: insertion allowed here (search.rs:994-1003) and, on the last edit, not ruled out by the masks,
+    // which subsume the reference's dead-end filter ("node has an output or the edge text[j+1]", :1005-1007) and look
+    // two nodes further along the exact walk of the exhausted child
+    if (!(C.flags & SUCC_F_INS_MASK)) return false;
     const uint32_t jr = succ_jr(C.pos), mr = succ_mr(C.pos);
-    if (mr == 0 && jr == 0) return false;
-    if (!(K.pen_ins <= FAC_SUB(K.maxpen, C.pen))) return false;
-    if (!(C.flags & SUCC_F_INS)) return false;
-    if (!LIM && (C.flags & SUCC_F_LAST) && !has_out) {
-        if (!(C.flags & SUCC_F_HAS_NXT) || !((C.bm >> ((C.packed >> 16) & 0xFFu)) & 1u)) return false;
-    }
     out.node = node; out.pen = FAC_ADD(C.pen, K.pen_ins); out.cnt = C.cnt + 1u; out.pos = succ_repos(C.pos, jr + 1, mr);
     return true;
 }

@@ -187,31 +187,17 @@ struct EmuSText {   // first chars / symbols of the haystack graphemes; position
         return (ci && c >= 'A' && c <= 'Z') ? c + 32u : c;
     }
     uint32_t sym(uint32_t j) const { if (j >= n) return nosym; const uint32_t c = byte(j); return c < 128u ? symof[c] : nosym; }
+    uint32_t ctx(uint32_t j) const { return succ_ctx_pack(byte(j), sym(j), sym(j + 1), sym(j + 2), sym(j + 3)); }
 };
 template <bool W>
-struct EmuGM {   // grandchild-mask rows: table for the first gm_nodes nodes, recomputed from the children beyond
+struct EmuGM {   // survivor-mask tables with the kernel's accessor interface (SuccGMDev)
     typedef typename SuccW<W>::M M;
-    const uint64_t *gm; uint32_t gm_nodes; const SuccRec *r;
-    M operator()(uint32_t node, uint32_t y) const {
-        if (node < gm_nodes) return (M)gm[(size_t)node * SuccW<W>::ROW + y];
-        M bmv = succ_bm<W>(r[node]), m = 0;
-        uint32_t k = 0;
-        while (bmv) {
-            const uint32_t sy = (uint32_t)__builtin_ctzll((uint64_t)bmv);
-            bmv &= bmv - 1;
-            const SuccRec &c = r[succ_fc<W>(r[node]) + k++];
-            if (y == SuccW<W>::NOSYM ? succ_has_out<W>(c) : succ_has_edge<W>(c, y)) m |= M(1) << sy;
-        }
-        return m;
-    }
-};
-template <bool W>
-struct EmuGM2 {
-    typedef typename SuccW<W>::M M;
-    const uint64_t *gm2; uint32_t gm2_nodes; EmuGM<W> G;
-    M operator()(uint32_t node, uint32_t y1, uint32_t y2) const {
-        if (node < gm2_nodes) return (M)gm2[((size_t)node * SuccW<W>::ROW + y1) * SuccW<W>::ROW + y2];
-        return G(node, y1);
+    const uint64_t *gm, *gm2; uint32_t gm_nodes, gm2_nodes;
+    bool two_deep(uint32_t node) const { return node < gm2_nodes; }
+    M row(uint32_t node, uint32_t y) const { return node < gm_nodes ? (M)gm[(size_t)node * SuccW<W>::ROW + y] : ~M(0); }
+    M row2(uint32_t node, uint32_t y1, uint32_t y2) const {
+        if (node >= gm_nodes) return ~M(0);
+        return node < gm2_nodes ? (M)gm2[((size_t)node * SuccW<W>::ROW + y1) * SuccW<W>::ROW + y2] : (M)gm[(size_t)node * SuccW<W>::ROW + y1];
     }
 };
 struct EmuEmit {
@@ -237,8 +223,7 @@ static void emu_succ_expand(const HostAutomaton &HA, const EmuText &ET, const ui
     K.mef = S.limits_mode ? (int32_t)S.edit_bound : HA.mef;
     K.lim = HA.lim.data(); K.node_lim = S.node_lim.data(); K.has_global = HA.has_global_limits; K.out_idx = S.out_idx.data();
     const EmuRecs R{recs.data()};
-    const EmuGM<W> G{S.gmask.data(), S.gm_nodes, recs.data()};
-    const EmuGM2<W> G2{S.gmask2.data(), S.gm2_nodes, G};
+    const EmuGM<W> G{S.gmask.data(), S.gmask2.data(), S.gm_nodes, S.gm2_nodes};
     const EmuSText T{hay, ET.tv.ascii ? nullptr : ET.first.data(), S.sym_of, HA.ci, n, NOSYM};
     const SuccOut *out2 = (const SuccOut *)S.out2.data();
     EmuEmit emit{&cands};
@@ -263,18 +248,18 @@ static void emu_succ_expand(const HostAutomaton &HA, const EmuText &ET, const ui
             if (s.pen > succ_ceil<W>(rec)) continue;
             if (succ_has_out<W>(rec)) succ_outputs<LIMM>(K, out2, emit, succ_out_idx<W>(K, rec, s.node), s.pen, s.cnt, start, start + succ_mr(s.pos));
             SuccCtx2<W> C;
-            succ_make_ctx2<LIMM, W>(K, T, G, G2, start, text_end, s.node, rec, s.pen, s.cnt, s.pos, C);
+            succ_make_ctx2<LIMM, W>(K, T, G, start, text_end, s.node, rec, s.pen, s.cnt, s.pos, C);
             const bool last = (C.flags & SUCC_F_LAST) != 0;
             const uint32_t jr = succ_jr(s.pos);
             auto child = [&](const FacState &c) {
                 if (last) states += succ_walk<LIMM, W>(K, R, out2, T, emit, start, text_end, c.node, R(c.node), c.pen, c.cnt, succ_jr(c.pos), succ_mr(c.pos));
                 else stack.push_back(c);
             };
-            const uint32_t cur_s = (C.packed >> 8) & 0xFFu;
+            const uint32_t cur_s = succ_ctx_s0(C.packed);
             if (succ_has_edge<W>(rec, cur_s)) stack.push_back(FacState{succ_child<W>(rec, cur_s), s.pen, s.cnt, succ_repos(s.pos, jr + 1, jr + 1)});
             FacState c;
             if (succ_swap2<LIMM, W>(K, R, C, c)) child(c);
-            if (succ_ins2<LIMM, W>(K, C, s.node, succ_has_out<W>(rec), c)) child(c);
+            if (succ_ins2<LIMM, W>(K, C, s.node, c)) child(c);
             const uint32_t n_items = succ_popc(C.sub_m) + succ_popc(C.del_m);
             for (uint32_t r = 0; r < n_items; r++)
                 if (succ_item2<W>(K, S.sub_pen.data(), C, r, c)) child(c);
