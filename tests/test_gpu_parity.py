@@ -421,6 +421,27 @@ def test_cfg2_32MiB_properties_and_sampled_parity(oracle, gpu):
         assert got == want, p
 
 
+def test_cfg2_64MiB_fast_equals_faithful_full_list(gpu, monkeypatch):
+    """The quoted configuration at size: cfg2 with all 10 000 patterns over 64 MiB, the fast kernel's COMPLETE match
+    list (11 M records) byte for byte against the order-faithful kernel (FAC_FAITHFUL=1: FIFO order, per-level dedup,
+    pushed-state count == the reference's queue.len()) -- two independent device paths, one of which the oracle pins at
+    small sizes with exactly this engine (tests/golden/cfg2_64KiB_10000pat.npz)."""
+    import torch
+    nbytes = 64 << 20
+    cfg = workload.cfg2(nbytes, 10000)
+    dev = torch.from_numpy(cfg["text"]).cuda()
+    monkeypatch.setenv("FAC_FAITHFUL", "0")
+    fast = workload.build_engine(cfg, gpu)
+    monkeypatch.setenv("FAC_FAITHFUL", "1")
+    faithful = workload.build_engine(cfg, gpu)
+    a, sa = gpu.search_device(fast._h, dev.data_ptr(), nbytes, 0.8, 0, 0, False)
+    b, sb = gpu.search_device(faithful._h, dev.data_ptr(), nbytes, 0.8, 0, 0, False)
+    assert len(a) == len(b) and len(a) > 10_000_000
+    assert np.array_equal(np.frombuffer(a, dtype=np.uint8), np.frombuffer(b, dtype=np.uint8))
+    # the faithful kernel counts the reference's pushed states, the fast kernel visits far fewer
+    assert sb["states_pushed"] > 2000 * nbytes and sa["states_pushed"] < sb["states_pushed"] // 3
+
+
 def _beam_cases(seed, trials):
     r = random.Random(seed)
     words = ["saddam", "hussein", "tincidunt", "porta", "vestibulum", "accumsan", "hello", "world", "help", "shell",

@@ -74,6 +74,17 @@ def test_prefilter_matches_full_search_unicode(oracle):  # prefilter.rs:539-546
     differential(oracle, 0xDEADBEEF0BADF00D, UNI_VOCAB, UNI_FILLER, 4000, _pf_check)
 
 
+# the same two seeded differentials on the GPU backend (Prefiltered::search == search, both through the C ABI)
+@pytest.mark.gpu
+def test_prefilter_matches_full_search_ascii_gpu(gpu):  # prefilter.rs:531-536
+    differential(gpu, 0x123456789ABCDEF1, ASCII_VOCAB, ASCII_FILLER, 4000, _pf_check)
+
+
+@pytest.mark.gpu
+def test_prefilter_matches_full_search_unicode_gpu(gpu):  # prefilter.rs:539-546
+    differential(gpu, 0xDEADBEEF0BADF00D, UNI_VOCAB, UNI_FILLER, 4000, _pf_check)
+
+
 # ---- Unicode tables -----------------------------------------------------------------------------
 TRICKY = (["a", "B", " ", "\r", "\n", "\t", "é", "́", "‍", "\U0001F468", "\U0001F469", "\U0001F467",
            "\U0001F1FA", "\U0001F1F8", "\U0001F3FB", "क", "्", "ष", "ि", "؀", "ᄀ",

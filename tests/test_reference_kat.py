@@ -473,3 +473,26 @@ def test_duplicate_patterns_both_reported(backend):  # tests.rs:38-58
     e = B(backend).build(["KO", "KO"])
     r = e.search("KO", O().threshold(0.9))
     assert sorted(m.pattern_index for m in r) == [0, 1]
+
+
+# ---- tests.rs:758-797 (print-only in the reference: they pin "no panic" and, here, oracle == GPU) ----
+@pytest.mark.parametrize("pattern,hay", [("SIMIC", "SIIC"), ("AMINULLAH", "Aminulah"), ("JAFAR", "Jaar")])
+def test_missing_letter_edits3(backend, pattern, hay):
+    e = B(backend).case_insensitive(True).build([Pattern(pattern).fuzzy(FuzzyLimits.new().edits(3))])
+    r = e.search(hay, O().threshold(0.7).sorted())
+    assert has(r, pattern)   # one deletion: similarity (n - 0.91) / n >= 0.7 for n >= 4
+
+
+# ---- tests.rs:1239-1259 ----
+def test_replace_stream_parallel_small_cases(backend):
+    e = B(backend).fuzzy(FuzzyLimits.new().edits(1)).case_insensitive(True).build(["needle"])
+
+    def run(inp, threads):
+        out = io.BytesIO()
+        e.replace_stream_parallel(io.BytesIO(inp.encode()), out, threads, 0.8, lambda m: "X")
+        return out.getvalue().decode()
+    assert run("a needle b", 8) == "a X b"
+    assert run("needle needle", 4) == "X X"
+    assert run("a neeedle b", 2) == "a X b"
+    assert run("nothing here", 4) == "nothing here"
+    assert run("", 4) == ""

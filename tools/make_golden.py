@@ -68,6 +68,20 @@ def main():
         json.dump(doc, f, ensure_ascii=True, separators=(",", ":"))
     print("unicode_mappings", {k: len(v) for k, v in doc["results"].items()})
     fast_domain_cases(ob, out_dir)
+    headline_case(ob, out_dir)
+
+
+def headline_case(ob, out_dir):
+    """The headline engine at its full pattern count: cfg2 with 10 000 patterns over the first 64 KiB of the haystack,
+    the oracle's complete match list (one row per match: start, end, pattern, similarity bits, ins, del, sub, swap,
+    edits) as a compressed int64 array."""
+    import numpy as np
+    cfg = workload.cfg2(65536, 10000)
+    eng = workload.build_engine(cfg, ob)
+    r = eng.search(bytes(cfg["text"]), SearchOptions.new().threshold(cfg["threshold"]))
+    rows = np.array([list(t) for t in r.tuples()], dtype=np.int64)
+    np.savez_compressed(os.path.join(out_dir, "cfg2_64KiB_10000pat.npz"), matches=rows)
+    print("cfg2_64KiB_10000pat", rows.shape)
 
 
 def fast_domain_cases(ob, out_dir):
