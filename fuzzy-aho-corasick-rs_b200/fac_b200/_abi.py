@@ -64,6 +64,12 @@ class fac_search_args(C.Structure):
                 ("use_prefilter", C.c_int32), ("flags", C.c_uint32)]
 
 
+class fac_stream_stats(C.Structure):
+    _fields_ = [("bytes_read", C.c_uint64), ("bytes_written", C.c_uint64), ("windows", C.c_uint64), ("matches", C.c_uint64),
+                ("states", C.c_uint64), ("device_ms", C.c_double), ("expand_ms", C.c_double), ("kernel_launches", C.c_uint32),
+                ("devices", C.c_uint32)]
+
+
 FAC_HAYSTACK_ON_DEVICE, FAC_RESULT_ON_DEVICE, FAC_TEXT_IS_UNICODE, FAC_APPLY_PRESORTED = 1, 2, 4, 8
 
 assert C.sizeof(fac_match) == 32
@@ -105,6 +111,9 @@ SYMBOLS = [
     ("fac_matches_kernel_launches", C.c_uint32, [C.c_void_p]),
     ("fac_matches_free", None, [C.c_void_p]),
     ("fac_search_stream", C.c_int, [C.c_void_p, READ_FN, C.c_void_p, C.c_float, MATCH_FN, C.c_void_p, C.POINTER(C.c_uint64)]),
+    ("fac_replace_stream_table", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_size_t), C.c_size_t, C.POINTER(fac_stream_stats)]),
+    ("fac_search_stream_stats", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(fac_stream_stats)]),
     ("fac_replace_stream", C.c_int, [C.c_void_p, READ_FN, C.c_void_p, WRITE_FN, C.c_void_p, C.c_float,
                                      REPLACE_FN, C.c_void_p, C.POINTER(C.c_uint64)]),
 ]

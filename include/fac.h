@@ -292,6 +292,28 @@ fac_status fac_replace_stream(const fac_engine *engine, fac_read_fn read, void *
                               fac_write_fn write, void *write_user, float threshold,
                               fac_replace_fn replace, void *replace_user, uint64_t *bytes_written);
 
+/* Counters of one stream call (all optional outputs). */
+typedef struct fac_stream_stats {
+    uint64_t bytes_read;
+    uint64_t bytes_written;
+    uint64_t windows;       /* reader-cut windows searched */
+    uint64_t matches;       /* matches owned by their windows */
+    uint64_t states;        /* search states (see fac_matches_states_pushed) */
+    double device_ms;       /* sum over window batches, CUDA events on the library's streams */
+    double expand_ms;
+    uint32_t kernel_launches;
+    uint32_t devices;       /* devices the windows were spread over */
+} fac_stream_stats;
+
+/* FuzzyReplacer::replace_stream (src/replacer.rs:35-46): replace_stream with the replacement taken from a table indexed
+ * by pattern index (entries beyond n_replacements, or NULL entries, keep the matched text).  `stats` may be NULL. */
+fac_status fac_replace_stream_table(const fac_engine *engine, fac_read_fn read, void *read_user, fac_write_fn write,
+                                    void *write_user, float threshold, const uint8_t *const *replacements,
+                                    const size_t *replacement_lens, size_t n_replacements, fac_stream_stats *stats);
+/* search_stream with the counters of the call (on_match may be NULL: count only). */
+fac_status fac_search_stream_stats(const fac_engine *engine, fac_read_fn read, void *read_user, float threshold,
+                                   fac_match_fn on_match, void *match_user, fac_stream_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif
