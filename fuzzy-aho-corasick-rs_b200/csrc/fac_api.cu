@@ -26,6 +26,7 @@
 #include "fac_fastreduce.cuh"
 #include "fac_segment.cuh"
 #include "fac_succinct.cuh"
+#include "fac_stack.cuh"
 #include "fac_bitap.cuh"
 
 #define FAC_TABLE_QUAL static const
@@ -246,9 +247,13 @@ struct fac_engine {
     const uint32_t *d_s_node_lim = nullptr;
     uint32_t succ_nt = 1024, succ_tile = 4096, succ_stack = 0, succ_min_stack = 64;
     int smem_optin = 0;
+    bool stack_ok = false;          // general stack-machine kernel (fac_stack.cuh) for fast engines outside the succinct domain
+    uint32_t stack_cap = 384, stack_tile = 1024;
     bool fast_ok = false;  // FAST kernel allowed (fast-path edit ceiling, no beam); FAC_FAITHFUL=1 forces the order-faithful kernel
     mutable std::mutex mu;
     mutable std::vector<Workspace *> pool;
+    // fac_engine_create_multi: the same automaton on further devices (the stream entry points deal window batches over them)
+    std::vector<fac_engine *> replicas;
 };
 
 struct fac_matches {
@@ -388,6 +393,34 @@ fac_status launch_succinct(const fac_engine *E, Workspace *ws, const TextView &t
     }
 }
 
+// ---- general stack-machine kernel launch (fac_stack.cuh) ----
+template <bool ASCII, bool MAPP>
+fac_status launch_stack_t(const StackParams &SP, uint32_t grid, size_t smem, cudaStream_t s) {
+    CK(cudaFuncSetAttribute(k_expand_stack<ASCII, MAPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_expand_stack<ASCII, MAPP><<<grid, STK_THREADS, smem, s>>>(SP);
+    CK(cudaGetLastError());
+    return FAC_OK;
+}
+size_t stack_smem_bytes(const fac_engine *E, bool ascii, uint32_t text_cap) {
+    const size_t tb = ascii ? ((text_cap + 31u) & ~15u) : ((text_cap * 4u + 31u) & ~15u);
+    const size_t mult = (!ascii && E->host.has_mappings) ? 2 : 1;
+    return tb * mult + (size_t)(STK_THREADS / 32) * (E->stack_cap + STK_WQ_CAP) * 16;
+}
+fac_status launch_stack(const fac_engine *E, const ExpandParams &P, uint32_t *dirty, uint32_t n_tiles, cudaStream_t s) {
+    StackParams SP;
+    SP.E = P; SP.stack_cap = E->stack_cap; SP.dirty = dirty;
+    SP.feed_below = 32u;
+    const bool ascii = P.tv.ascii != 0, mapp = P.A.has_mappings != 0;
+    const size_t smem = stack_smem_bytes(E, ascii, P.smem_text_cap);
+    if (smem + 1024 > (size_t)E->smem_optin) { set_err("stack kernel: shared-memory budget too small for the configured stack / tile"); return FAC_UNSUPPORTED; }
+    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, ((size_t)228 * 1024) / (smem + 1024)));
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)E->sm_count * per_sm, n_tiles);
+    if (ascii && !mapp) return launch_stack_t<true, false>(SP, grid, smem, s);
+    if (ascii && mapp) return launch_stack_t<true, true>(SP, grid, smem, s);
+    if (!ascii && !mapp) return launch_stack_t<false, false>(SP, grid, smem, s);
+    return launch_stack_t<false, true>(SP, grid, smem, s);
+}
+
 size_t expand_smem_bytes(const fac_engine *E, bool ascii, uint32_t text_cap) {
     const size_t tb = ascii ? ((text_cap + 31u) & ~15u) : ((text_cap * 4u + 31u) & ~15u);
     const size_t mult = (!ascii && E->host.has_mappings) ? 2 : 1;
@@ -455,6 +488,10 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
     const bool ascii = R.tv.ascii != 0;
     const bool explicit_tiles = !R.tiles.empty();
     const uint64_t n_windows_total = explicit_tiles ? 0 : (uint64_t)(R.seg_end - R.seg_begin);
+    const bool succ_text = ascii || E->host.succ.unicode_text_ok;   // K1 first-char stream works too
+    const bool use_succ = R.fast && (E->succ_ok || E->succ_generic_ok) && succ_text && (!explicit_tiles || R.slices) && !R.beam && !R.d_per_window;
+    const bool use_stack = R.fast && E->stack_ok && !use_succ && !R.beam && !R.d_per_window;
+    if (use_stack && !explicit_tiles) tile = E->stack_tile;   // the stack machines stream windows: large tiles, one staging per tile
     uint32_t n_tiles = explicit_tiles ? (uint32_t)R.tiles.size() : cdiv(n_windows_total, tile);
     if (n_tiles == 0) return FAC_OK;
     uint32_t max_count = tile;
@@ -466,7 +503,7 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
     const uint32_t ctas = beam_bs == 32 ? 32u : (uint32_t)E->ctas_per_sm;
     const uint32_t run_qcap = beam_bs == 32 ? (uint32_t)std::max(4096, env_int("FAC_BEAM_QCAP", 16384)) : E->qcap;
     const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)E->sm_count * ctas, n_tiles);
-    CKS(ensure_scratch(E, ws, (uint32_t)E->sm_count * ctas, run_qcap));
+    if (!use_succ && !use_stack) CKS(ensure_scratch(E, ws, (uint32_t)E->sm_count * ctas, run_qcap));   // the stack machines keep their frontier in shared memory
     uint32_t cand_cap = (uint32_t)std::max<size_t>(ws->cands.cap / sizeof(FacCand), 1u << 20);
     // dense-match workloads emit ~0.2-0.4 candidates per start window: size the first attempt so it need not be redone
     if (R.fast && !explicit_tiles) cand_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(cand_cap, n_windows_total / 2 + (1u << 20)), 0x7FFFFFF0u);
@@ -499,11 +536,10 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
     P.per_window = R.d_per_window;
     P.use_tma = E->use_tma;
     const size_t smem = expand_smem_bytes(E, ascii, P.smem_text_cap);
-    const bool succ_text = ascii || E->host.succ.unicode_text_ok;   // K1 first-char stream works too
-    const bool use_succ = R.fast && (E->succ_ok || E->succ_generic_ok) && succ_text && (!explicit_tiles || R.slices) && !R.beam && !R.d_per_window;
     // an exact-only engine is "fast" only through the succinct kernel; the generic FAST kernel needs an edit budget
     const bool fast_run = R.fast && (E->fast_ok || use_succ);
     if (use_succ && explicit_tiles && max_count > E->succ_tile) { set_err("internal: slice tile larger than the succinct tile"); return FAC_INVALID_ARGUMENT; }
+    if (use_stack && max_count > FAC_MAX_TILE) { set_err("internal: tile larger than the 12-bit window field"); return FAC_INVALID_ARGUMENT; }
     const uint32_t n_win_seg = R.seg_end - R.seg_begin;
     const uint32_t dirty_words = n_win_seg / 32 + 1;
     if (fast_run) CKS(ws->dirty.ensure((size_t)dirty_words * 4));
@@ -522,7 +558,8 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
             CKS(launch_succinct(E, ws, R.tv, R.thr, R.seg_begin, R.seg_end, R.text_end, ws->cands.as<FacCand>(), cand_cap, s,
                                 explicit_tiles ? ws->tiles.as<uint4>() : nullptr, n_tiles));
             stats.launches++;
-        } else CKS(launch_expand(P, grid, smem, s, fast_run));
+        } else if (use_stack) CKS(launch_stack(E, P, ws->dirty.as<uint32_t>(), n_tiles, s));
+        else CKS(launch_expand(P, grid, smem, s, fast_run));
         CK(cudaEventRecord(ws->evk1, s));
         stats.launches++;
         CK(cudaMemcpyAsync(ws->h_counters, ws->counters.p, 8 * 8, cudaMemcpyDeviceToHost, s));
@@ -597,7 +634,7 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
         if (R.limit_after_expand) sg_end = R.limit_after_expand(states);
         else if (R.count_states) stats.states += states;
         if (states_per_window_out && n_windows_total) *states_per_window_out = (double)ws->h_counters[6] / (double)n_windows_total;
-        const uint64_t n_overflowed = use_succ ? ws->h_counters[7] : 0;
+        const uint64_t n_overflowed = (use_succ || use_stack) ? ws->h_counters[7] : 0;
         if (n_cand == 0 && n_overflowed == 0) return FAC_OK;
 
         // ---- best-per-span reduction ----
@@ -1101,7 +1138,7 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
         bool fallback = false;
         CKS(prefilter_slices(E, ws, d_text, (uint32_t)n, thr, slices, &fallback, stats));
         if (!fallback) {
-            const uint32_t tile_w = (E->succ_ok || E->succ_generic_ok) ? E->succ_tile : 64u;
+            const uint32_t tile_w = (E->succ_ok || E->succ_generic_ok) ? E->succ_tile : (E->stack_ok ? E->stack_tile : 64u);
             size_t si = 0;
             while (si < slices.size()) {
                 // batches of slices bounded by a window budget so the candidate buffers stay modest
@@ -1128,6 +1165,7 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
     uint32_t tile = E->default_tile;
     bool calibrated = tile != 0;
     if ((E->succ_ok || E->succ_generic_ok) && (ascii || E->host.succ.unicode_text_ok)) { calibrated = true; if (!tile) tile = 8; }  // the succinct kernel tiles by itself
+    if (E->stack_ok && !calibrated) { calibrated = true; tile = 8; }   // the stack kernel tiles by itself; 8 = faithful redo tile
     if (!calibrated) tile = 4;
     uint64_t pos = g_begin;
     while (pos < g_end) {
@@ -1304,6 +1342,9 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
     // only through the succinct kernel (exact-chain shortcut / limits mode)
     E->succ_generic_ok = H.succ.ok && (H.succ.exact_only || H.succ.limits_mode) && H.beam_width == 0 && !H.has_auto_beam && env_int("FAC_FAITHFUL", 0) == 0 &&
                     env_int("FAC_SUCCINCT", 1) != 0;
+    E->stack_ok = E->fast_ok && env_int("FAC_STACK", 1) != 0;
+    E->stack_cap = (uint32_t)std::min(2048, std::max(64, env_int("FAC_STACK_CAP", 384)));
+    E->stack_tile = (uint32_t)std::min(4096, std::max(32, env_int("FAC_STACK_TILE", 1024)));
     E->succ_nt = (uint32_t)env_int("FAC_SUCC_THREADS", 1024);
     E->succ_tile = (uint32_t)std::min(4096, std::max(32, env_int("FAC_SUCC_TILE", 4096)));  // 12-bit window field of a state
     E->succ_stack = (uint32_t)env_int("FAC_SUCC_STACK", 0);
@@ -1331,8 +1372,31 @@ fac_status fac_engine_create(const fac_config *cfg, const fac_pattern *patterns,
     return fac_engine_create_on(-1, cfg, patterns, n_patterns, out);
 }
 
+fac_status fac_engine_create_multi(const int *devices, size_t n_devices, const fac_config *cfg, const fac_pattern *patterns, size_t n_patterns,
+                                   fac_engine **out) {
+    if (!out) { set_err("null out pointer"); return FAC_INVALID_ARGUMENT; }
+    *out = nullptr;
+    if (!devices || n_devices == 0) { set_err("fac_engine_create_multi needs at least one device"); return FAC_INVALID_ARGUMENT; }
+    for (size_t i = 0; i < n_devices; i++)
+        for (size_t j = 0; j < i; j++)
+            if (devices[i] == devices[j]) { set_err("fac_engine_create_multi: duplicate device index"); return FAC_INVALID_ARGUMENT; }
+    fac_engine *primary = nullptr;
+    CKS(fac_engine_create_on(devices[0], cfg, patterns, n_patterns, &primary));
+    for (size_t i = 1; i < n_devices; i++) {
+        fac_engine *r = nullptr;
+        const fac_status st = fac_engine_create_on(devices[i], cfg, patterns, n_patterns, &r);
+        if (st != FAC_OK) { fac_engine_free(primary); return st; }
+        primary->replicas.push_back(r);
+    }
+    cudaSetDevice(primary->device);
+    *out = primary;
+    return FAC_OK;
+}
+
 void fac_engine_free(fac_engine *E) {
     if (!E) return;
+    for (fac_engine *r : E->replicas) fac_engine_free(r);
+    E->replicas.clear();
     cudaSetDevice(E->device);
     for (Workspace *w : E->pool) { w->destroy(); delete w; }
     for (void *p : E->dallocs) cudaFree(p);
@@ -1344,6 +1408,7 @@ int fac_engine_prefilter_active(const fac_engine *E) { return E && E->host.bitap
 size_t fac_engine_num_nodes(const fac_engine *E) { return E ? E->host.n_nodes() : 0; }
 size_t fac_engine_num_patterns(const fac_engine *E) { return E ? E->host.patterns.size() : 0; }
 int fac_engine_device(const fac_engine *E) { return E ? E->device : -1; }
+size_t fac_engine_num_devices(const fac_engine *E) { return E ? 1 + E->replicas.size() : 0; }
 
 static fac_status search_common(const fac_engine *E, const uint8_t *hay, size_t len, bool on_device, float thr, int order, int overlap,
                                 int use_prefilter, size_t own_begin, size_t own_end, uint64_t base, bool apply, fac_matches **out,

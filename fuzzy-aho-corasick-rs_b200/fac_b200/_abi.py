@@ -87,12 +87,14 @@ SYMBOLS = [
     ("fac_build_source_hash", C.c_char_p, []),
     ("fac_engine_create", C.c_int, [C.POINTER(fac_config), C.POINTER(fac_pattern), C.c_size_t, C.POINTER(C.c_void_p)]),
     ("fac_engine_create_on", C.c_int, [C.c_int, C.POINTER(fac_config), C.POINTER(fac_pattern), C.c_size_t, C.POINTER(C.c_void_p)]),
+    ("fac_engine_create_multi", C.c_int, [C.POINTER(C.c_int), C.c_size_t, C.POINTER(fac_config), C.POINTER(fac_pattern), C.c_size_t, C.POINTER(C.c_void_p)]),
     ("fac_engine_free", None, [C.c_void_p]),
     ("fac_engine_max_match_graphemes", C.c_size_t, [C.c_void_p]),
     ("fac_engine_prefilter_active", C.c_int, [C.c_void_p]),
     ("fac_engine_num_nodes", C.c_size_t, [C.c_void_p]),
     ("fac_engine_num_patterns", C.c_size_t, [C.c_void_p]),
     ("fac_engine_device", C.c_int, [C.c_void_p]),
+    ("fac_engine_num_devices", C.c_size_t, [C.c_void_p]),
     ("fac_search", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_float, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     ("fac_search_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_float, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     ("fac_last_haystack_graphemes", C.c_uint64, []),

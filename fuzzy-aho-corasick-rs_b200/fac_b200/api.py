@@ -433,6 +433,9 @@ class GpuBackend:
         h = C.c_void_p()
         if device is None:
             st = self.lib.fac_engine_create(C.byref(cfg), pats, n, C.byref(h))
+        elif isinstance(device, (list, tuple)):   # one replica per device: the stream calls deal windows over them
+            devs = (C.c_int * len(device))(*device)
+            st = self.lib.fac_engine_create_multi(devs, len(device), C.byref(cfg), pats, n, C.byref(h))
         else:
             st = self.lib.fac_engine_create_on(device, C.byref(cfg), pats, n, C.byref(h))
         if st != 0:
@@ -686,7 +689,8 @@ class FuzzyAhoCorasickBuilder:
         return self
 
     def device(self, index):
-        """B200 extension: CUDA device to place the automaton on (fac_engine_create_on)."""
+        """B200 extension: CUDA device to place the automaton on (fac_engine_create_on), or a list of devices
+        (fac_engine_create_multi: one replica per device, stream windows are dealt over them)."""
         self._device = index
         return self
 

@@ -145,6 +145,13 @@ fac_status fac_engine_create(const fac_config *cfg, const fac_pattern *patterns,
                              fac_engine **out);
 fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pattern *patterns,
                                 size_t n_patterns, fac_engine **out);
+/* One engine replicated on several CUDA devices (SURVEY 8b `fac_engine_create_on(devices[], n)`, 8e "windows
+ * round-robin over GPUs"): the automaton is built once on the host and uploaded to every device.  The stream entry
+ * points deal their window batches round-robin over the devices (the GPU analogue of search_stream_parallel /
+ * replace_stream_parallel, src/stream.rs:378-429, 533-638) and reassemble the results in stream order; the
+ * whole-haystack entry points use devices[0].  fac_engine_free releases every replica. */
+fac_status fac_engine_create_multi(const int *devices, size_t n_devices, const fac_config *cfg,
+                                   const fac_pattern *patterns, size_t n_patterns, fac_engine **out);
 void fac_engine_free(fac_engine *engine);
 
 /* FuzzyAhoCorasick::max_match_graphemes (src/stream.rs:213-253). */
@@ -155,6 +162,7 @@ int fac_engine_prefilter_active(const fac_engine *engine);
 size_t fac_engine_num_nodes(const fac_engine *engine);
 size_t fac_engine_num_patterns(const fac_engine *engine);
 int fac_engine_device(const fac_engine *engine);
+size_t fac_engine_num_devices(const fac_engine *engine);
 
 /* FuzzyAhoCorasick::search (src/query.rs:30-38) and Prefiltered::search
  * (src/prefilter.rs:135-143) when use_prefilter != 0.  `haystack` is host memory holding
