@@ -8,6 +8,10 @@
 
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -74,6 +78,9 @@ inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b
 
 struct U8ToU32 {
     __host__ __device__ __forceinline__ uint32_t operator()(const uint8_t &v) const { return v; }
+};
+struct U8ToU64 {
+    __host__ __device__ __forceinline__ unsigned long long operator()(const uint8_t &v) const { return v; }
 };
 
 struct SearchStats {
@@ -234,8 +241,12 @@ struct fac_engine {
     int ctas_per_sm = 6;
     int use_tma = 1;
     // bitap pre-filter (fac_bitap.cuh)
-    const uint64_t *d_bp_mask = nullptr;
+    const uint64_t *d_bp_mask = nullptr;      // [P][128] ASCII bytes (case folding baked in)
+    const uint64_t *d_bp_symmask = nullptr;   // [P][alphabet + 1] symbol ids (non-ASCII haystacks)
     const uint8_t *d_bp_m = nullptr;
+    const FacSymbol *d_pf_symbols = nullptr;  // folded grapheme -> pre-filter symbol id (transcode, prefilter.rs:262-281)
+    const uint8_t *d_pf_pool = nullptr;
+    uint32_t pf_mask = 0;
     // succinct-trie fast kernel (fac_succinct.cuh)
     bool succ_ok = false, succ_generic_ok = false;
     const void *d_s_bm = nullptr;   // u32 [N] (narrow) or u64 [N] with bit 63 = has outputs (wide)
@@ -870,10 +881,13 @@ fac_status finalize_and_fetch(Workspace *ws, uint32_t n, const FacWindow *d_wind
 }
 
 // Segment a non-ASCII text range on the device (K1).  Fills ws->first/gid/off and *n_graphemes.
+// Byte offsets are 32-bit for haystacks below 4 GiB and 64-bit above (*wide_out): the reference's limit is the number
+// of graphemes (u32 positions, src/search.rs:198-202, 296-300), not the number of bytes.
 fac_status segment_device(const fac_engine *E, Workspace *ws, const uint8_t *d_text, uint64_t len, bool want_pf, uint64_t *n_graphemes,
-                          SearchStats &stats) {
+                          SearchStats &stats, bool *wide_out) {
     cudaStream_t s = ws->stream;
-    if (len >= 0xFFFFFFF0ull) { set_err("non-ASCII haystacks of 4 GiB or more are not supported by the 32-bit offset streams yet"); return FAC_UNSUPPORTED; }
+    const bool wide = len >= 0xFFFFFFF0ull;
+    *wide_out = wide;
     CKS(ws->misc.ensure(64));
     CK(cudaMemsetAsync(ws->misc.p, 0, 8, s));
     k_validate_utf8<<<cdiv(len, 256), 256, 0, s>>>(d_text, len, ws->misc.as<uint32_t>());
@@ -888,26 +902,39 @@ fac_status segment_device(const fac_engine *E, Workspace *ws, const uint8_t *d_t
         CK(cudaMemsetAsync(ws->mark.as<uint8_t>() + len, 0, 1, s));
         CK(cub::DeviceScan::ExclusiveSum(ws->cubtmp.p, tb, it, ws->gidx.as<uint32_t>(), (int64_t)len + 1, s));
     }
+    if (wide) {  // the 32-bit scan may wrap: the true cluster count decides HaystackTooLarge
+        size_t tb = 0;
+        cub::TransformInputIterator<unsigned long long, U8ToU64, const uint8_t *> it64(ws->mark.as<uint8_t>(), U8ToU64());
+        CK(cub::DeviceReduce::Sum((void *)nullptr, tb, it64, ws->misc.as<unsigned long long>() + 1, (int64_t)len, s));
+        CKS(ws->cubtmp.ensure(tb));
+        CK(cub::DeviceReduce::Sum(ws->cubtmp.p, tb, it64, ws->misc.as<unsigned long long>() + 1, (int64_t)len, s));
+        CK(cudaMemcpyAsync(ws->h_counters, ws->misc.as<unsigned long long>() + 1, 8, cudaMemcpyDeviceToHost, s));
+    }
     CK(cudaMemcpyAsync(ws->h_flags, ws->misc.p, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ws->h_flags + 1, ws->gidx.as<uint32_t>() + len, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     stats.launches += 4;
     if (ws->h_flags[0]) { set_err("haystack is not valid UTF-8"); return FAC_INVALID_UTF8; }
-    const uint64_t n = ws->h_flags[1];
+    const uint64_t n = wide ? ws->h_counters[0] : (uint64_t)ws->h_flags[1];
     *n_graphemes = n;
+    if (n > 0xFFFFFFFFull) return FAC_OK;   // the caller reports SearchError::HaystackTooLarge
     CKS(ws->first.ensure((n + 4) * 4));
-    CKS(ws->off.ensure((n + 4) * 4));
+    CKS(ws->off.ensure((n + 4) * (wide ? 8 : 4)));
     if (E->host.has_mappings) CKS(ws->gid.ensure((n + 4) * 4));
     if (want_pf) CKS(ws->pfsym.ensure(n + 16));
     SegEmitParams P;
     memset(&P, 0, sizeof(P));
     P.s = d_text; P.lo = 0; P.hi = len; P.mark = ws->mark.as<uint8_t>(); P.gidx = ws->gidx.as<uint32_t>(); P.g_base = 0; P.U = E->dU;
     if (E->host.has_mappings) { P.symbols = E->d_symbols; P.sym_mask = E->sym_mask; P.pool = E->d_pool; }
-    P.fold = E->host.ci; P.first = ws->first.as<uint32_t>(); P.gid = ws->gid.as<uint32_t>(); P.off32 = ws->off.as<uint32_t>();
+    if (want_pf) { P.pf_symbols = E->d_pf_symbols; P.pf_mask = E->pf_mask; P.pf_pool = E->d_pf_pool; P.pf_sym = ws->pfsym.as<uint8_t>(); }
+    P.fold = E->host.ci; P.first = ws->first.as<uint32_t>(); P.gid = ws->gid.as<uint32_t>();
+    if (wide) P.off64 = ws->off.as<uint64_t>(); else P.off32 = ws->off.as<uint32_t>();
     k_seg_emit<<<cdiv(len, 256), 256, 0, s>>>(P);
     const uint32_t len32 = (uint32_t)len;
-    CK(cudaMemcpyAsync(ws->off.as<uint32_t>() + n, &len32, 4, cudaMemcpyHostToDevice, s));
-    CK(cudaStreamSynchronize(s));  // len32 is a stack variable
+    const uint64_t len64 = len;
+    if (wide) CK(cudaMemcpyAsync(ws->off.as<uint64_t>() + n, &len64, 8, cudaMemcpyHostToDevice, s));
+    else CK(cudaMemcpyAsync(ws->off.as<uint32_t>() + n, &len32, 4, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));  // the sentinel is a stack variable
     stats.launches++;
     CK(cudaGetLastError());
     return FAC_OK;
@@ -1000,11 +1027,16 @@ bool bitap_k_for(const fac::HostBitap &B, size_t p, float thr, uint32_t &k_out) 
 }
 
 template <int KMAX>
-void launch_bitap_t(const BitapParams &P, dim3 grid, cudaStream_t s) { k_bitap_scan<KMAX><<<grid, BITAP_WARPS * 32, 0, s>>>(P); }
+void launch_bitap_t(const BitapParams &P, dim3 grid, cudaStream_t s) {
+    const size_t smem = (size_t)P.rows * 32 * sizeof(uint64_t);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_bitap_scan<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_bitap_scan<KMAX><<<grid, BITAP_WARPS * 32, smem, s>>>(P);
+}
 
 // Scans, merges and returns the slices (gs, ge) in ascending order.  *fallback = true when a pattern's
 // budget exceeds MAX_USEFUL_K (the reference then runs the plain search).
-fac_status prefilter_slices(const fac_engine *E, Workspace *ws, const uint8_t *d_text, uint32_t n, float thr,
+// `d_stream` = one byte per grapheme: the ASCII haystack itself, or (sym_stream) the K1 symbol-id stream.
+fac_status prefilter_slices(const fac_engine *E, Workspace *ws, const uint8_t *d_stream, bool sym_stream, uint32_t n, float thr,
                             std::vector<std::pair<uint32_t, uint32_t>> &slices, bool *fallback, SearchStats &stats) {
     cudaStream_t s = ws->stream;
     const fac::HostBitap &B = E->host.bitap;
@@ -1027,7 +1059,9 @@ fac_status prefilter_slices(const fac_engine *E, Workspace *ws, const uint8_t *d
     CK(cudaMemsetAsync(ws->cov.p, 0, (size_t)(n_words + 2) * 4, s));
     CK(cudaMemsetAsync(ws->misc.p, 0, 16, s));
     BitapParams BP;
-    BP.text = d_text; BP.n = n; BP.bytemask = E->d_bp_mask; BP.m = E->d_bp_m; BP.k = ws->bp_k.as<uint8_t>();
+    BP.text = d_stream; BP.n = n; BP.m = E->d_bp_m; BP.k = ws->bp_k.as<uint8_t>();
+    if (sym_stream) { BP.bytemask = E->d_bp_symmask; BP.rows = B.alphabet + 1; }
+    else { BP.bytemask = E->d_bp_mask; BP.rows = 128; }
     BP.n_patterns = (uint32_t)P; BP.warm = warm; BP.cov = ws->cov.as<uint32_t>(); BP.hits = ws->misc.as<unsigned long long>();
     const dim3 grid(cdiv(n, (uint64_t)BITAP_SUB * BITAP_WARPS), cdiv(P, 32));
     if (kmax <= 2) launch_bitap_t<2>(BP, grid, s);
@@ -1087,14 +1121,18 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
         stats.launches++;
         ascii = ws->h_flags[0] == 0;
     }
+    // the pre-filter applies to whole-haystack calls of beam-less engines whose configuration reduced to the bit model
+    const bool want_pf = use_prefilter && E->host.bitap.active && own_begin == 0 && own_end >= len && E->host.beam_width == 0 && !E->host.has_auto_beam;
     TextView tv;
     memset(&tv, 0, sizeof(tv));
     tv.n_bytes = len; tv.ascii = ascii;
     uint64_t n = len;
     if (ascii) tv.bytes = d_text;
     else {
-        CKS(segment_device(E, ws, d_text, len, false, &n, stats));
-        tv.first = ws->first.as<uint32_t>(); tv.gid = ws->gid.as<uint32_t>(); tv.off32 = ws->off.as<uint32_t>();
+        bool wide = false;
+        CKS(segment_device(E, ws, d_text, len, want_pf, &n, stats, &wide));
+        tv.first = ws->first.as<uint32_t>(); tv.gid = ws->gid.as<uint32_t>();
+        if (wide) tv.off64 = ws->off.as<uint64_t>(); else tv.off32 = ws->off.as<uint32_t>();
     }
     if (n > 0xFFFFFFFFull) {  // SearchError::HaystackTooLarge, search.rs:198-202
         g_last_graphemes = n;
@@ -1108,11 +1146,18 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
     if (own_begin > 0 || own_end < len) {
         if (ascii) { g_begin = (uint32_t)std::min<uint64_t>(own_begin, n); g_end = (uint32_t)std::min<uint64_t>(own_end, n); }
         else {
-            // first grapheme with offset >= own_begin / own_end: read the offsets back around the cut (small)
-            std::vector<uint32_t> off(n + 1);
-            CK(cudaMemcpy(off.data(), ws->off.p, (n + 1) * 4, cudaMemcpyDeviceToHost));
-            g_begin = (uint32_t)(std::lower_bound(off.begin(), off.begin() + n, (uint32_t)std::min<uint64_t>(own_begin, len)) - off.begin());
-            g_end = (uint32_t)(std::lower_bound(off.begin(), off.begin() + n, (uint32_t)std::min<uint64_t>(own_end, len)) - off.begin());
+            // first grapheme with offset >= own_begin / own_end
+            if (tv.off64) {
+                std::vector<uint64_t> off(n + 1);
+                CK(cudaMemcpy(off.data(), ws->off.p, (n + 1) * 8, cudaMemcpyDeviceToHost));
+                g_begin = (uint32_t)(std::lower_bound(off.begin(), off.begin() + n, std::min<uint64_t>(own_begin, len)) - off.begin());
+                g_end = (uint32_t)(std::lower_bound(off.begin(), off.begin() + n, std::min<uint64_t>(own_end, len)) - off.begin());
+            } else {
+                std::vector<uint32_t> off(n + 1);
+                CK(cudaMemcpy(off.data(), ws->off.p, (n + 1) * 4, cudaMemcpyDeviceToHost));
+                g_begin = (uint32_t)(std::lower_bound(off.begin(), off.begin() + n, (uint32_t)std::min<uint64_t>(own_begin, len)) - off.begin());
+                g_end = (uint32_t)(std::lower_bound(off.begin(), off.begin() + n, (uint32_t)std::min<uint64_t>(own_end, len)) - off.begin());
+            }
         }
     }
     FacWindow w;
@@ -1131,29 +1176,80 @@ fac_status search_resident(const fac_engine *E, Workspace *ws, const uint8_t *d_
         return FAC_OK;
     }
     // Prefiltered::search (src/prefilter.rs:135-155, 304-374): bitap scan -> merged slices -> the engine on every
-    // slice as its own haystack.  Device path for ASCII haystacks of beam-less engines; elsewhere the plain
-    // search below answers (result-neutral by the reference's contract, prefilter.rs:1-21).
-    if (use_prefilter && E->host.bitap.active && ascii && own_begin == 0 && own_end >= len) {
+    // slice as its own haystack.  ASCII haystacks are scanned byte by byte (Offsets::Identity); non-ASCII haystacks
+    // through the symbol-id stream K1 emitted (transcode, prefilter.rs:262-281), slices then are grapheme ranges.
+    // Engines with a beam answer with the plain search (result-neutral by the reference's contract, prefilter.rs:1-21).
+    if (want_pf) {
         std::vector<std::pair<uint32_t, uint32_t>> slices;
         bool fallback = false;
-        CKS(prefilter_slices(E, ws, d_text, (uint32_t)n, thr, slices, &fallback, stats));
+        CKS(prefilter_slices(E, ws, ascii ? d_text : ws->pfsym.as<uint8_t>(), !ascii, (uint32_t)n, thr, slices, &fallback, stats));
         if (!fallback) {
-            const uint32_t tile_w = (E->succ_ok || E->succ_generic_ok) ? E->succ_tile : (E->stack_ok ? E->stack_tile : 64u);
-            size_t si = 0;
-            while (si < slices.size()) {
-                // batches of slices bounded by a window budget so the candidate buffers stay modest
-                ExpandRun R;
-                R.tv = tv; R.d_windows = ws->windows.as<FacWindow>(); R.thr = thr; R.fast = E->fast_ok || (E->succ_generic_ok && ascii); R.slices = &slices;
-                uint64_t wins = 0;
-                const size_t s0 = si;
-                for (; si < slices.size() && wins < (1u << 25); si++) {
-                    const uint32_t gs = slices[si].first, ge = slices[si].second;
-                    for (uint32_t a = gs; a < ge; a += tile_w) R.tiles.push_back(make_uint4(a, std::min(tile_w, ge - a), ge, 0u));
-                    wins += ge - gs;
+            // Per-slice `is_ascii` (prefilter.rs:346-350 -> search.rs:196): an all-ASCII slice of a non-ASCII haystack is
+            // searched with the byte-per-grapheme storage.  That differs from the K1 streams only when the slice holds a
+            // CR LF pair (one cluster in UAX #29, two graphemes as bytes): those slices are searched from the bytes.
+            std::vector<std::pair<uint32_t, uint32_t>> byte_slices;   // (byte begin, byte end) of ASCII slices holding CR LF
+            if (!ascii && !slices.empty()) {
+                const uint32_t ns = (uint32_t)slices.size();
+                CKS(ws->misc.ensure((size_t)ns * 4 + 64));
+                k_slice_classify<<<cdiv((uint64_t)ns * 32, 256), 256, 0, s>>>(d_text, tv.off32, tv.off64, ws->sl_gs.as<uint32_t>(), ws->sl_ge.as<uint32_t>(), ns,
+                                                                             ws->misc.as<uint32_t>());
+                CK(cudaGetLastError());
+                std::vector<uint32_t> fl(ns);
+                CK(cudaMemcpyAsync(fl.data(), ws->misc.p, (size_t)ns * 4, cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                stats.launches++;
+                std::vector<uint32_t> special;
+                for (uint32_t i = 0; i < ns; i++) if (fl[i] == 2u) special.push_back(i);
+                if (!special.empty()) {
+                    // byte ranges of those slices: read the two offsets of each back
+                    std::vector<std::pair<uint32_t, uint32_t>> keep;
+                    for (uint32_t i : special) {
+                        uint64_t b0 = 0, b1 = 0;
+                        if (tv.off64) {
+                            CK(cudaMemcpy(&b0, tv.off64 + slices[i].first, 8, cudaMemcpyDeviceToHost));
+                            CK(cudaMemcpy(&b1, tv.off64 + slices[i].second, 8, cudaMemcpyDeviceToHost));
+                        } else {
+                            uint32_t a0 = 0, a1 = 0;
+                            CK(cudaMemcpy(&a0, tv.off32 + slices[i].first, 4, cudaMemcpyDeviceToHost));
+                            CK(cudaMemcpy(&a1, tv.off32 + slices[i].second, 4, cudaMemcpyDeviceToHost));
+                            b0 = a0; b1 = a1;
+                        }
+                        if (b1 > 0xFFFFFFF0ull) { set_err("an ASCII pre-filter slice lies beyond the 32-bit byte index space"); return FAC_UNSUPPORTED; }
+                        byte_slices.emplace_back((uint32_t)b0, (uint32_t)b1);
+                    }
+                    size_t k = 0;
+                    for (uint32_t i = 0; i < ns; i++) { if (k < special.size() && special[k] == i) { k++; continue; } keep.push_back(slices[i]); }
+                    slices.swap(keep);
                 }
-                R.seg_begin = slices[s0].first; R.seg_end = slices[si - 1].second; R.text_end = (uint32_t)n;
-                CKS(grow_keep(ws->m_a, n_matches * sizeof(WMatch), (n_matches + (1u << 20)) * sizeof(WMatch), s));
-                CKS(expand_and_reduce(E, ws, R, tile_w, &n_matches, stats, nullptr));
+            }
+            auto run_slices = [&](const TextView &stv, const std::vector<std::pair<uint32_t, uint32_t>> &sl, uint32_t stream_len) -> fac_status {
+                const bool s_ascii = stv.ascii != 0;
+                const bool succ_here = (E->succ_ok || E->succ_generic_ok) && (s_ascii || E->host.succ.unicode_text_ok);
+                const uint32_t tile_w = succ_here ? E->succ_tile : (E->stack_ok ? E->stack_tile : 64u);
+                size_t si = 0;
+                while (si < sl.size()) {
+                    // batches of slices bounded by a window budget so the candidate buffers stay modest
+                    ExpandRun R;
+                    R.tv = stv; R.d_windows = ws->windows.as<FacWindow>(); R.thr = thr; R.fast = E->fast_ok || (E->succ_generic_ok && succ_here); R.slices = &sl;
+                    uint64_t wins = 0;
+                    const size_t s0 = si;
+                    for (; si < sl.size() && wins < (1u << 25); si++) {
+                        const uint32_t gs = sl[si].first, ge = sl[si].second;
+                        for (uint32_t a = gs; a < ge; a += tile_w) R.tiles.push_back(make_uint4(a, std::min(tile_w, ge - a), ge, 0u));
+                        wins += ge - gs;
+                    }
+                    R.seg_begin = sl[s0].first; R.seg_end = sl[si - 1].second; R.text_end = stream_len;
+                    CKS(grow_keep(ws->m_a, n_matches * sizeof(WMatch), (n_matches + (1u << 20)) * sizeof(WMatch), s));
+                    CKS(expand_and_reduce(E, ws, R, tile_w, &n_matches, stats, nullptr));
+                }
+                return FAC_OK;
+            };
+            CKS(run_slices(tv, slices, (uint32_t)n));
+            if (!byte_slices.empty()) {
+                TextView btv;
+                memset(&btv, 0, sizeof(btv));
+                btv.bytes = d_text; btv.n_bytes = len; btv.n = (uint32_t)std::min<uint64_t>(len, 0xFFFFFFF0ull); btv.ascii = 1;
+                CKS(run_slices(btv, byte_slices, btv.n));
             }
             uint32_t n_final = (uint32_t)n_matches;
             if (apply) CKS(apply_device(E, ws, (uint32_t)n_matches, order, overlap, 1, &n_final, stats));
@@ -1277,6 +1373,11 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
         }
         if ((st = upload(E, bm, &E->d_bp_mask)) != FAC_OK) return fail(st);
         if ((st = upload(E, mm, &E->d_bp_m)) != FAC_OK) return fail(st);
+        if ((st = upload(E, B.masks, &E->d_bp_symmask)) != FAC_OK) return fail(st);
+        const fac::HostSymbol *psy; const uint8_t *ppool;
+        if ((st = upload(E, B.symbols, &psy)) != FAC_OK) return fail(st);
+        if ((st = upload(E, B.symbol_pool, &ppool)) != FAC_OK) return fail(st);
+        E->d_pf_symbols = (const FacSymbol *)psy; E->pf_mask = (uint32_t)B.symbols.size() - 1; E->d_pf_pool = ppool;
     }
     if (H.succ.ok) {
         const fac::HostSuccinct &S = H.succ;

@@ -1,4 +1,8 @@
-// fac_bitap.cuh -- K2: the bitap pre-filter of src/prefilter.rs on the device (ASCII haystacks).
+// fac_bitap.cuh -- K2: the bitap pre-filter of src/prefilter.rs on the device.
+//
+// The scan runs over a stream of one byte per grapheme: the haystack bytes themselves for an ASCII haystack
+// (Offsets::Identity, prefilter.rs:253-260) or the symbol-id stream K1 emits for a non-ASCII one (`transcode`,
+// prefilter.rs:262-281: id of the folded grapheme in the filter's symbol table, 0 = other).
 //
 // BitapFilter::search_unsorted (prefilter.rs:304-374) scans the haystack once PER PATTERN with a
 // Wu-Manber shift-AND automaton of k+1 u64 rows (bitap_windows, :410-435), pushes the candidate
@@ -27,9 +31,10 @@
 #define BITAP_WARPS 8u
 
 struct BitapParams {
-    const uint8_t *text;          // ASCII haystack
-    uint32_t n;                   // graphemes (== bytes)
-    const uint64_t *bytemask;     // [P][128]: mask of the (case-folded) byte for pattern p, prefilter.rs:210-231
+    const uint8_t *text;          // ASCII haystack bytes, or the K1 symbol-id stream of a non-ASCII haystack
+    uint32_t n;                   // graphemes (== stream bytes)
+    const uint64_t *bytemask;     // [P][rows]: mask of stream byte b for pattern p, prefilter.rs:210-231
+    uint32_t rows;                // 128 (ASCII bytes, case folding baked in) or alphabet + 1 (symbol ids)
     const uint8_t *m;             // [P] pattern length in graphemes (1..63)
     const uint8_t *k;             // [P] edit budget of this call (k_for, prefilter.rs:285-302)
     uint32_t n_patterns;
@@ -49,13 +54,14 @@ __device__ __forceinline__ void bitap_mark(uint32_t *cov, uint32_t s, uint32_t e
 
 template <int KMAX>
 __global__ void __launch_bounds__(BITAP_WARPS * 32) k_bitap_scan(const BitapParams P) {
-    __shared__ uint64_t s_mask[128 * 32];  // [byte][lane]
+    extern __shared__ __align__(16) uint64_t s_mask[];  // [rows][lane]
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t p = blockIdx.y * 32u + lane;
     const bool live = p < P.n_patterns;
-    for (uint32_t i = threadIdx.x; i < 128u * 32u; i += blockDim.x) {
+    const uint32_t rows = P.rows;
+    for (uint32_t i = threadIdx.x; i < rows * 32u; i += blockDim.x) {
         const uint32_t b = i >> 5, l = i & 31u, pp = blockIdx.y * 32u + l;
-        s_mask[i] = pp < P.n_patterns ? P.bytemask[(size_t)pp * 128u + b] : 0ull;
+        s_mask[i] = pp < P.n_patterns ? P.bytemask[(size_t)pp * rows + b] : 0ull;
     }
     __syncthreads();
     const uint32_t m = live ? P.m[p] : 1u, k = live ? P.k[p] : 0u;
@@ -71,7 +77,7 @@ __global__ void __launch_bounds__(BITAP_WARPS * 32) k_bitap_scan(const BitapPara
     for (int d = 0; d <= KMAX; d++) r[d] = (1ull << d) - 1ull;  // prefilter.rs:416-418
     uint32_t n_hits = 0;
     auto step = [&](uint32_t c, uint32_t i) {
-        const uint64_t bc = s_mask[(c & 127u) * 32u + lane];
+        const uint64_t bc = s_mask[min(c, rows - 1u) * 32u + lane];
         nr[0] = ((r[0] << 1) | 1ull) & bc;
         uint64_t rk = nr[0];
 #pragma unroll
@@ -133,3 +139,23 @@ struct CovCountToU64 {
         return (unsigned long long)(c & 0xFFFFu) | ((unsigned long long)(c >> 16) << 32);
     }
 };
+
+// Per merged slice of a non-ASCII haystack: bit 0 = the slice holds a non-ASCII byte, bit 1 = it holds a "\r\n" pair.
+// The reference searches every slice as its own haystack and re-tests `is_ascii` per slice (prefilter.rs:346-350,
+// search.rs:196): an all-ASCII slice uses the byte-per-grapheme storage, where CR LF are two graphemes instead of the
+// one cluster of UAX #29 -- the only case in which the two storages segment ASCII text differently.
+__global__ void __launch_bounds__(256) k_slice_classify(const uint8_t *__restrict__ text, const uint32_t *__restrict__ off32, const uint64_t *__restrict__ off64,
+                                                        const uint32_t *__restrict__ gs, const uint32_t *__restrict__ ge, uint32_t n_slices,
+                                                        uint32_t *__restrict__ flags) {
+    const uint32_t sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (sl >= n_slices) return;
+    const uint64_t b0 = off64 ? off64[gs[sl]] : (uint64_t)off32[gs[sl]], b1 = off64 ? off64[ge[sl]] : (uint64_t)off32[ge[sl]];
+    uint32_t f = 0;
+    for (uint64_t i = b0 + lane; i < b1; i += 32u) {
+        const uint8_t c = text[i];
+        if (c & 0x80u) f |= 1u;
+        if (c == '\r' && i + 1 < b1 && text[i + 1] == '\n') f |= 2u;
+    }
+    f = __reduce_or_sync(0xFFFFFFFFu, f);
+    if (lane == 0) flags[sl] = f;
+}

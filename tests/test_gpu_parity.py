@@ -318,6 +318,84 @@ def test_prefilter_fuzz_ascii(oracle, gpu, monkeypatch):
     assert used > 50
 
 
+def test_prefilter_non_ascii_haystack_per_slice_is_ascii(oracle, gpu):
+    # K2 on a non-ASCII haystack: the bitap scan runs over K1's symbol-id stream (transcode, prefilter.rs:262-281) and
+    # every merged slice is searched as its own haystack with its own is_ascii test (prefilter.rs:346-350, quirk Q8):
+    # the all-ASCII slice around "abcd\r\nefgh" uses byte graphemes (CR, LF = two insertions), while the plain search
+    # of the whole (non-ASCII) haystack sees one CR LF cluster (one insertion).  The reference is not self-consistent
+    # here and neither are we: pre-filtered GPU == pre-filtered oracle != plain search.
+    mk = lambda b: FuzzyAhoCorasickBuilder.new(b).fuzzy(FuzzyLimits.new().edits(2)).build(["abcdefgh", "zebra"])
+    eo, eg = mk(oracle), mk(gpu)
+    text = "lorem ipsum abcd\r\nefgh dolor sit amet " + "x" * 40 + " caf\u00e9 zebra"
+    opts = SearchOptions.new().threshold(0.7)
+    assert eg.with_prefilter().is_active()
+    o, g = eo.with_prefilter().search(text, opts), eg.with_prefilter().search(text, opts)
+    assert o.tuples() == g.tuples()
+    assert any(m.insertions == 2 for m in g)                      # the ASCII-storage reading of the slice
+    plain = eg.search(text, opts)
+    assert plain.tuples() == eo.search(text, opts).tuples()
+    assert plain.tuples() != g.tuples()                           # i.e. the device pre-filter really ran
+    # randomized: ASCII-alphabet and Unicode engines over haystacks sprinkled with accents, CJK, CR LF, emoji
+    r = random.Random(77 + SEED)
+    extra = ["\u00e9", "e\u0301", "\u4e2d\u6587", "\U0001F600", "\r\n", "\u00df", "\r\n\r\n", "\u00c9", "\u043c\u043e\u0441\u043a\u0432\u0430"]
+    words = ["vestibulum", "consectetur", "moskva", "\u043c\u043e\u0441\u043a\u0432\u0430", "na\u00efve", "stra\u00dfe", "lorem", "ipsum", "dolor"]
+    used = 0
+    for t in range(60):
+        pats = r.sample(words, r.randrange(1, 5))
+        ci = r.random() < 0.5
+        edits = r.choice([1, 1, 2])
+        mk = lambda b: FuzzyAhoCorasickBuilder.new(b).fuzzy(FuzzyLimits.new().edits(edits)).case_insensitive(ci).build(pats)
+        eo, eg = mk(oracle), mk(gpu)
+        parts = []
+        for _ in range(r.randrange(5, 60)):
+            w = r.choice(words + ["foo", "bar", "quux", "zzz", "amet"])
+            if r.random() < 0.3 and len(w) > 3:
+                k = r.randrange(1, len(w) - 1)
+                w = r.choice([w[:k] + w[k + 1:], w[:k] + "\r\n" + w[k:], w[:k] + "q" + w[k:], w.upper()])
+            parts.append(w)
+            parts.append(r.choice([" ", " ", "  ", "\r\n", ", "]) if r.random() < 0.8 else r.choice(extra))
+        hay = "".join(parts) + r.choice(extra)
+        thr = r.choice([0.6, 0.7, 0.8, 0.9])
+        order, overlap = r.choice(ALL_OPTS)
+        opts = SearchOptions(thr, order, overlap)
+        assert eo.with_prefilter().is_active() == eg.with_prefilter().is_active()
+        used += eg.with_prefilter().is_active()
+        assert eo.with_prefilter().search(hay, opts).tuples() == eg.with_prefilter().search(hay, opts).tuples(), (t, pats, ci, edits, thr, hay)
+    assert used > 30
+
+
+def test_non_ascii_haystack_beyond_4GiB_bytes(gpu, oracle):
+    # the reference's limit is graphemes (u32 positions, search.rs:198-202, 296-300), not bytes: a 4 GiB + 64 MiB UTF-8
+    # haystack with non-ASCII graphemes is segmented with 64-bit byte offsets and searched; matches planted beyond
+    # 2^32 bytes come back with their absolute offsets
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    n = (1 << 32) + (64 << 20)
+    if free < 110 * (1 << 30):
+        pytest.skip("needs ~100 GiB of device memory for the 4 GiB grapheme streams")
+    pats = ["vestibulum", "tincidunt"]
+    mk = lambda b: FuzzyAhoCorasickBuilder.new(b).fuzzy(FuzzyLimits.new().edits(1)).build(pats)
+    eg, eo = mk(gpu), mk(oracle)
+    dev = torch.full((n,), ord("z"), dtype=torch.uint8, device="cuda")
+    plants = [(1000, "caf\u00e9 vestibulum "), ((1 << 32) - 7, " vestibulm t\u00efncidunt "), ((1 << 32) + (48 << 20) + 3, " \u4e2d tincidunt\r\n")]
+    for pos, txt in plants:
+        b = txt.encode("utf-8")
+        dev[pos:pos + len(b)] = torch.tensor(list(b), dtype=torch.uint8, device="cuda")
+    arr, st = gpu.search_device(eg._h, dev.data_ptr(), n, 0.8, 0, 0, False)
+    got = sorted((m.start, m.end, m.pattern_index, C.c_uint32.from_buffer(C.c_float(m.similarity)).value, m.insertions, m.deletions,
+                  m.substitutions, m.swaps) for m in arr)
+    want = []
+    for pos, txt in plants:
+        lo = pos - 32
+        sl = bytes(dev[lo:pos + 96].cpu().numpy())
+        o, _ = oracle.search(eo._h, sl, 0.8, 0, 0, False)
+        want += [(m.start + lo, m.end + lo, m.pattern_index, C.c_uint32.from_buffer(C.c_float(m.similarity)).value, m.insertions, m.deletions,
+                  m.substitutions, m.swaps) for m in o]
+    assert len(want) >= 4 and max(w[0] for w in want) > (1 << 32)
+    assert got == sorted(want)
+    del dev
+
+
 @pytest.mark.parametrize("faithful", [True, False])
 def test_cfg1_prefilter_parity(oracle, gpu, faithful, monkeypatch):
     monkeypatch.setenv("FAC_FAITHFUL", "1" if faithful else "0")

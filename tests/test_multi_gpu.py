@@ -223,3 +223,32 @@ def test_sharded_search_world2_nccl():
         pytest.skip("needs 2 GPUs")
     _run(2, "gpu")
     _run(2, "gpu", "dense")
+
+
+@pytest.mark.gpu
+def test_stream_windows_dealt_over_devices(gpu, oracle):
+    """fac_engine_create_multi + the stream pipeline (search_stream_parallel / replace_stream_parallel,
+    src/stream.rs:378-429, 533-638): window batches dealt over every visible device (a single-device list on 1-GPU
+    boxes still runs the threaded pipeline), results reassembled in stream order == the oracle's sequential stream."""
+    import io
+    import torch
+    from fac_b200 import FuzzyAhoCorasickBuilder, FuzzyLimits, workload
+    ndev = torch.cuda.device_count()
+    devices = list(range(min(ndev, 4)))
+    cfg = workload.cfg5(total=3 << 20, n_pairs=200, block=1 << 19, auto_beam=None)
+    mk = lambda be, dev: (FuzzyAhoCorasickBuilder.new(be).fuzzy(FuzzyLimits.new().edits(1)).case_insensitive(True)
+                          .device(dev) if dev is not None else
+                          FuzzyAhoCorasickBuilder.new(be).fuzzy(FuzzyLimits.new().edits(1)).case_insensitive(True)).build_replacer(cfg["pairs"])
+    rg, ro = mk(gpu, devices), mk(oracle, None)
+    assert gpu.lib.fac_engine_num_devices(rg.engine()._h) == len(devices)
+    outs = []
+    for rep in (rg, ro):
+        sink = io.BytesIO()
+        rep.replace_stream(workload.BlockReader(cfg["block"], cfg["total"], max_read=50000), sink, 0.8)
+        outs.append(sink.getvalue())
+    assert outs[0] == outs[1]
+    assert len(outs[0]) != cfg["total"]     # replacements happened
+    got, want = [], []
+    rg.engine().search_stream(workload.BlockReader(cfg["block"], cfg["total"]), 0.8, lambda m: got.append((m.start, m.end, m.pattern_index)))
+    ro.engine().search_stream(workload.BlockReader(cfg["block"], cfg["total"]), 0.8, lambda m: want.append((m.start, m.end, m.pattern_index)))
+    assert got == want and len(got) > 100
