@@ -94,6 +94,7 @@ struct SearchStats {
 struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, evk0 = nullptr, evk1 = nullptr;
+    DBuf flat_n, flat_e;
     DBuf hay, mark, gidx, first, gid, off, pfsym, srec, cov, covcnt, covoff, sl_gs, sl_ge, bp_k;
     DBuf queue, nxt, hslot, gtab_rep, gtab_head, gtab_min;
     uint32_t grid = 0, qcap = 0, gtab_size = 0;
@@ -110,7 +111,7 @@ struct Workspace {
         return FAC_OK;
     }
     void destroy() {
-        for (DBuf *b : {&hay, &mark, &gidx, &first, &gid, &off, &pfsym, &srec, &cov, &covcnt, &covoff, &sl_gs, &sl_ge, &bp_k, &queue, &nxt, &hslot, &gtab_rep, &gtab_head, &gtab_min, &cands, &counters,
+        for (DBuf *b : {&flat_n, &flat_e, &hay, &mark, &gidx, &first, &gid, &off, &pfsym, &srec, &cov, &covcnt, &covoff, &sl_gs, &sl_ge, &bp_k, &queue, &nxt, &hslot, &gtab_rep, &gtab_head, &gtab_min, &cands, &counters,
                         &failed_tiles, &failed_bitmap, &tiles, &best_rep, &best_val, &cslot, &tab_sim, &tab_cmin, &tab_cmax, &tab_first, &dirty, &m_a, &m_b, &idx_a, &idx_b, &winend, &st_a, &st_b,
                         &flags8, &sel, &nsel, &outm, &keep8, &windows, &misc, &cubtmp, &used})
             b->release();
@@ -258,6 +259,7 @@ struct fac_engine {
     const uint32_t *d_s_node_lim = nullptr;
     uint32_t succ_nt = 1024, succ_tile = 4096, succ_stack = 0, succ_min_stack = 64;
     int smem_optin = 0;
+    const uint32_t *d_flat_nrec = nullptr, *d_flat_erec = nullptr;   // static parts of the merged records (fac_flat.h)
     bool stack_ok = false;          // general stack-machine kernel (fac_stack.cuh) for fast engines outside the succinct domain
     uint32_t stack_cap = 384, stack_tile = 1024;
     bool fast_ok = false;  // FAST kernel allowed (fast-path edit ceiling, no beam); FAC_FAITHFUL=1 forces the order-faithful kernel
@@ -417,9 +419,16 @@ size_t stack_smem_bytes(const fac_engine *E, bool ascii, uint32_t text_cap) {
     const size_t mult = (!ascii && E->host.has_mappings) ? 2 : 1;
     return tb * mult + (size_t)(STK_THREADS / 32) * (E->stack_cap + STK_WQ_CAP) * 16;
 }
-fac_status launch_stack(const fac_engine *E, const ExpandParams &P, uint32_t *dirty, uint32_t n_tiles, cudaStream_t s) {
+fac_status launch_stack(const fac_engine *E, Workspace *ws, const ExpandParams &P, uint32_t *dirty, uint32_t n_tiles, cudaStream_t s) {
+    const uint32_t N = E->host.n_nodes(), NE = (uint32_t)E->host.edge_char.size();
+    CKS(ws->flat_n.ensure((size_t)std::max<uint32_t>(N, 1) * 16));
+    CKS(ws->flat_e.ensure((size_t)std::max<uint32_t>(NE, 1) * 16));
+    k_flat_prepare_nodes<<<cdiv(N, 256), 256, 0, s>>>((const uint4 *)E->d_flat_nrec, E->dview.node_prune_len, E->dview.node_prune_low, P.thr, N, ws->flat_n.as<uint4>());
+    if (NE) k_flat_prepare_edges<<<cdiv(NE, 256), 256, 0, s>>>((const uint4 *)E->d_flat_erec, ws->flat_n.as<uint4>(), NE, ws->flat_e.as<uint4>());
+    CK(cudaGetLastError());
     StackParams SP;
     SP.E = P; SP.stack_cap = E->stack_cap; SP.dirty = dirty;
+    SP.F.nrec = ws->flat_n.as<FlatRec>(); SP.F.erec = ws->flat_e.as<FlatRec>();
     SP.feed_below = 32u;
     const bool ascii = P.tv.ascii != 0, mapp = P.A.has_mappings != 0;
     const size_t smem = stack_smem_bytes(E, ascii, P.smem_text_cap);
@@ -569,7 +578,7 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
             CKS(launch_succinct(E, ws, R.tv, R.thr, R.seg_begin, R.seg_end, R.text_end, ws->cands.as<FacCand>(), cand_cap, s,
                                 explicit_tiles ? ws->tiles.as<uint4>() : nullptr, n_tiles));
             stats.launches++;
-        } else if (use_stack) CKS(launch_stack(E, P, ws->dirty.as<uint32_t>(), n_tiles, s));
+        } else if (use_stack) { CKS(launch_stack(E, ws, P, ws->dirty.as<uint32_t>(), n_tiles, s)); stats.launches += 2; }
         else CKS(launch_expand(P, grid, smem, s, fast_run));
         CK(cudaEventRecord(ws->evk1, s));
         stats.launches++;
@@ -1443,7 +1452,11 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
     // only through the succinct kernel (exact-chain shortcut / limits mode)
     E->succ_generic_ok = H.succ.ok && (H.succ.exact_only || H.succ.limits_mode) && H.beam_width == 0 && !H.has_auto_beam && env_int("FAC_FAITHFUL", 0) == 0 &&
                     env_int("FAC_SUCCINCT", 1) != 0;
-    E->stack_ok = E->fast_ok && env_int("FAC_STACK", 1) != 0;
+    if (H.flat_ok) {
+        if ((st = upload(E, H.flat_nrec, &E->d_flat_nrec)) != FAC_OK) return fail(st);
+        if ((st = upload(E, H.flat_erec, &E->d_flat_erec)) != FAC_OK) return fail(st);
+    }
+    E->stack_ok = E->fast_ok && H.flat_ok && env_int("FAC_STACK", 1) != 0;
     E->stack_cap = (uint32_t)std::min(2048, std::max(64, env_int("FAC_STACK_CAP", 384)));
     E->stack_tile = (uint32_t)std::min(4096, std::max(32, env_int("FAC_STACK_TILE", 1024)));
     E->succ_nt = (uint32_t)env_int("FAC_SUCC_THREADS", 1024);

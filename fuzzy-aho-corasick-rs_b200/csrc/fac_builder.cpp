@@ -570,6 +570,22 @@ fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_
         }
     }
 
+    // ---- merged records for the general stack-machine kernel (fac_flat.h) ----
+    {
+        A.flat_ok = true;
+        A.flat_nrec.assign(N * 4, 0); A.flat_erec.assign(A.edge_char.size() * 4, 0);
+        for (size_t i = 0; i < N && A.flat_ok; i++) {
+            const uint32_t deg = A.node_edge_off[i + 1] - A.node_edge_off[i], no = A.node_out_off[i + 1] - A.node_out_off[i];
+            const uint32_t nm = A.node_map_off[i + 1] - A.node_map_off[i];
+            if (deg > 4095u || no > 1023u || nm > 1023u) { A.flat_ok = false; break; }
+            A.flat_nrec[i * 4 + 0] = A.node_edge_off[i]; A.flat_nrec[i * 4 + 1] = deg | (no << 12) | (nm << 22);
+            A.flat_nrec[i * 4 + 3] = A.node_out_off[i];
+        }
+        for (size_t e = 0; e < A.edge_char.size(); e++) {
+            A.flat_erec[e * 4 + 0] = A.edge_next[e]; A.flat_erec[e * 4 + 1] = A.edge_char[e]; A.flat_erec[e * 4 + 2] = A.edge_sym[e];
+        }
+    }
+
     // ---- max_match_graphemes (src/stream.rs:213-253) ----
     {
         size_t max_pattern = 0, max_edits = 0;

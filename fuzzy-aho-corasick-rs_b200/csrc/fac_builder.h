@@ -126,6 +126,9 @@ struct HostAutomaton {
     std::vector<HostPattern> patterns;
     HostBitap bitap;
     HostSuccinct succ;
+    // merged 16-byte records of the general stack-machine kernel (fac_flat.h); flat_ok = the packed fields fit
+    bool flat_ok = false;
+    std::vector<uint32_t> flat_nrec, flat_erec;   // 4 words per node / edge (ceilings are filled per call)
 
     uint32_t n_nodes() const { return (uint32_t)node_prune_len.size(); }
     // View over the host vectors (used by the CPU-side emulator in tests).

@@ -4,9 +4,9 @@
 // (src/search.rs:883-923), multi-byte / non-ASCII pattern graphemes (src/structs.rs:452-519), alphabets of
 // more than 63 symbols, similarity tables with non-ASCII members -- the Unicode workload (cfg3).
 //
-// Same execution shape as k_expand_succinct (fac_succinct.cuh), with the per-state arithmetic of fac_core.h
-// (fac_make_ctx / fac_eval_slot: every potential child of a state is a numbered slot) over the flattened CSR
-// automaton instead of the succinct trie:
+// Same execution shape as k_expand_succinct (fac_succinct.cuh), with the slot formulation of fac_core.h (every
+// potential child of a state is a numbered slot) over merged 16-byte node / edge records (fac_flat.h: one record
+// load per state, one per child) instead of the succinct trie:
 //
 //   * persistent CTAs, tiles of start windows fetched with one atomicAdd per tile; the tile's grapheme
 //     stream (folded first chars, + grapheme ids for engines with mappings, or the haystack bytes) staged
@@ -26,6 +26,7 @@
 // maximum similarity with tie detection (fac_fastreduce.cuh); tied windows and windows whose states did not fit
 // the warp stack are redone by the order-faithful kernel (k_expand).  No global-memory frontier.
 #pragma once
+#include "fac_flat.h"
 #include "fac_kernels.cuh"
 
 #define STK_WQ_CAP 96u
@@ -33,18 +34,37 @@
 
 struct StackParams {
     ExpandParams E;
+    FlatView F;           // per-call merged records (k_flat_prepare)
     uint32_t stack_cap;   // states per warp stack
     uint32_t feed_below;  // a new root is fed while fewer than this many states are stacked
     uint32_t *dirty;      // bitmap over start windows (bit start - E.seg_begin): a state of the window did not fit
 };
 
-template <class Text>
-__device__ __forceinline__ uint32_t stk_walk(const ExpandParams &P, const Text &T, uint32_t start, uint32_t text_end, uint4 q, uint32_t tile,
-                                             uint32_t tag) {
-    FacState c;
-    c.node = q.x; c.pen = __uint_as_float(q.y); c.cnt = q.z; c.pos = q.w;
-    return fac_walk_exhausted(P, T, start, text_end, c, tile, tag);
+// per-call records: node ceiling = prune_len - prune_len_over_weight * threshold (search.rs:638-642, exact f32 ops);
+// an edge record carries the ceiling of its child so that a doomed child is never pushed
+__global__ void __launch_bounds__(256) k_flat_prepare_nodes(const uint4 *__restrict__ stat, const float *__restrict__ plen, const float *__restrict__ plow,
+                                                            float thr, uint32_t n, uint4 *__restrict__ nrec) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 v = stat[i];
+    v.z = __float_as_uint(__fsub_rn(plen[i], __fmul_rn(plow[i], thr)));
+    nrec[i] = v;
 }
+__global__ void __launch_bounds__(256) k_flat_prepare_edges(const uint4 *__restrict__ stat, const uint4 *__restrict__ nrec, uint32_t n, uint4 *__restrict__ erec) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 v = stat[i];
+    v.w = nrec[v.x & 0x7FFFFFFFu].z;
+    erec[i] = v;
+}
+
+struct StkEmit {
+    const ExpandParams *P;
+    uint32_t tile, tag;
+    __device__ __forceinline__ void operator()(uint32_t sg, uint32_t eg, uint32_t pat, float sim, uint32_t cnt) const {
+        fac_emit_cand(*P, sg, eg, pat, sim, cnt, 0u, tile, tag);
+    }
+};
 
 template <bool ASCII, bool MAPP>
 __global__ void __launch_bounds__(STK_THREADS) k_expand_stack(const __grid_constant__ StackParams SP) {
@@ -54,6 +74,7 @@ __global__ void __launch_bounds__(STK_THREADS) k_expand_stack(const __grid_const
     constexpr uint32_t NW = STK_THREADS / 32;
     const ExpandParams &P = SP.E;
     const AutomatonView &A = P.A;
+    const FlatView F = SP.F;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
@@ -130,8 +151,9 @@ __global__ void __launch_bounds__(STK_THREADS) k_expand_stack(const __grid_const
             uint32_t b0 = 0, total = 0;    // item rounds of the current pop
             uint32_t off = 0;              // exclusive prefix of the lanes' slot counts
             bool more = true, fed = false;
-            FacCtx C;
-            C.node = C.cnt = C.pos = C.flags = C.nslots = 0; C.exact = FAC_NONE; C.pen = 0.f;
+            FlatCtx C;
+            C.node = C.cnt = C.pos = C.eoff = C.shape = C.nslots = 0; C.exact = FAC_NONE; C.pen = 0.f;
+            const StkEmit emit{&P, t, win_tag};
             for (;;) {
                 __syncwarp();
                 // (1) exhausted children: exact transitions only, 32 at a time
@@ -139,7 +161,9 @@ __global__ void __launch_bounds__(STK_THREADS) k_expand_stack(const __grid_const
                     const uint32_t n = min(wn, 32u);
                     if (lane < n) {
                         const uint4 q = wq[wn - n + lane];
-                        n_states += stk_walk(P, T, tile_start + (q.w >> FAC_POS_W_SHIFT), text_end, q, t, win_tag);
+                        FacState c;
+                        c.node = q.x; c.pen = __uint_as_float(q.y); c.cnt = q.z; c.pos = q.w;
+                        n_states += flat_walk(A, F, T, P.thr, emit, tile_start + (q.w >> FAC_POS_W_SHIFT), text_end, c);
                     }
                     wn -= n;
                     continue;
@@ -155,13 +179,14 @@ __global__ void __launch_bounds__(STK_THREADS) k_expand_stack(const __grid_const
                         const uint32_t v = __shfl_sync(0xFFFFFFFFu, off, cand & 31u);
                         if (cand < 32u && v <= it) lo = cand;
                     }
-                    FacCtx O;
+                    FlatCtx O;
                     O.node = __shfl_sync(0xFFFFFFFFu, C.node, lo);
                     O.pen = __shfl_sync(0xFFFFFFFFu, C.pen, lo);
                     O.cnt = __shfl_sync(0xFFFFFFFFu, C.cnt, lo);
                     O.pos = __shfl_sync(0xFFFFFFFFu, C.pos, lo);
                     O.exact = __shfl_sync(0xFFFFFFFFu, C.exact, lo);
-                    O.flags = __shfl_sync(0xFFFFFFFFu, C.flags, lo);
+                    O.eoff = __shfl_sync(0xFFFFFFFFu, C.eoff, lo);
+                    O.shape = __shfl_sync(0xFFFFFFFFu, C.shape, lo);
                     O.nslots = 0;
                     const uint32_t r = it - __shfl_sync(0xFFFFFFFFu, off, lo);
                     FacState c;
@@ -169,9 +194,7 @@ __global__ void __launch_bounds__(STK_THREADS) k_expand_stack(const __grid_const
                     bool ok = false;
                     if (it < total) {
                         const uint32_t start = tile_start + (O.pos >> FAC_POS_W_SHIFT);
-                        ok = fac_eval_slot(A, T, P.maxpen, start, text_end, O, r, c);
-                        // the child would be dropped by the node ceiling when popped (search.rs:638-642)
-                        if (ok && fac_over_ceiling(A, c.node, c.pen, P.thr)) ok = false;
+                        ok = flat_eval_slot(A, F, T, P.maxpen, start, text_end, O, r, c);
                     }
                     const bool exhausted = (int)fac_edits_of(c.cnt) >= A.mef;
                     const bool to_walk = ok && exhausted, to_stack = ok && !exhausted;
@@ -216,12 +239,15 @@ __global__ void __launch_bounds__(STK_THREADS) k_expand_stack(const __grid_const
                 S.node = 0; S.pen = 0.f; S.cnt = 0; S.pos = 0;
                 if (has) { const uint4 sv = stk[top - 1u - lane]; S.node = sv.x; S.pen = __uint_as_float(sv.y); S.cnt = sv.z; S.pos = sv.w; }
                 const uint32_t start = tile_start + (S.pos >> FAC_POS_W_SHIFT);
-                const bool live = has && !fac_over_ceiling(A, S.node, S.pen, P.thr);
+                FlatRec nr;
+                nr.x = nr.y = nr.w = 0u; nr.z = 0xFF800000u;   // -inf ceiling: not live
+                if (has) { const uint4 v = reinterpret_cast<const uint4 *>(F.nrec)[S.node]; nr.x = v.x; nr.y = v.y; nr.z = v.z; nr.w = v.w; }
+                const bool live = has && !(S.pen > __uint_as_float(nr.z));   // node ceiling, search.rs:638-642
                 const bool last = (int)fac_edits_of(S.cnt) + 1 >= A.mef;
-                C.nslots = 0; C.flags = 0; C.exact = FAC_NONE;
-                if (live) fac_make_ctx(A, T, P.maxpen, start, text_end, S, C);
+                C.nslots = 0; C.shape = 0; C.exact = FAC_NONE;
+                if (live) flat_make_ctx(A, F, T, P.maxpen, start, text_end, S, nr, C);
                 // stack pushes of this state in the worst case: a state on its last edit keeps only its exact child
-                const uint32_t ub = !live ? 0u : (last ? ((C.flags & FAC_F_EXACT) ? 1u : 0u) : C.nslots);
+                const uint32_t ub = !live ? 0u : (last ? ((C.shape & FLAT_F_EXACT) ? 1u : 0u) : C.nslots);
                 uint32_t n_pop = navail;
                 if (__any_sync(0xFFFFFFFFu, ub > 1u)) {
                     uint32_t incl = ub;
@@ -247,12 +273,12 @@ __global__ void __launch_bounds__(STK_THREADS) k_expand_stack(const __grid_const
                 top -= n_pop;
                 if (active) {
                     n_states++;
-                    const uint32_t o1 = A.node_out_off[S.node + 1];
-                    for (uint32_t o = A.node_out_off[S.node]; o < o1; o++) {   // outputs, search.rs:659-737
-                        const uint32_t pat = A.out_pat[o];
-                        float sim;
-                        if (fac_eval_output(A, P.thr, pat, S.pen, S.cnt, sim))
-                            fac_emit_cand(P, start, start + (S.pos & FAC_POS_MASK), pat, sim, S.cnt, 0u, t, win_tag);
+                    const uint32_t no = flat_nout(nr);
+                    for (uint32_t o = 0; o < no; o++) {   // outputs, search.rs:659-737 (`edits > MAX_EDITS_FAST` never holds)
+                        const uint32_t pat = A.out_pat[nr.w + o];
+                        const float total = A.pat_glen[pat];
+                        const float sim = __fmul_rn(__fdiv_rn(__fsub_rn(total, S.pen), total), A.pat_weight[pat]);   // search.rs:698-699
+                        if (!(sim < P.thr)) emit(start, start + (S.pos & FAC_POS_MASK), pat, sim, S.cnt);
                     }
                 }
                 const uint32_t n_items = active ? C.nslots : 0u;

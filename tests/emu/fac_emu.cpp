@@ -15,6 +15,7 @@
 
 #include "../../fuzzy-aho-corasick-rs_b200/csrc/fac_builder.h"
 #include "../../fuzzy-aho-corasick-rs_b200/csrc/fac_core.h"
+#include "../../fuzzy-aho-corasick-rs_b200/csrc/fac_flat.h"
 #include "../../fuzzy-aho-corasick-rs_b200/csrc/fac_succinct.h"
 #include "../../fuzzy-aho-corasick-rs_b200/csrc/fac_unicode.h"
 
@@ -315,6 +316,105 @@ int emu_search_succinct(const fac_config *cfg, const fac_pattern *pats, size_t n
         if (rc != 0) return rc;
         std::vector<uint8_t> dirty_byte(len + 1, 0);
         for (uint32_t g = 0; g < n; g++) if (dirty[g]) dirty_byte[fac_byte_offset(ET.tv, g)] = 1;
+        for (size_t i = 0; i < fn; i++) if (dirty_byte[fm[i].start]) res.push_back(fm[i]);
+        free(fm);
+    }
+    std::sort(res.begin(), res.end(), [](const fac_match &a, const fac_match &b) {
+        if (a.start != b.start) return a.start < b.start;
+        if (a.end != b.end) return a.end < b.end;
+        return a.pattern_index < b.pattern_index;
+    });
+    *n_out = res.size();
+    *out = (fac_match *)malloc(sizeof(fac_match) * (res.size() ? res.size() : 1));
+    if (!res.empty()) memcpy(*out, res.data(), sizeof(fac_match) * res.size());
+    if (info) { info[0] = n_dirty; info[1] = states; info[2] = cands.size(); info[3] = best.size(); }
+    return 0;
+}
+
+// General stack-machine fast path (csrc/fac_flat.h + fac_stack.cuh) run sequentially: merged records, a plain LIFO
+// stack, exhausted children walked, the order-independent reduction with tie detection, faithful emulation for tied
+// windows.  returns 0 ok, -3 engine outside the kernel's domain.  info[0] = dirty windows, info[1] = states visited
+int emu_search_flat(const fac_config *cfg, const fac_pattern *pats, size_t np, const uint8_t *hay, size_t len, float thr,
+                    fac_match **out, size_t *n_out, uint64_t *info) {
+    HostAutomaton HA; std::string err;
+    fac_status st = build_automaton(cfg, pats, np, HA, err);
+    if (st != FAC_OK) return (int)st;
+    if (!HA.flat_ok || HA.mef == 255 || HA.beam_width != 0 || HA.has_auto_beam) return -3;
+    const AutomatonView A = HA.host_view();
+    EmuText ET; segment_host(HA, hay, len, ET);
+    const TextView &tv = ET.tv;
+    FacTextDirect T{tv, A.ascii_gid, A.ci};
+    const uint32_t n = tv.n, N = HA.n_nodes();
+    std::vector<FlatRec> nrec(N), erec(HA.edge_char.size());
+    for (uint32_t i = 0; i < N; i++) {
+        union { float f; uint32_t u; } c;
+        c.f = FAC_SUB(HA.node_prune_len[i], FAC_MUL(HA.node_prune_low[i], thr));
+        nrec[i] = FlatRec{HA.flat_nrec[i * 4], HA.flat_nrec[i * 4 + 1], c.u, HA.flat_nrec[i * 4 + 3]};
+    }
+    for (size_t e = 0; e < erec.size(); e++)
+        erec[e] = FlatRec{HA.flat_erec[e * 4], HA.flat_erec[e * 4 + 1], HA.flat_erec[e * 4 + 2], nrec[HA.flat_erec[e * 4] & 0x7FFFFFFFu].z};
+    const FlatView F{nrec.data(), erec.data()};
+    std::vector<FacCand> cands;
+    EmuEmit emit{&cands};
+    uint64_t states = 0;
+    const float maxpen = n ? FAC_SUB(A.node_prune_len[0], FAC_MUL(A.node_prune_low[0], thr)) : 0.f;
+    for (uint32_t start = 0; start < n; start++) {
+        const bool has1 = start + 1 < n;
+        if (fac_window_skipped(A, T.first(start), has1, has1 ? T.first(start + 1) : 0)) continue;
+        std::vector<FacState> stack;
+        stack.push_back(FacState{0, 0.f, 0, 0});
+        while (!stack.empty()) {
+            const FacState s = stack.back();
+            stack.pop_back();
+            const FlatRec nr = nrec[s.node];
+            if (s.pen > FLAT_AS_FLOAT(nr.z)) continue;
+            states++;
+            for (uint32_t o = 0; o < flat_nout(nr); o++) {
+                const uint32_t pat = A.out_pat[nr.w + o];
+                const float total = A.pat_glen[pat];
+                const float sim = FAC_MUL(FAC_DIV(FAC_SUB(total, s.pen), total), A.pat_weight[pat]);
+                if (!(sim < thr)) emit(start, start + (s.pos & FAC_POS_MASK), pat, sim, s.cnt);
+            }
+            FlatCtx C;
+            flat_make_ctx(A, F, T, maxpen, start, n, s, nr, C);
+            for (uint32_t k = 0; k < C.nslots; k++) {
+                FacState c;
+                if (!flat_eval_slot(A, F, T, maxpen, start, n, C, k, c)) continue;
+                if ((int)fac_edits_of(c.cnt) >= A.mef) states += flat_walk(A, F, T, thr, emit, start, n, c);
+                else stack.push_back(c);
+            }
+        }
+    }
+    typedef std::tuple<uint32_t, uint32_t, uint32_t> Key;
+    struct Best { float sim; uint32_t cmin, cmax; };
+    std::map<Key, Best> best;
+    for (const FacCand &c : cands) {
+        const Key k(c.sg, c.eg, c.pat);
+        auto it = best.find(k);
+        if (it == best.end()) best.emplace(k, Best{c.sim, c.cnt, c.cnt});
+        else if (c.sim > it->second.sim) it->second = Best{c.sim, c.cnt, c.cnt};
+        else if (c.sim == it->second.sim) { it->second.cmin = std::min(it->second.cmin, c.cnt); it->second.cmax = std::max(it->second.cmax, c.cnt); }
+    }
+    std::vector<uint8_t> dirty(n + 1, 0);
+    uint64_t n_dirty = 0;
+    for (auto &kv : best) if (kv.second.cmin != kv.second.cmax && !dirty[std::get<0>(kv.first)]) { dirty[std::get<0>(kv.first)] = 1; n_dirty++; }
+    std::vector<fac_match> res;
+    for (auto &kv : best) {
+        if (dirty[std::get<0>(kv.first)]) continue;
+        fac_match m; memset(&m, 0, sizeof(m));
+        const uint32_t cnt = kv.second.cmin;
+        m.start = fac_byte_offset(tv, std::get<0>(kv.first)); m.end = fac_byte_offset(tv, std::get<1>(kv.first));
+        m.pattern_index = std::get<2>(kv.first); m.similarity = kv.second.sim;
+        m.insertions = cnt & 0xFF; m.deletions = (cnt >> 8) & 0xFF; m.substitutions = (cnt >> 16) & 0xFF; m.swaps = cnt >> 24;
+        m.edits = (uint8_t)fac_edits_of(cnt);
+        res.push_back(m);
+    }
+    if (n_dirty) {
+        fac_match *fm = nullptr; size_t fn = 0; uint64_t fs = 0;
+        const int rc = emu_search(cfg, pats, np, hay, len, thr, 16, &fm, &fn, &fs, nullptr);
+        if (rc != 0) return rc;
+        std::vector<uint8_t> dirty_byte(len + 1, 0);
+        for (uint32_t g = 0; g < n; g++) if (dirty[g]) dirty_byte[fac_byte_offset(tv, g)] = 1;
         for (size_t i = 0; i < fn; i++) if (dirty_byte[fm[i].start]) res.push_back(fm[i]);
         free(fm);
     }

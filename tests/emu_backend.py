@@ -14,7 +14,7 @@ CSRC = os.path.join(ROOT, "fuzzy-aho-corasick-rs_b200", "csrc")
 
 def build_emu():
     srcs = [os.path.join(EMU_DIR, "fac_emu.cpp"), os.path.join(CSRC, "fac_builder.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("fac_core.h", "fac_types.h", "fac_unicode.h", "fac_builder.h", "fac_succinct.h")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("fac_core.h", "fac_types.h", "fac_unicode.h", "fac_builder.h", "fac_succinct.h", "fac_flat.h")]
     if (not os.path.exists(EMU_LIB)) or any(os.path.getmtime(EMU_LIB) < os.path.getmtime(d) for d in deps):
         os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off"] + srcs +
@@ -41,6 +41,9 @@ class EmuBackend:
         self.lib.emu_search_succinct.argtypes = [C.POINTER(fac_config), C.POINTER(fac_pattern), C.c_size_t, C.c_char_p,
                                                  C.c_size_t, C.c_float, C.POINTER(C.POINTER(fac_match)),
                                                  C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
+        self.lib.emu_search_flat.argtypes = self.lib.emu_search_succinct.argtypes
+        self.flat = False          # True: run the general stack-machine fast path (merged records) where it applies
+        self.flat_used = 0
         self._keep = {}
         self._next = 1
         self.succinct = False      # True: run the succinct-trie fast path where it applies
@@ -91,6 +94,18 @@ class EmuBackend:
                 return arr, {"states_pushed": info[1], "dirty_windows": info[0], "candidates": info[2], "keys": info[3]}
             if st != -3:
                 raise RuntimeError("emu succinct status %d" % st)
+        if self.flat:
+            info = (C.c_uint64 * 4)()
+            st = self.lib.emu_search_flat(C.byref(cfg), pats, n, data, len(data), thr, C.byref(out), C.byref(cnt), info)
+            if st == 0:
+                self.flat_used += 1
+                arr = (fac_match * cnt.value)()
+                if cnt.value:
+                    C.memmove(arr, out, cnt.value * C.sizeof(fac_match))
+                self.lib.emu_free(out)
+                return arr, {"states_pushed": info[1], "dirty_windows": info[0], "candidates": info[2], "keys": info[3]}
+            if st != -3:
+                raise RuntimeError("emu flat status %d" % st)
         pw = (C.c_uint32 * max(1, len(data)))() if per_window else None
         st = self.lib.emu_search(C.byref(cfg), pats, n, data, len(data), thr, self.tile, C.byref(out), C.byref(cnt),
                                  C.byref(states), pw)

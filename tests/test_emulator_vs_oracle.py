@@ -115,3 +115,45 @@ def test_succinct_on_unicode_haystacks(oracle):
         e = mk(emu).search(hay, SearchOptions.new().threshold(thr))
         assert o.tuples() == e.tuples(), (t, pats, edits, ci, thr, hay)
     assert emu.succinct_used - used0 == 600
+
+
+def test_flat_fast_path_matches_oracle(oracle):
+    """The general stack-machine formulation (csrc/fac_flat.h: merged node / edge records, push-time ceiling prune,
+    exhausted children walked, order-independent reduction + tie detection + faithful redo) must equal the oracle on
+    every fast engine: ASCII and Unicode alphabets, multi-character mappings, non-ASCII haystacks."""
+    emu = EmuBackend(tile=16)
+    emu.flat = True
+    for seed, unicode_, trials in ((71, False, 1200), (72, True, 2000)):
+        r1, r2 = random.Random(seed), random.Random(seed)
+        for t in range(trials):
+            eo, hay, thr, desc = rand_case(r1, oracle, unicode_)
+            ee, _, _, _ = rand_case(r2, emu, unicode_)
+            o = eo.search(hay, SearchOptions.new().threshold(thr))
+            e = ee.search(hay, SearchOptions.new().threshold(thr))
+            assert o.tuples() == e.tuples(), (t, desc)
+    assert emu.flat_used > 600, emu.flat_used
+
+
+def test_flat_fast_path_mappings_and_ties(oracle):
+    emu = EmuBackend(tile=16)
+    emu.flat = True
+    from fac_b200 import FuzzyAhoCorasickBuilder, FuzzyLimits
+    r = random.Random(606)
+    words = ["straße", "strasse", "cæsar", "caesar", "taxi", "taksi", "fußball", "æble", "keks", "fix", "maße",
+             "москва", "東京都", "café", "éclair"]
+    fill = ["a", "e", "s", "ss", "ß", "æ", "ae", "x", "ks", "k", " ", "é", "é", "́", "t", "r", "м", "о", "東", "京", "E", "S"]
+    for t in range(700):
+        pats = r.sample(words, r.randrange(1, 6))
+        edits = r.choice([1, 2, 2, 3])
+        ci = r.random() < 0.6
+        hay = ""
+        for _ in range(r.randrange(0, 40)):
+            hay += (r.choice(words) if r.random() < 0.6 else "".join(r.choice(fill) for _ in range(3))) if r.randrange(4) == 0 else r.choice(fill)
+        def mk(b):
+            bb = FuzzyAhoCorasickBuilder.new(b).fuzzy(FuzzyLimits.new().edits(edits)).case_insensitive(ci)
+            return bb.mapping("æ", "ae").mapping("ß", "ss").mapping_scored("ks", "x", 0.8).build(pats)
+        thr = r.choice([0.3, 0.5, 0.7, 0.8])
+        o = mk(oracle).search(hay, SearchOptions.new().threshold(thr))
+        e = mk(emu).search(hay, SearchOptions.new().threshold(thr))
+        assert o.tuples() == e.tuples(), (t, pats, edits, ci, thr, hay)
+    assert emu.flat_used == 700

@@ -40,7 +40,7 @@ def _fuzz(oracle, gpu, seed, unicode_, trials, faithful, monkeypatch):
 
 @pytest.mark.parametrize("faithful", [True, False])
 def test_fuzz_ascii(oracle, gpu, faithful, monkeypatch):
-    _fuzz(oracle, gpu, 11 + SEED, False, 400, faithful, monkeypatch)
+    _fuzz(oracle, gpu, 11 + SEED, False, 150 if faithful else 400, faithful, monkeypatch)
 
 
 @pytest.mark.parametrize("faithful", [True, False])

@@ -190,8 +190,11 @@ def test_shard_replay_single_device(gpu, oracle):
     cases.append((mk(gpu), mk(oracle), np.frombuffer(text, dtype=np.uint8), 0.7))
     for eng, oeng, text, thr in cases:
         ascii_ = sharding.is_ascii(text)
-        for world in (2, 5, 8):
-            for order, overlap in ((0, 0), (1, 1), (2, 2)):
+        for order, overlap in ((0, 0), (1, 1), (2, 2)):
+            whole, _ = gpu.search(eng._h, bytes(text), thr, order, overlap, False)
+            ref, _ = oracle.search(oeng._h, bytes(text), thr, order, overlap, False)
+            assert _tuples(whole) == _tuples(ref) and len(ref) > 5
+            for world in (2, 5, 8):
                 parts = []
                 for sh in sharding.plan_shards(eng.max_match_graphemes(), text, world):
                     dm, _ = sharding.search_shard(eng, gpu, text, sh, thr, order, ascii_, result_on_device=True)
@@ -199,10 +202,7 @@ def test_shard_replay_single_device(gpu, oracle):
                 buf = torch.cat(parts) if parts else torch.empty(0, dtype=torch.uint8, device="cuda")
                 flags = _abi.FAC_APPLY_PRESORTED if order == 0 else 0
                 final, _ = gpu.apply_device(eng._h, buf.data_ptr(), buf.numel() // 32, order, overlap, flags)
-                whole, _ = gpu.search(eng._h, bytes(text), thr, order, overlap, False)
-                ref, _ = oracle.search(oeng._h, bytes(text), thr, order, overlap, False)
-                assert _tuples(final) == _tuples(whole) == _tuples(ref), (world, order, overlap)
-                assert len(ref) > 5
+                assert _tuples(final) == _tuples(whole), (world, order, overlap)
 
 
 @pytest.mark.gpu

@@ -2,6 +2,7 @@
 (src/prefilter.rs:442-546, same xorshift seeds and draw order) and the Unicode tables that stand
 in for unicode-segmentation / to_lowercase (checked against the python `regex` \\X and str.lower)."""
 import ctypes as C
+import os
 import random
 
 import pytest
@@ -74,15 +75,20 @@ def test_prefilter_matches_full_search_unicode(oracle):  # prefilter.rs:539-546
     differential(oracle, 0xDEADBEEF0BADF00D, UNI_VOCAB, UNI_FILLER, 4000, _pf_check)
 
 
-# the same two seeded differentials on the GPU backend (Prefiltered::search == search, both through the C ABI)
+# the same two seeded differentials on the GPU backend (Prefiltered::search == search, both through the C ABI).  Every
+# trial builds an engine on the device (~40 ms of cudaMalloc / upload): the default run replays the first 1000 trials of
+# each seeded sequence, FAC_TEST_FULL=1 all 4000 (the oracle always runs all 4000 above).
+GPU_TRIALS = 4000 if os.environ.get("FAC_TEST_FULL") == "1" else 1000
+
+
 @pytest.mark.gpu
 def test_prefilter_matches_full_search_ascii_gpu(gpu):  # prefilter.rs:531-536
-    differential(gpu, 0x123456789ABCDEF1, ASCII_VOCAB, ASCII_FILLER, 4000, _pf_check)
+    differential(gpu, 0x123456789ABCDEF1, ASCII_VOCAB, ASCII_FILLER, GPU_TRIALS, _pf_check)
 
 
 @pytest.mark.gpu
 def test_prefilter_matches_full_search_unicode_gpu(gpu):  # prefilter.rs:539-546
-    differential(gpu, 0xDEADBEEF0BADF00D, UNI_VOCAB, UNI_FILLER, 4000, _pf_check)
+    differential(gpu, 0xDEADBEEF0BADF00D, UNI_VOCAB, UNI_FILLER, GPU_TRIALS, _pf_check)
 
 
 # ---- Unicode tables -----------------------------------------------------------------------------
