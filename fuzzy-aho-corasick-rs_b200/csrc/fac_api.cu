@@ -31,6 +31,7 @@
 #include "fac_segment.cuh"
 #include "fac_succinct.cuh"
 #include "fac_stack.cuh"
+#include "fac_beam2.cuh"
 #include "fac_bitap.cuh"
 
 #define FAC_TABLE_QUAL static const
@@ -259,7 +260,10 @@ struct fac_engine {
     const uint32_t *d_s_node_lim = nullptr;
     uint32_t succ_nt = 1024, succ_tile = 4096, succ_stack = 0, succ_min_stack = 64;
     int smem_optin = 0;
-    const uint32_t *d_flat_nrec = nullptr, *d_flat_erec = nullptr;   // static parts of the merged records (fac_flat.h)
+    const uint32_t *d_flat_nrec = nullptr, *d_flat_erec = nullptr, *d_flat_ooff = nullptr, *d_flat_olist = nullptr, *d_flat_gm_row = nullptr;
+    const uint64_t *d_flat_gm = nullptr;   // static parts of the merged records (fac_flat.h)
+    bool beam2_ok = false;          // shared-memory beamed kernel (fac_beam2.cuh)
+    uint32_t max_fan = 0;           // most children one state can push (2 * widest node + mapping transitions + 3)
     bool stack_ok = false;          // general stack-machine kernel (fac_stack.cuh) for fast engines outside the succinct domain
     uint32_t stack_cap = 384, stack_tile = 1024;
     bool fast_ok = false;  // FAST kernel allowed (fast-path edit ceiling, no beam); FAC_FAITHFUL=1 forces the order-faithful kernel
@@ -419,16 +423,34 @@ size_t stack_smem_bytes(const fac_engine *E, bool ascii, uint32_t text_cap) {
     const size_t mult = (!ascii && E->host.has_mappings) ? 2 : 1;
     return tb * mult + (size_t)(STK_THREADS / 32) * (E->stack_cap + STK_WQ_CAP) * 16;
 }
-fac_status launch_stack(const fac_engine *E, Workspace *ws, const ExpandParams &P, uint32_t *dirty, uint32_t n_tiles, cudaStream_t s) {
+// per-call merged records (the node ceilings depend on the threshold)
+fac_status prepare_flat(const fac_engine *E, Workspace *ws, float thr, FlatView &F, cudaStream_t s) {
     const uint32_t N = E->host.n_nodes(), NE = (uint32_t)E->host.edge_char.size();
     CKS(ws->flat_n.ensure((size_t)std::max<uint32_t>(N, 1) * 16));
     CKS(ws->flat_e.ensure((size_t)std::max<uint32_t>(NE, 1) * 16));
-    k_flat_prepare_nodes<<<cdiv(N, 256), 256, 0, s>>>((const uint4 *)E->d_flat_nrec, E->dview.node_prune_len, E->dview.node_prune_low, P.thr, N, ws->flat_n.as<uint4>());
+    k_flat_prepare_nodes<<<cdiv(N, 256), 256, 0, s>>>((const uint4 *)E->d_flat_nrec, E->dview.node_prune_len, E->dview.node_prune_low, thr, N, ws->flat_n.as<uint4>());
     if (NE) k_flat_prepare_edges<<<cdiv(NE, 256), 256, 0, s>>>((const uint4 *)E->d_flat_erec, ws->flat_n.as<uint4>(), NE, ws->flat_e.as<uint4>());
     CK(cudaGetLastError());
+    F.nrec = ws->flat_n.as<FlatRec>(); F.erec = ws->flat_e.as<FlatRec>(); F.ooff = E->d_flat_ooff; F.olist = E->d_flat_olist;
+    F.gm_row = E->d_flat_gm_row; F.gm = (const unsigned long long *)E->d_flat_gm;
+    return FAC_OK;
+}
+fac_status launch_beam2(const fac_engine *E, Workspace *ws, const ExpandParams &P, uint32_t bw, uint32_t n_tiles, cudaStream_t s) {
+    Beam2Params BP;
+    BP.E = P;
+    CKS(prepare_flat(E, ws, P.thr, BP.F, s));
+    const size_t smem = (size_t)BM2_WARPS * BM2_SMEM_PER_WARP;
+    CK(cudaFuncSetAttribute(k_beam_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, ((size_t)227 * 1024) / (smem + 1024));
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)E->sm_count * per_sm, cdiv(n_tiles, BM2_WARPS));
+    k_beam_warp<<<grid, BM2_WARPS * 32, smem, s>>>(BP, bw);
+    CK(cudaGetLastError());
+    return FAC_OK;
+}
+fac_status launch_stack(const fac_engine *E, Workspace *ws, const ExpandParams &P, uint32_t *dirty, uint32_t n_tiles, cudaStream_t s) {
     StackParams SP;
     SP.E = P; SP.stack_cap = E->stack_cap; SP.dirty = dirty;
-    SP.F.nrec = ws->flat_n.as<FlatRec>(); SP.F.erec = ws->flat_e.as<FlatRec>();
+    CKS(prepare_flat(E, ws, P.thr, SP.F, s));
     SP.feed_below = 32u;
     const bool ascii = P.tv.ascii != 0, mapp = P.A.has_mappings != 0;
     const size_t smem = stack_smem_bytes(E, ascii, P.smem_text_cap);
@@ -519,11 +541,13 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
 
     // beamed windows run one per CTA: by default one WARP per window (32 windows in flight per SM, small scratch),
     // windows that overflow that scratch are redone by 256-thread CTAs with the large queue
+    // beam widths whose un-popped queue fits the shared-memory ring run on the one-warp-per-window shared-memory kernel
+    const bool use_beam2 = R.beam && R.bw > 0 && E->beam2_ok && !R.d_per_window && 2ull * R.bw + 2ull * E->max_fan + 64ull <= BM2_QCAP;
     const uint32_t beam_bs = R.beam ? (uint32_t)(env_int("FAC_BEAM_BLOCK", 32) == 256 ? 256 : 32) : 0;
     const uint32_t ctas = beam_bs == 32 ? 32u : (uint32_t)E->ctas_per_sm;
     const uint32_t run_qcap = beam_bs == 32 ? (uint32_t)std::max(4096, env_int("FAC_BEAM_QCAP", 16384)) : E->qcap;
     const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)E->sm_count * ctas, n_tiles);
-    if (!use_succ && !use_stack) CKS(ensure_scratch(E, ws, (uint32_t)E->sm_count * ctas, run_qcap));   // the stack machines keep their frontier in shared memory
+    if (!use_succ && !use_stack && !use_beam2) CKS(ensure_scratch(E, ws, (uint32_t)E->sm_count * ctas, run_qcap));   // the stack machines keep their frontier in shared memory
     uint32_t cand_cap = (uint32_t)std::max<size_t>(ws->cands.cap / sizeof(FacCand), 1u << 20);
     // dense-match workloads emit ~0.2-0.4 candidates per start window: size the first attempt so it need not be redone
     if (R.fast && !explicit_tiles) cand_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(cand_cap, n_windows_total / 2 + (1u << 20)), 0x7FFFFFF0u);
@@ -570,7 +594,8 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
         CK(cudaMemsetAsync(ws->failed_bitmap.p, 0, (size_t)4 * (n_tiles / 32 + 1), s));
         P.pass = 0; P.cand_cap = cand_cap; P.cands = ws->cands.as<FacCand>();
         CK(cudaEventRecord(ws->evk0, s));
-        if (R.beam) {
+        if (use_beam2) { CKS(launch_beam2(E, ws, P, R.bw, n_tiles, s)); stats.launches += 2; }
+        else if (R.beam) {
             if (beam_bs == 32) k_expand_beam<32><<<grid, 32, 0, s>>>(P, R.bw);
             else k_expand_beam<256><<<grid, 256, 0, s>>>(P, R.bw);
             CK(cudaGetLastError());
@@ -589,7 +614,7 @@ fac_status expand_and_reduce(const fac_engine *E, Workspace *ws, const ExpandRun
         stats.expand_ms += ms;
         uint64_t n_cand = ws->h_counters[1], n_failed = ws->h_counters[3];
         uint64_t states = ws->h_counters[2];
-        if (R.beam && n_failed && beam_bs != 32) {
+        if (R.beam && n_failed && beam_bs != 32 && !use_beam2) {
             set_err("a beamed start window exceeded the per-window queue capacity (" + std::to_string(ws->qcap / 4) + " states)");
             return FAC_UNSUPPORTED;
         }
@@ -1455,8 +1480,21 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
     if (H.flat_ok) {
         if ((st = upload(E, H.flat_nrec, &E->d_flat_nrec)) != FAC_OK) return fail(st);
         if ((st = upload(E, H.flat_erec, &E->d_flat_erec)) != FAC_OK) return fail(st);
+        if ((st = upload(E, H.flat_ooff, &E->d_flat_ooff)) != FAC_OK) return fail(st);
+        if ((st = upload(E, H.flat_olist, &E->d_flat_olist)) != FAC_OK) return fail(st);
+        if ((st = upload(E, H.flat_gm_row, &E->d_flat_gm_row)) != FAC_OK) return fail(st);
+        if ((st = upload(E, H.flat_gm, &E->d_flat_gm)) != FAC_OK) return fail(st);
     }
     E->stack_ok = E->fast_ok && H.flat_ok && env_int("FAC_STACK", 1) != 0;
+    {
+        uint32_t maxdeg = 0, maxmaps = 0;
+        for (uint32_t i = 0; i < H.n_nodes(); i++) {
+            maxdeg = std::max(maxdeg, H.node_edge_off[i + 1] - H.node_edge_off[i]);
+            maxmaps = std::max(maxmaps, H.node_map_off[i + 1] - H.node_map_off[i]);
+        }
+        E->max_fan = 2 * maxdeg + maxmaps + 3;
+    }
+    E->beam2_ok = H.flat_ok && H.mef != 255 && (H.beam_width != 0 || H.has_auto_beam) && env_int("FAC_BEAM2", 1) != 0;
     E->stack_cap = (uint32_t)std::min(2048, std::max(64, env_int("FAC_STACK_CAP", 384)));
     E->stack_tile = (uint32_t)std::min(4096, std::max(32, env_int("FAC_STACK_TILE", 1024)));
     E->succ_nt = (uint32_t)env_int("FAC_SUCC_THREADS", 1024);

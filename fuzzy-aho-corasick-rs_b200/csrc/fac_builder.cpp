@@ -577,10 +577,32 @@ fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_
         for (size_t i = 0; i < N && A.flat_ok; i++) {
             const uint32_t deg = A.node_edge_off[i + 1] - A.node_edge_off[i], no = A.node_out_off[i + 1] - A.node_out_off[i];
             const uint32_t nm = A.node_map_off[i + 1] - A.node_map_off[i];
-            if (deg > 4095u || no > 1023u || nm > 1023u) { A.flat_ok = false; break; }
+            if (deg > 4095u || no > 1023u || nm > 255u) { A.flat_ok = false; break; }
             A.flat_nrec[i * 4 + 0] = A.node_edge_off[i]; A.flat_nrec[i * 4 + 1] = deg | (no << 12) | (nm << 22);
             A.flat_nrec[i * 4 + 3] = A.node_out_off[i];
         }
+        A.flat_ooff.assign(N + 1, 0); A.flat_olist.clear();
+        for (size_t i = 0; i < N; i++) {
+            A.flat_ooff[i] = (uint32_t)A.flat_olist.size();
+            for (uint32_t e = A.node_edge_off[i]; e < A.node_edge_off[i + 1]; e++)
+                if (A.edge_next[e] >> 31) A.flat_olist.push_back(e - A.node_edge_off[i]);
+        }
+        A.flat_ooff[N] = (uint32_t)A.flat_olist.size();
+        A.flat_gm_row.assign(N, FAC_NONE); A.flat_gm.clear();
+        for (size_t i = 0; i < N; i++) {
+            const uint32_t e0 = A.node_edge_off[i], deg = A.node_edge_off[i + 1] - e0;
+            if (deg < 3 || deg > 64 || A.flat_gm.size() / 128 >= (1u << 20)) continue;
+            A.flat_gm_row[i] = (uint32_t)(A.flat_gm.size() / 128);
+            const size_t base = A.flat_gm.size();
+            A.flat_gm.resize(base + 128, 0);
+            for (uint32_t e = 0; e < deg; e++) {
+                const uint32_t child = A.edge_next[e0 + e] & 0x7FFFFFFFu;
+                const bool has_out = (A.edge_next[e0 + e] >> 31) != 0;
+                for (uint32_t c = 0; c < 128; c++)
+                    if (has_out || ((A.node_bitmap[child * 4 + (c >> 5)] >> (c & 31)) & 1u)) A.flat_gm[base + c] |= 1ull << e;
+            }
+        }
+        if (A.flat_gm.empty()) A.flat_gm.assign(128, 0);
         for (size_t e = 0; e < A.edge_char.size(); e++) {
             A.flat_erec[e * 4 + 0] = A.edge_next[e]; A.flat_erec[e * 4 + 1] = A.edge_char[e]; A.flat_erec[e * 4 + 2] = A.edge_sym[e];
         }

@@ -129,6 +129,9 @@ struct HostAutomaton {
     // merged 16-byte records of the general stack-machine kernel (fac_flat.h); flat_ok = the packed fields fit
     bool flat_ok = false;
     std::vector<uint32_t> flat_nrec, flat_erec;   // 4 words per node / edge (ceilings are filled per call)
+    std::vector<uint32_t> flat_ooff, flat_olist;  // per node: node-relative edges whose child has outputs (build order)
+    std::vector<uint32_t> flat_gm_row;            // [N] survivor-mask row of a branching node (3..64 edges) or FAC_NONE
+    std::vector<uint64_t> flat_gm;                // [rows * 128] per ASCII look-ahead char: edges whose child has an output or that byte edge
 
     uint32_t n_nodes() const { return (uint32_t)node_prune_len.size(); }
     // View over the host vectors (used by the CPU-side emulator in tests).

@@ -21,18 +21,55 @@
 
 #define FLAT_MAX_DEG 4095u
 #define FLAT_MAX_OUT 1023u
-#define FLAT_MAX_MAPS 1023u
+#define FLAT_MAX_MAPS 255u
 
 struct FlatRec { uint32_t x, y, z, w; };   // same bytes as uint4
 
 struct FlatView {
-    const FlatRec *nrec;   // [N]
-    const FlatRec *erec;   // [E]
+    const FlatRec *nrec;     // [N]
+    const FlatRec *erec;     // [E]
+    // per node, in build order: the (node-relative) edges whose child has outputs.  A state on its last edit keeps a
+    // child only if it has an output or a single-ASCII-byte edge for the look-ahead char (src/search.rs:839-847,
+    // 1057-1063, src/structs.rs:471-475): when that char is not ASCII (or there is none) only these edges can pass,
+    // so the substitution / deletion slots of such a state are this short list instead of all edges.
+    const uint32_t *ooff;    // [N+1]
+    const uint32_t *olist;
+    // ... and when the look-ahead char IS ASCII: for branching nodes (3..64 edges) one 64-bit survivor mask per ASCII
+    // char c over the node-relative edge index (== build order): bit e set iff the child of edge e has an output or a
+    // single-byte edge c.  gm_row[node] = row of the node or FAC_NONE; gm[row * 128 + c].
+    const uint32_t *gm_row;  // [N]
+    const unsigned long long *gm;
 };
+#define FLAT_SUBF 0x40000000u   // substitution slots run over the output-children list
+#define FLAT_DELF 0x80000000u   // deletion slots run over the output-children list
+#define FLAT_SUBM 0x10000000u   // substitution slots run over the set bits of the survivor mask of the look-ahead char
+#define FLAT_DELM 0x20000000u   // deletion slots likewise
+
+#if defined(__CUDA_ARCH__)
+#define FLAT_POPC64(x) ((uint32_t)__popcll(x))
+#else
+#define FLAT_POPC64(x) ((uint32_t)__builtin_popcountll(x))
+#endif
+// position of the n-th (0-based) set bit of m; m must have more than n bits set
+FAC_HD uint32_t flat_nth_bit64(unsigned long long m, uint32_t n) {
+    uint32_t pos = 0;
+    uint32_t c = FLAT_POPC64(m & 0xFFFFFFFFull);
+    if (n >= c) { n -= c; pos = 32; m >>= 32; }
+    c = FLAT_POPC64(m & 0xFFFFull);
+    if (n >= c) { n -= c; pos += 16; m >>= 16; }
+    c = FLAT_POPC64(m & 0xFFull);
+    if (n >= c) { n -= c; pos += 8; m >>= 8; }
+    c = FLAT_POPC64(m & 0xFull);
+    if (n >= c) { n -= c; pos += 4; m >>= 4; }
+    c = FLAT_POPC64(m & 0x3ull);
+    if (n >= c) { n -= c; pos += 2; m >>= 2; }
+    if (n >= (uint32_t)(m & 1ull)) pos += 1;
+    return pos;
+}
 
 FAC_HD uint32_t flat_deg(const FlatRec &n) { return n.y & 0xFFFu; }
 FAC_HD uint32_t flat_nout(const FlatRec &n) { return (n.y >> 12) & 0x3FFu; }
-FAC_HD uint32_t flat_nmaps(const FlatRec &n) { return n.y >> 22; }
+FAC_HD uint32_t flat_nmaps(const FlatRec &n) { return n.y >> 22; }   // <= FLAT_MAX_MAPS
 #if defined(__CUDA_ARCH__)
 #define FLAT_AS_FLOAT(u) __uint_as_float(u)
 #else
@@ -54,7 +91,7 @@ FAC_HD uint32_t flat_lookup(const AutomatonView &A, const FlatView &F, uint32_t 
     return fac_lookup_hash(A, node, key);
 }
 
-enum : uint32_t { FLAT_F_IN_TEXT = 1u, FLAT_F_SWAP = 4u, FLAT_F_INS = 8u, FLAT_F_DEL = 16u, FLAT_F_LAST = 32u, FLAT_F_HAS_NXT = 64u, FLAT_F_EXACT = 128u };
+enum : uint32_t { FLAT_F_IN_TEXT = 1u, FLAT_F_SUB = 2u, FLAT_F_SWAP = 4u, FLAT_F_INS = 8u, FLAT_F_DEL = 16u, FLAT_F_LAST = 32u, FLAT_F_HAS_NXT = 64u, FLAT_F_EXACT = 128u };
 
 struct FlatCtx {
     uint32_t node;
@@ -66,11 +103,13 @@ struct FlatCtx {
     uint32_t nslots;
 };
 FAC_HD uint32_t flat_ctx_deg(const FlatCtx &C) { return (C.shape >> 8) & 0xFFFu; }
-FAC_HD uint32_t flat_ctx_nmaps(const FlatCtx &C) { return C.shape >> 20; }
+FAC_HD uint32_t flat_ctx_nmaps(const FlatCtx &C) { return (C.shape >> 20) & 0xFFu; }
 
-// Guards that do not depend on the edge + the slot count of a state that still has edit budget (edits < MAX_EDITS_FAST):
+// Guards that do not depend on the edge + the slot count of a state:
 // slots = [exact] [substitution per edge] [mapping transitions] [swap] [insertion] [deletion per edge].
-template <class Text>
+// FAST = the order-independent kernel: every popped state still has edit budget (exhausted states are walked).
+// !FAST = the order-faithful beamed kernel: exhausted states are popped like any other (edits < MAX_EDITS_FAST is tested).
+template <bool FAST, class Text>
 FAC_HD void flat_make_ctx(const AutomatonView &A, const FlatView &F, const Text &T, float maxpen, uint32_t start, uint32_t text_end, const FacState &S,
                           const FlatRec &nr, FlatCtx &C) {
     C.node = S.node; C.pen = S.pen; C.cnt = S.cnt; C.pos = S.pos;
@@ -79,30 +118,47 @@ FAC_HD void flat_make_ctx(const AutomatonView &A, const FlatView &F, const Text 
     const int edits = (int)fac_edits_of(S.cnt);
     const float remaining = FAC_SUB(maxpen, S.pen);          // search.rs:648
     const bool is_last = edits + 1 >= A.mef;                 // search.rs:742
+    const bool can_edit = FAST || edits < A.mef;             // search.rs:810, 937, 1003, 1043
     const bool in_text = j < text_end;
     const uint32_t deg = flat_deg(nr), nmaps = A.has_mappings ? flat_nmaps(nr) : 0u;
     uint32_t flags = is_last ? FLAT_F_LAST : 0u, nslots = 0, exact = FAC_NONE;
     if (in_text) {
         flags |= FLAT_F_IN_TEXT;
-        const bool has_nxt = is_last && (j + 1 < text_end);  // search.rs:758-765 (edits < MAX_EDITS_FAST holds for every state here)
+        const bool has_nxt = is_last && can_edit && (j + 1 < text_end);  // search.rs:758-765
         if (has_nxt) flags |= FLAT_F_HAS_NXT;
         exact = flat_lookup(A, F, S.node, nr, A.has_mappings ? T.gid(j) : T.first(j));   // search.rs:776-780
         if (exact != FAC_NONE) { flags |= FLAT_F_EXACT; nslots += 1; }
-        nslots += deg + nmaps;                               // substitutions + mapping transitions (search.rs:803-811: edits < MEF)
-        if (j + 1 < text_end && A.pen_swap <= remaining) { flags |= FLAT_F_SWAP; nslots += 1; }   // search.rs:935-938
-        bool ins_ok = (mr != 0 || jr != 0) && A.pen_ins <= remaining;                            // search.rs:994-1003
+        if (can_edit) {   // substitutions + mapping transitions, search.rs:803-811
+            flags |= FLAT_F_SUB;
+            const uint32_t c1 = has_nxt ? T.first(j + 1) : 0xFFFFFFFFu;
+            const uint32_t row = (is_last && deg > 2u && c1 < 128u) ? F.gm_row[S.node] : FAC_NONE;
+            if (is_last && deg > 2u && c1 >= 128u) { flags |= FLAT_SUBF; nslots += F.ooff[S.node + 1] - F.ooff[S.node]; }
+            else if (row != FAC_NONE) { flags |= FLAT_SUBM; nslots += FLAT_POPC64(F.gm[(size_t)row * 128u + c1]); }
+            else nslots += deg;
+            nslots += nmaps;
+        }
+        if (can_edit && j + 1 < text_end && A.pen_swap <= remaining) { flags |= FLAT_F_SWAP; nslots += 1; }   // search.rs:935-938
+        bool ins_ok = can_edit && (mr != 0 || jr != 0) && A.pen_ins <= remaining;                            // search.rs:994-1003
         if (ins_ok && is_last && flat_nout(nr) == 0) {       // dead-end filter on the node itself, search.rs:1005-1007
             if (!has_nxt || !fac_has_byte_edge(A, S.node, T.first(j + 1))) ins_ok = false;
         }
         if (ins_ok) { flags |= FLAT_F_INS; nslots += 1; }
     }
-    if (A.pen_del <= remaining) { flags |= FLAT_F_DEL; nslots += deg; }   // search.rs:1035-1045
+    if (can_edit && A.pen_del <= remaining) {   // search.rs:1035-1045
+        flags |= FLAT_F_DEL;
+        const uint32_t c0 = in_text ? T.first(j) : 0xFFFFFFFFu;
+        const uint32_t row = (is_last && deg > 2u && c0 < 128u) ? F.gm_row[S.node] : FAC_NONE;
+        if (is_last && deg > 2u && c0 >= 128u) { flags |= FLAT_DELF; nslots += F.ooff[S.node + 1] - F.ooff[S.node]; }
+        else if (row != FAC_NONE) { flags |= FLAT_DELM; nslots += FLAT_POPC64(F.gm[(size_t)row * 128u + c0]); }
+        else nslots += deg;
+    }
     C.exact = exact; C.eoff = nr.x; C.shape = flags | (deg << 8) | (nmaps << 20); C.nslots = nslots;
 }
 
-// Decide slot `slot` of a state; on success `out` is the pushed child.  A child whose own node ceiling already rejects
-// it (it would be dropped when popped, search.rs:638-642) is not produced: result-neutral.
-template <class Text>
+// Decide slot `slot` of a state; on success `out` is the pushed child.  FAST: a child whose own node ceiling already
+// rejects it (it would be dropped when popped, search.rs:638-642) is not produced -- result-neutral, but it changes
+// queue.len(), so the order-faithful kernel (!FAST) pushes it like the reference does.
+template <bool FAST, class Text>
 FAC_HD bool flat_eval_slot(const AutomatonView &A, const FlatView &F, const Text &T, float maxpen, uint32_t start, uint32_t text_end, const FlatCtx &C,
                            uint32_t slot, FacState &out) {
     const uint32_t w = C.pos >> FAC_POS_W_SHIFT;
@@ -118,9 +174,19 @@ FAC_HD bool flat_eval_slot(const AutomatonView &A, const FlatView &F, const Text
         }
         s -= 1;
     }
-    if (C.shape & FLAT_F_IN_TEXT) {
-        if (s < deg) {  // substitution over edge s, search.rs:814-874
-            const FlatRec er = F.erec[C.eoff + s];
+    if (C.shape & FLAT_F_SUB) {
+        uint32_t n_sub = deg, e_sub = s;
+        if (C.shape & FLAT_SUBF) {
+            const uint32_t o0 = F.ooff[C.node];
+            n_sub = F.ooff[C.node + 1] - o0;
+            if (s < n_sub) e_sub = F.olist[o0 + s];
+        } else if (C.shape & FLAT_SUBM) {
+            const unsigned long long m = F.gm[(size_t)F.gm_row[C.node] * 128u + T.first(j + 1)];
+            n_sub = FLAT_POPC64(m);
+            if (s < n_sub) e_sub = flat_nth_bit64(m, s);
+        }
+        if (s < n_sub) {  // substitution over edge e_sub, search.rs:814-874
+            const FlatRec er = F.erec[C.eoff + e_sub];
             const uint32_t nx = er.x & 0x7FFFFFFFu;
             if (nx == C.exact) return false;
             const uint32_t cur = T.first(j);
@@ -130,9 +196,9 @@ FAC_HD bool flat_eval_slot(const AutomatonView &A, const FlatView &F, const Text
             if (pp > FAC_SUB(maxpen, C.pen)) return false;
             if (is_last && !(er.x >> 31) && (!has_nxt || !fac_has_byte_edge(A, nx, T.first(j + 1)))) return false;
             out.node = nx; out.pen = FAC_ADD(C.pen, pp); out.cnt = C.cnt + 0x10000u; out.pos = fac_make_pos(w, jr + 1, jr + 1);
-            return !(out.pen > FLAT_AS_FLOAT(er.w));
+            return !FAST || !(out.pen > FLAT_AS_FLOAT(er.w));
         }
-        s -= deg;
+        s -= n_sub;
         const uint32_t nmaps = flat_ctx_nmaps(C);
         if (s < nmaps) {  // mapping transition, search.rs:883-923
             const uint32_t m = A.node_map_off[C.node] + s;
@@ -167,11 +233,13 @@ FAC_HD bool flat_eval_slot(const AutomatonView &A, const FlatView &F, const Text
         s -= 1;
     }
     {   // deletion over edge s, search.rs:1055-1088
+        if (C.shape & FLAT_DELF) s = F.olist[F.ooff[C.node] + s];
+        else if (C.shape & FLAT_DELM) s = flat_nth_bit64(F.gm[(size_t)F.gm_row[C.node] * 128u + T.first(j)], s);
         const FlatRec er = F.erec[C.eoff + s];
         const uint32_t nx = er.x & 0x7FFFFFFFu;
         if (is_last && !(er.x >> 31) && (!(C.shape & FLAT_F_IN_TEXT) || !fac_has_byte_edge(A, nx, T.first(j)))) return false;
         out.node = nx; out.pen = FAC_ADD(C.pen, A.pen_del); out.cnt = C.cnt + 0x100u; out.pos = fac_make_pos(w, jr, mr);
-        return !(out.pen > FLAT_AS_FLOAT(er.w));
+        return !FAST || !(out.pen > FLAT_AS_FLOAT(er.w));
     }
 }
 

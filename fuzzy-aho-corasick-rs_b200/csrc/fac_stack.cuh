@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(STK_THREADS) k_expand_stack(const __grid_const
                     bool ok = false;
                     if (it < total) {
                         const uint32_t start = tile_start + (O.pos >> FAC_POS_W_SHIFT);
-                        ok = flat_eval_slot(A, F, T, P.maxpen, start, text_end, O, r, c);
+                        ok = flat_eval_slot<true>(A, F, T, P.maxpen, start, text_end, O, r, c);
                     }
                     const bool exhausted = (int)fac_edits_of(c.cnt) >= A.mef;
                     const bool to_walk = ok && exhausted, to_stack = ok && !exhausted;
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(STK_THREADS) k_expand_stack(const __grid_const
                 const bool live = has && !(S.pen > __uint_as_float(nr.z));   // node ceiling, search.rs:638-642
                 const bool last = (int)fac_edits_of(S.cnt) + 1 >= A.mef;
                 C.nslots = 0; C.shape = 0; C.exact = FAC_NONE;
-                if (live) flat_make_ctx(A, F, T, P.maxpen, start, text_end, S, nr, C);
+                if (live) flat_make_ctx<true>(A, F, T, P.maxpen, start, text_end, S, nr, C);
                 // stack pushes of this state in the worst case: a state on its last edit keeps only its exact child
                 const uint32_t ub = !live ? 0u : (last ? ((C.shape & FLAT_F_EXACT) ? 1u : 0u) : C.nslots);
                 uint32_t n_pop = navail;

@@ -353,7 +353,7 @@ int emu_search_flat(const fac_config *cfg, const fac_pattern *pats, size_t np, c
     }
     for (size_t e = 0; e < erec.size(); e++)
         erec[e] = FlatRec{HA.flat_erec[e * 4], HA.flat_erec[e * 4 + 1], HA.flat_erec[e * 4 + 2], nrec[HA.flat_erec[e * 4] & 0x7FFFFFFFu].z};
-    const FlatView F{nrec.data(), erec.data()};
+    const FlatView F{nrec.data(), erec.data(), HA.flat_ooff.data(), HA.flat_olist.data(), HA.flat_gm_row.data(), (const unsigned long long *)HA.flat_gm.data()};
     std::vector<FacCand> cands;
     EmuEmit emit{&cands};
     uint64_t states = 0;
@@ -376,10 +376,10 @@ int emu_search_flat(const fac_config *cfg, const fac_pattern *pats, size_t np, c
                 if (!(sim < thr)) emit(start, start + (s.pos & FAC_POS_MASK), pat, sim, s.cnt);
             }
             FlatCtx C;
-            flat_make_ctx(A, F, T, maxpen, start, n, s, nr, C);
+            flat_make_ctx<true>(A, F, T, maxpen, start, n, s, nr, C);
             for (uint32_t k = 0; k < C.nslots; k++) {
                 FacState c;
-                if (!flat_eval_slot(A, F, T, maxpen, start, n, C, k, c)) continue;
+                if (!flat_eval_slot<true>(A, F, T, maxpen, start, n, C, k, c)) continue;
                 if ((int)fac_edits_of(c.cnt) >= A.mef) states += flat_walk(A, F, T, thr, emit, start, n, c);
                 else stack.push_back(c);
             }

@@ -132,6 +132,18 @@ def test_flat_fast_path_matches_oracle(oracle):
             e = ee.search(hay, SearchOptions.new().threshold(thr))
             assert o.tuples() == e.tuples(), (t, desc)
     assert emu.flat_used > 600, emu.flat_used
+    # dense tries: branching nodes on their last edit use the per-look-ahead-char survivor masks / output-children lists
+    used0 = emu.flat_used
+    r1, r2 = random.Random(277), random.Random(277)
+    for t in range(60):
+        eo, hay, thr, desc = rand_dense_case(r1, oracle)
+        ee, _, _, _ = rand_dense_case(r2, emu)
+        hay2 = hay[:300] + " \u00e9x\u4e2d " + hay[300:500]
+        for h in (hay[:400], hay2):
+            o = eo.search(h, SearchOptions.new().threshold(thr))
+            e = ee.search(h, SearchOptions.new().threshold(thr))
+            assert o.tuples() == e.tuples(), (t, desc)
+    assert emu.flat_used - used0 >= 20
 
 
 def test_flat_fast_path_mappings_and_ties(oracle):
