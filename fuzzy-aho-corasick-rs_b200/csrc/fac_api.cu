@@ -263,6 +263,7 @@ struct fac_engine {
     const uint32_t *d_flat_nrec = nullptr, *d_flat_erec = nullptr, *d_flat_ooff = nullptr, *d_flat_olist = nullptr, *d_flat_gm_row = nullptr;
     const uint64_t *d_flat_gm = nullptr;   // static parts of the merged records (fac_flat.h)
     bool beam2_ok = false;          // shared-memory beamed kernel (fac_beam2.cuh)
+    uint32_t beam2_warps = 5, beam2_vcap = 1024, beam2_ctas = 8;
     uint32_t max_fan = 0;           // most children one state can push (2 * widest node + mapping transitions + 3)
     bool stack_ok = false;          // general stack-machine kernel (fac_stack.cuh) for fast engines outside the succinct domain
     uint32_t stack_cap = 384, stack_tile = 1024;
@@ -439,11 +440,17 @@ fac_status launch_beam2(const fac_engine *E, Workspace *ws, const ExpandParams &
     Beam2Params BP;
     BP.E = P;
     CKS(prepare_flat(E, ws, P.thr, BP.F, s));
-    const size_t smem = (size_t)BM2_WARPS * BM2_SMEM_PER_WARP;
-    CK(cudaFuncSetAttribute(k_beam_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, ((size_t)227 * 1024) / (smem + 1024));
-    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)E->sm_count * per_sm, cdiv(n_tiles, BM2_WARPS));
-    k_beam_warp<<<grid, BM2_WARPS * 32, smem, s>>>(BP, bw);
+    const uint32_t warps = E->beam2_warps, vcap = E->beam2_vcap;
+    const size_t smem = (size_t)warps * BM2_SMEM_PER_WARP(vcap);
+    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(E->beam2_ctas, ((size_t)227 * 1024) / (smem + 1024)));
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)E->sm_count * per_sm, cdiv(n_tiles, warps));
+    if (vcap == 512) {
+        CK(cudaFuncSetAttribute(k_beam_warp<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_beam_warp<512><<<grid, warps * 32, smem, s>>>(BP, bw);
+    } else {
+        CK(cudaFuncSetAttribute(k_beam_warp<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_beam_warp<1024><<<grid, warps * 32, smem, s>>>(BP, bw);
+    }
     CK(cudaGetLastError());
     return FAC_OK;
 }
@@ -1494,8 +1501,13 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
         }
         E->max_fan = 2 * maxdeg + maxmaps + 3;
     }
+    E->beam2_warps = (uint32_t)std::min(8, std::max(1, env_int("FAC_BEAM2_WARPS", 5)));
+    E->beam2_vcap = env_int("FAC_BEAM2_VCAP", 1024) == 512 ? 512u : 1024u;
+    E->beam2_ctas = (uint32_t)std::min(8, std::max(1, env_int("FAC_BEAM2_CTAS", 8)));
+    if (env_int("FAC_STACK_CAP", 0) == 0) E->stack_cap = std::max<uint32_t>(256u, (E->max_fan + 40u + 31u) & ~31u);   // the widest state must fit on top of a fed stack
+    if (E->stack_cap > 1400u) E->stack_ok = false;   // such a fan-out does not fit the per-warp shared-memory stacks: generic kernel
     E->beam2_ok = H.flat_ok && H.mef != 255 && (H.beam_width != 0 || H.has_auto_beam) && env_int("FAC_BEAM2", 1) != 0;
-    E->stack_cap = (uint32_t)std::min(2048, std::max(64, env_int("FAC_STACK_CAP", 384)));
+    E->stack_cap = (uint32_t)std::min(2048, std::max(64, env_int("FAC_STACK_CAP", 256)));
     E->stack_tile = (uint32_t)std::min(4096, std::max(32, env_int("FAC_STACK_TILE", 1024)));
     E->succ_nt = (uint32_t)env_int("FAC_SUCC_THREADS", 1024);
     E->succ_tile = (uint32_t)std::min(4096, std::max(32, env_int("FAC_SUCC_TILE", 4096)));  // 12-bit window field of a state

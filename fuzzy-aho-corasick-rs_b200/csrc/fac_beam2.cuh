@@ -9,7 +9,7 @@
 // the state lives and how much is read per state:
 //
 //   * FIFO queue = a 512-entry ring in shared memory (the un-popped part never exceeds 2*bw + one state's pushes);
-//   * visited map = a 1024-slot open-addressing table in shared memory (64-bit packed key + f32 penalty);
+//   * visited map = a 512- or 1024-slot open-addressing table in shared memory (64-bit packed key + f32 penalty);
 //   * children are evaluated ONCE: they are written behind the tail speculatively, per-parent push counts come from
 //     shared-memory atomics, and a cut simply truncates the tail to the committed prefix;
 //   * the cut is a 4-pass radix select on the total-order image of the penalty (shared-memory histogram) followed by
@@ -24,11 +24,9 @@
 #include "fac_flat.h"
 #include "fac_kernels.cuh"
 
-#define BM2_WARPS 5
 #define BM2_QCAP 512u
-#define BM2_VCAP 1024u
-#define BM2_VMAX 800u
-#define BM2_SMEM_PER_WARP (BM2_QCAP * 16u + BM2_VCAP * 12u + 256u * 4u + 32u * 4u)
+// visited slots per window (template VCAP: 512 or 1024); a window that records more than 3/4 of them is handed over
+#define BM2_SMEM_PER_WARP(VCAP) (BM2_QCAP * 16u + (VCAP) * 12u + 256u * 4u + 32u * 4u)
 
 struct Beam2Params {
     ExpandParams E;
@@ -44,14 +42,16 @@ __device__ __forceinline__ uint32_t bm2_hash(unsigned long long k) {
     return (uint32_t)k;
 }
 
-__global__ void __launch_bounds__(BM2_WARPS * 32) k_beam_warp(const __grid_constant__ Beam2Params BP, const uint32_t bw) {
+template <uint32_t BM2_VCAP>
+__global__ void __launch_bounds__(256) k_beam_warp(const __grid_constant__ Beam2Params BP, const uint32_t bw) {
+    constexpr uint32_t BM2_VMAX = BM2_VCAP / 4u * 3u;
     extern __shared__ __align__(16) uint8_t dyn_smem[];   // per warp: [ring][visited keys][visited penalties][histogram][push counts]
     const ExpandParams &P = BP.E;
     const AutomatonView &A = P.A;
     const FlatView F = BP.F;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint8_t *const mine_smem = dyn_smem + (size_t)warp * BM2_SMEM_PER_WARP;
+    uint8_t *const mine_smem = dyn_smem + (size_t)warp * BM2_SMEM_PER_WARP(BM2_VCAP);
     uint4 *const Q = reinterpret_cast<uint4 *>(mine_smem);
     unsigned long long *const vkey = reinterpret_cast<unsigned long long *>(mine_smem + BM2_QCAP * 16u);
     float *const vpen = reinterpret_cast<float *>(mine_smem + BM2_QCAP * 16u + BM2_VCAP * 8u);
