@@ -12,8 +12,10 @@ in the same contract as the headline line (value / e2e / roofline / cpu_baseline
         The stream length per step is the largest that fits ~20 s at the measured rate (stated in the line); 16 GiB at
         that rate is given as `projected_16GiB_s`.
 
-These run on one GPU (rank 0; other ranks exit): the pre-filter and the auto_beam budget are whole-haystack /
-whole-window properties, stream windows are independent and could be dealt over GPUs.
+cfg3 / cfg4 run on one GPU (rank 0; other ranks exit): the pre-filter and the auto_beam budget are whole-haystack
+properties.  cfg5 uses every GPU of the job from rank 0's process: `--gpus N` builds ONE engine replicated on
+devices 0..N-1 (fac_engine_create_multi) and the stream pipeline deals its window batches over them (the other ranks of a
+torchrun launch exit without touching their device).
 """
 import ctypes as C
 import json
@@ -140,7 +142,7 @@ def run(args, B):
     if name in ("cfg3", "cfg4"):
         if name == "cfg3":
             cfg = cfg3_text(args.bytes)
-            order, overlap, pf, kernel = 0, 0, False, "k_expand<false,true,true> (generic frontier kernel: mappings + grapheme-id stream)"
+            order, overlap, pf, kernel = 0, 0, False, "k_expand_stack<false,true> (stack-machine kernel over merged records: mappings + grapheme-id stream)"
             desc = ("cfg3: 1000 Unicode patterns (Cyrillic / CJK / NFD Latin / German-Nordic), case-insensitive, mappings ae<->ae-ligature, "
                     "ss<->sharp-s, ks<->x, edits(2), threshold 0.8, Order::Unsorted / Overlap::Keep; UTF-8 haystack = an 8 MiB generated block repeated")
             cut = _cut_utf8
@@ -215,7 +217,9 @@ def run(args, B):
     # ---- cfg5: streaming find-and-replace ----
     cfg = workload.cfg5(total=args.bytes)
     thr = cfg["threshold"]
-    rep = workload.build_engine(cfg, gpu)          # FuzzyReplacer
+    world = max(1, int(os.environ.get("WORLD_SIZE", args.gpus)))
+    ndev = min(world, torch.cuda.device_count())
+    rep = workload.build_engine(cfg, gpu, device=list(range(ndev)) if ndev > 1 else None)          # FuzzyReplacer (one replica per device)
     eng = rep.engine()
     io = load_facio()
     lib = gpu.lib
@@ -257,6 +261,8 @@ def run(args, B):
     sk = rows[-1][2]
     exp_ms = sum(r[1].expand_ms for r in rows) / K
     alg = total + 32.0 * ss.matches
+    line["n_gpus"] = int(ss.devices)
+    exp_ms = exp_ms / max(1, int(ss.devices) * 2)   # expand_ms sums over the batches in flight (two workers per device)
     line.update({"value": total / ms / 1e6, "ms_per_step": ms, "device_ms_per_step": sum(r[1].device_ms for r in rows) / K, "expand_ms_per_step": exp_ms,
                  "config": {"workload": "cfg5: Read source repeating a 1 MiB block (64 KiB reads, short read at every block end), auto_beam(200000, 100), edits(2), "
                                         "case-insensitive, 1000-pair FuzzyReplacer::replace_stream, threshold 0.8, absolute u64 offsets; native reader / writer / "
@@ -272,8 +278,9 @@ def run(args, B):
                  "clocks": sampler.summary(),
                  "roofline": {"bound": "hbm", "achieved": alg / exp_ms / 1e6 if exp_ms > 0 else 0.0, "peak": peak, "unit": "GB/s",
                               "frac": (alg / exp_ms / 1e6 / peak) if exp_ms > 0 else 0.0, "traffic": None, "peak_source": which,
-                              "kernel": "k_expand_beam (order-faithful pop loop with the beam cut, one warp per start window)",
-                              "note": "algorithmic bytes (stream bytes + 32 B x owned matches) / CUDA-event time of the beamed expansion launches"}})
+                              "kernel": "k_beam_warp (order-faithful pop loop with the beam cut, one warp per start window, queue + visited map in shared memory)",
+                              "note": "algorithmic bytes (stream bytes + 32 B x owned matches) / CUDA-event time of the beamed expansion launches; the launches of "
+                                      "the batches in flight overlap (two pipeline workers per device), so their summed time is divided by 2 x devices"}})
     if not args.no_cpu_baseline:
         ob = OracleBackend()
         orep = workload.build_engine(cfg, ob)

@@ -26,7 +26,18 @@
 
 #define BM2_QCAP 512u
 // visited slots per window (template VCAP: 512 or 1024); a window that records more than 3/4 of them is handed over
-#define BM2_SMEM_PER_WARP(VCAP) (BM2_QCAP * 16u + (VCAP) * 12u + 256u * 4u + 32u * 4u)
+#define BM2_TEXT 64u      // graphemes of the window staged in shared memory (first chars + grapheme ids)
+#define BM2_SMEM_PER_WARP(VCAP) (BM2_QCAP * 16u + (VCAP) * 12u + 256u * 4u + 32u * 4u + BM2_TEXT * 8u)
+
+// The window's own graphemes from shared memory (already case folded / translated to grapheme ids), anything beyond from
+// the global streams.
+struct WarpText {
+    const uint32_t *sf, *sg;
+    uint32_t base, len;
+    FacTextDirect G;
+    __device__ __forceinline__ uint32_t first(uint32_t j) const { const uint32_t r = j - base; return r < len ? sf[r] : G.first(j); }
+    __device__ __forceinline__ uint32_t gid(uint32_t j) const { const uint32_t r = j - base; return r < len ? sg[r] : G.gid(j); }
+};
 
 struct Beam2Params {
     ExpandParams E;
@@ -57,11 +68,13 @@ __global__ void __launch_bounds__(256) k_beam_warp(const __grid_constant__ Beam2
     float *const vpen = reinterpret_cast<float *>(mine_smem + BM2_QCAP * 16u + BM2_VCAP * 8u);
     uint32_t *const hist = reinterpret_cast<uint32_t *>(mine_smem + BM2_QCAP * 16u + BM2_VCAP * 12u);
     uint32_t *const pc = hist + 256;
+    uint32_t *const s_first = pc + 32, *const s_gid = s_first + BM2_TEXT;
     constexpr uint32_t QM = BM2_QCAP - 1u, VM = BM2_VCAP - 1u;
     const float INF = __int_as_float(0x7F800000);
 
-    FacTextDirect T;
-    T.tv = P.tv; T.ascii_gid = A.ascii_gid; T.ci = A.ci;
+    WarpText T;
+    T.G.tv = P.tv; T.G.ascii_gid = A.ascii_gid; T.G.ci = A.ci;
+    T.sf = s_first; T.sg = s_gid; T.base = 0; T.len = 0;
 
     for (;;) {
         uint32_t t_idx = 0;
@@ -72,6 +85,13 @@ __global__ void __launch_bounds__(256) k_beam_warp(const __grid_constant__ Beam2
         if (P.mode == 0) { start = P.seg_begin + t_idx; text_end = P.text_end; }
         else { const uint4 d = P.tiles[t_idx]; start = d.x; text_end = d.z; win_tag |= d.w; }
         for (uint32_t k = lane; k < BM2_VCAP; k += 32u) vkey[k] = 0ull;
+        {   // stage the window's graphemes: every later text access of the window is a shared-memory load
+            const uint32_t len = min(BM2_TEXT, text_end - start);
+            __syncwarp();
+            for (uint32_t k = lane; k < len; k += 32u) { s_first[k] = T.G.first(start + k); if (A.has_mappings) s_gid[k] = T.G.gid(start + k); }
+            T.base = start; T.len = len;
+            __syncwarp();
+        }
         const bool has1 = start + 1 < text_end;
         const bool skipped = fac_window_skipped(A, T.first(start), has1, has1 ? T.first(start + 1) : 0u);
         uint32_t head = 0, tail = 0, vcount = 0, mcap = 32u;   // un-popped states live in ring positions [head, tail); tail = queue.len()
@@ -111,7 +131,7 @@ __global__ void __launch_bounds__(256) k_beam_warp(const __grid_constant__ Beam2
             if (expanded) { const uint4 v = reinterpret_cast<const uint4 *>(F.nrec)[S.node]; nr.x = v.x; nr.y = v.y; nr.z = v.z; nr.w = v.w; }
             const bool live = expanded && !(S.pen > __uint_as_float(nr.z));   // node ceiling, search.rs:638-642
             FlatCtx C;
-            C.node = C.cnt = C.pos = C.eoff = C.shape = C.nslots = 0; C.exact = FAC_NONE; C.pen = 0.f;
+            C.node = C.cnt = C.pos = C.eoff = C.shape = C.lists = C.nslots = 0; C.exact = C.row = FAC_NONE; C.pen = 0.f;
             if (live) flat_make_ctx<false>(A, F, T, P.maxpen, start, text_end, S, nr, C);
             uint32_t off = C.nslots;
 #pragma unroll
@@ -142,6 +162,8 @@ __global__ void __launch_bounds__(256) k_beam_warp(const __grid_constant__ Beam2
                 O.exact = __shfl_sync(0xFFFFFFFFu, C.exact, lo);
                 O.eoff = __shfl_sync(0xFFFFFFFFu, C.eoff, lo);
                 O.shape = __shfl_sync(0xFFFFFFFFu, C.shape, lo);
+                    O.lists = __shfl_sync(0xFFFFFFFFu, C.lists, lo);
+                    O.row = __shfl_sync(0xFFFFFFFFu, C.row, lo);
                 O.nslots = 0;
                 const uint32_t r = it - __shfl_sync(0xFFFFFFFFu, off, lo);
                 FacState c;

@@ -99,7 +99,9 @@ struct FlatCtx {
     uint32_t cnt, pos;
     uint32_t exact;   // exact_next or FAC_NONE
     uint32_t eoff;
-    uint32_t shape;   // flags | degree << 8 | mapping transitions << 20
+    uint32_t shape;   // flags | degree << 8 | mapping transitions << 20 | list / mask modes (bits 28..31)
+    uint32_t lists;   // substitution slots | deletion slots << 16 (after the last-edit filter)
+    uint32_t row;     // survivor-mask row of the node (FLAT_SUBM / FLAT_DELM)
     uint32_t nslots;
 };
 FAC_HD uint32_t flat_ctx_deg(const FlatCtx &C) { return (C.shape >> 8) & 0xFFFu; }
@@ -121,7 +123,12 @@ FAC_HD void flat_make_ctx(const AutomatonView &A, const FlatView &F, const Text 
     const bool can_edit = FAST || edits < A.mef;             // search.rs:810, 937, 1003, 1043
     const bool in_text = j < text_end;
     const uint32_t deg = flat_deg(nr), nmaps = A.has_mappings ? flat_nmaps(nr) : 0u;
-    uint32_t flags = is_last ? FLAT_F_LAST : 0u, nslots = 0, exact = FAC_NONE;
+    uint32_t flags = is_last ? FLAT_F_LAST : 0u, nslots = 0, exact = FAC_NONE, n_sub = 0, n_del = 0;
+    // a state on its last edit keeps a child only if it has an output or a single-ASCII-byte edge for the look-ahead
+    // char: branching nodes enumerate just those children (output-children list / survivor mask of the char)
+    const bool filt = is_last && deg > 2u;
+    const uint32_t row = filt ? F.gm_row[S.node] : FAC_NONE;
+    const uint32_t n_out_children = filt ? F.ooff[S.node + 1] - F.ooff[S.node] : 0u;
     if (in_text) {
         flags |= FLAT_F_IN_TEXT;
         const bool has_nxt = is_last && can_edit && (j + 1 < text_end);  // search.rs:758-765
@@ -131,11 +138,10 @@ FAC_HD void flat_make_ctx(const AutomatonView &A, const FlatView &F, const Text 
         if (can_edit) {   // substitutions + mapping transitions, search.rs:803-811
             flags |= FLAT_F_SUB;
             const uint32_t c1 = has_nxt ? T.first(j + 1) : 0xFFFFFFFFu;
-            const uint32_t row = (is_last && deg > 2u && c1 < 128u) ? F.gm_row[S.node] : FAC_NONE;
-            if (is_last && deg > 2u && c1 >= 128u) { flags |= FLAT_SUBF; nslots += F.ooff[S.node + 1] - F.ooff[S.node]; }
-            else if (row != FAC_NONE) { flags |= FLAT_SUBM; nslots += FLAT_POPC64(F.gm[(size_t)row * 128u + c1]); }
-            else nslots += deg;
-            nslots += nmaps;
+            if (filt && c1 >= 128u) { flags |= FLAT_SUBF; n_sub = n_out_children; }
+            else if (filt && row != FAC_NONE) { flags |= FLAT_SUBM; n_sub = FLAT_POPC64(F.gm[(size_t)row * 128u + c1]); }
+            else n_sub = deg;
+            nslots += n_sub + nmaps;
         }
         if (can_edit && j + 1 < text_end && A.pen_swap <= remaining) { flags |= FLAT_F_SWAP; nslots += 1; }   // search.rs:935-938
         bool ins_ok = can_edit && (mr != 0 || jr != 0) && A.pen_ins <= remaining;                            // search.rs:994-1003
@@ -147,100 +153,82 @@ FAC_HD void flat_make_ctx(const AutomatonView &A, const FlatView &F, const Text 
     if (can_edit && A.pen_del <= remaining) {   // search.rs:1035-1045
         flags |= FLAT_F_DEL;
         const uint32_t c0 = in_text ? T.first(j) : 0xFFFFFFFFu;
-        const uint32_t row = (is_last && deg > 2u && c0 < 128u) ? F.gm_row[S.node] : FAC_NONE;
-        if (is_last && deg > 2u && c0 >= 128u) { flags |= FLAT_DELF; nslots += F.ooff[S.node + 1] - F.ooff[S.node]; }
-        else if (row != FAC_NONE) { flags |= FLAT_DELM; nslots += FLAT_POPC64(F.gm[(size_t)row * 128u + c0]); }
-        else nslots += deg;
+        if (filt && c0 >= 128u) { flags |= FLAT_DELF; n_del = n_out_children; }
+        else if (filt && row != FAC_NONE) { flags |= FLAT_DELM; n_del = FLAT_POPC64(F.gm[(size_t)row * 128u + c0]); }
+        else n_del = deg;
+        nslots += n_del;
     }
-    C.exact = exact; C.eoff = nr.x; C.shape = flags | (deg << 8) | (nmaps << 20); C.nslots = nslots;
+    C.exact = exact; C.eoff = nr.x; C.shape = flags | (deg << 8) | (nmaps << 20); C.lists = n_sub | (n_del << 16); C.row = row; C.nslots = nslots;
 }
 
 // Decide slot `slot` of a state; on success `out` is the pushed child.  FAST: a child whose own node ceiling already
 // rejects it (it would be dropped when popped, search.rs:638-642) is not produced -- result-neutral, but it changes
-// queue.len(), so the order-faithful kernel (!FAST) pushes it like the reference does.
+// queue.len(), so the order-faithful kernel (!FAST) pushes it like the reference does.  Substitution and deletion slots
+// (the bulk) share one code path so that the lanes of a warp that evaluate them stay converged.
 template <bool FAST, class Text>
 FAC_HD bool flat_eval_slot(const AutomatonView &A, const FlatView &F, const Text &T, float maxpen, uint32_t start, uint32_t text_end, const FlatCtx &C,
                            uint32_t slot, FacState &out) {
     const uint32_t w = C.pos >> FAC_POS_W_SHIFT;
     const uint32_t jr = (C.pos >> FAC_POS_J_SHIFT) & FAC_POS_MASK, mr = C.pos & FAC_POS_MASK;
     const uint32_t j = start + jr;
-    const uint32_t deg = flat_ctx_deg(C);
-    const bool is_last = (C.shape & FLAT_F_LAST) != 0, has_nxt = (C.shape & FLAT_F_HAS_NXT) != 0;
-    uint32_t s = slot;
-    if (C.shape & FLAT_F_EXACT) {
-        if (s == 0) {  // search.rs:781-798
-            out.node = C.exact; out.pen = C.pen; out.cnt = C.cnt; out.pos = fac_make_pos(w, jr + 1, jr + 1);
-            return true;
-        }
-        s -= 1;
-    }
-    if (C.shape & FLAT_F_SUB) {
-        uint32_t n_sub = deg, e_sub = s;
-        if (C.shape & FLAT_SUBF) {
-            const uint32_t o0 = F.ooff[C.node];
-            n_sub = F.ooff[C.node + 1] - o0;
-            if (s < n_sub) e_sub = F.olist[o0 + s];
-        } else if (C.shape & FLAT_SUBM) {
-            const unsigned long long m = F.gm[(size_t)F.gm_row[C.node] * 128u + T.first(j + 1)];
-            n_sub = FLAT_POPC64(m);
-            if (s < n_sub) e_sub = flat_nth_bit64(m, s);
-        }
-        if (s < n_sub) {  // substitution over edge e_sub, search.rs:814-874
-            const FlatRec er = F.erec[C.eoff + e_sub];
-            const uint32_t nx = er.x & 0x7FFFFFFFu;
-            if (nx == C.exact) return false;
-            const uint32_t cur = T.first(j);
-            const float sm = fac_similarity(A, er.y, cur);
-            if (sm < A.min_sym) return false;
-            const float pp = FAC_MUL(A.pen_sub, FAC_SUB(1.0f, sm));
-            if (pp > FAC_SUB(maxpen, C.pen)) return false;
-            if (is_last && !(er.x >> 31) && (!has_nxt || !fac_has_byte_edge(A, nx, T.first(j + 1)))) return false;
-            out.node = nx; out.pen = FAC_ADD(C.pen, pp); out.cnt = C.cnt + 0x10000u; out.pos = fac_make_pos(w, jr + 1, jr + 1);
-            return !FAST || !(out.pen > FLAT_AS_FLOAT(er.w));
-        }
-        s -= n_sub;
-        const uint32_t nmaps = flat_ctx_nmaps(C);
-        if (s < nmaps) {  // mapping transition, search.rs:883-923
-            const uint32_t m = A.node_map_off[C.node] + s;
-            const uint32_t h0 = A.map_hay_off[m], hlen = A.map_hay_off[m + 1] - h0;
-            if ((uint64_t)j + hlen > text_end) return false;
-            for (uint32_t k = 0; k < hlen; k++)
-                if (T.gid(j + k) != A.map_hay_gid[h0 + k]) return false;
-            const float np = FAC_ADD(C.pen, A.map_pen[m]);
-            if (np > maxpen) return false;
-            out.node = A.map_next[m]; out.pen = np; out.cnt = C.cnt + 0x10000u; out.pos = fac_make_pos(w, jr + hlen, jr + hlen);
-            return true;
-        }
-        s -= nmaps;
-    }
-    if (C.shape & FLAT_F_SWAP) {
-        if (s == 0) {  // search.rs:941-988
-            const uint32_t k1 = A.has_mappings ? T.gid(j + 1) : T.first(j + 1), k0 = A.has_mappings ? T.gid(j) : T.first(j);
-            const uint32_t x = flat_lookup(A, F, C.node, F.nrec[C.node], k1);
-            if (x == FAC_NONE) return false;
-            const uint32_t n2 = flat_lookup(A, F, x, F.nrec[x], k0);
-            if (n2 == FAC_NONE) return false;
-            out.node = n2; out.pen = FAC_ADD(C.pen, A.pen_swap); out.cnt = C.cnt + 0x1000000u; out.pos = fac_make_pos(w, jr + 2, jr + 2);
-            return true;
-        }
-        s -= 1;
-    }
-    if (C.shape & FLAT_F_INS) {
-        if (s == 0) {  // search.rs:1018-1028
-            out.node = C.node; out.pen = FAC_ADD(C.pen, A.pen_ins); out.cnt = C.cnt + 1u; out.pos = fac_make_pos(w, jr + 1, mr);
-            return true;
-        }
-        s -= 1;
-    }
-    {   // deletion over edge s, search.rs:1055-1088
-        if (C.shape & FLAT_DELF) s = F.olist[F.ooff[C.node] + s];
-        else if (C.shape & FLAT_DELM) s = flat_nth_bit64(F.gm[(size_t)F.gm_row[C.node] * 128u + T.first(j)], s);
-        const FlatRec er = F.erec[C.eoff + s];
+    const bool is_last = (C.shape & FLAT_F_LAST) != 0, has_nxt = (C.shape & FLAT_F_HAS_NXT) != 0, in_text = (C.shape & FLAT_F_IN_TEXT) != 0;
+    const uint32_t n_sub = C.lists & 0xFFFFu, nmaps = (C.shape & FLAT_F_SUB) ? flat_ctx_nmaps(C) : 0u;
+    // slot boundaries
+    const uint32_t b_sub = (C.shape & FLAT_F_EXACT) ? 1u : 0u;
+    const uint32_t b_map = b_sub + n_sub, b_swap = b_map + nmaps;
+    const uint32_t b_ins = b_swap + ((C.shape & FLAT_F_SWAP) ? 1u : 0u);
+    const uint32_t b_del = b_ins + ((C.shape & FLAT_F_INS) ? 1u : 0u);
+    const bool is_sub = slot >= b_sub && slot < b_map;
+    if (is_sub || slot >= b_del) {   // substitution (search.rs:814-874) or deletion (search.rs:1055-1088) over one edge
+        const uint32_t k = is_sub ? slot - b_sub : slot - b_del;
+        const uint32_t mode = is_sub ? C.shape : (C.shape >> 1);    // FLAT_DELF / FLAT_DELM sit one bit above FLAT_SUBF / FLAT_SUBM
+        const uint32_t look_j = is_sub ? j + 1u : j;                // look-ahead position of the dead-end filter
+        const bool look_ok = is_sub ? has_nxt : in_text;
+        uint32_t e = k;
+        if (mode & FLAT_SUBF) e = F.olist[F.ooff[C.node] + k];
+        else if (mode & FLAT_SUBM) e = flat_nth_bit64(F.gm[(size_t)C.row * 128u + T.first(look_j)], k);
+        const FlatRec er = F.erec[C.eoff + e];
         const uint32_t nx = er.x & 0x7FFFFFFFu;
-        if (is_last && !(er.x >> 31) && (!(C.shape & FLAT_F_IN_TEXT) || !fac_has_byte_edge(A, nx, T.first(j)))) return false;
-        out.node = nx; out.pen = FAC_ADD(C.pen, A.pen_del); out.cnt = C.cnt + 0x100u; out.pos = fac_make_pos(w, jr, mr);
+        if (is_sub && nx == C.exact) return false;
+        float pp = A.pen_del;
+        if (is_sub) {
+            const float sm = fac_similarity(A, er.y, T.first(j));
+            if (sm < A.min_sym) return false;
+            pp = FAC_MUL(A.pen_sub, FAC_SUB(1.0f, sm));
+            if (pp > FAC_SUB(maxpen, C.pen)) return false;
+        }
+        if (is_last && !(er.x >> 31) && (!look_ok || !fac_has_byte_edge(A, nx, T.first(look_j)))) return false;
+        out.node = nx; out.pen = FAC_ADD(C.pen, pp); out.cnt = C.cnt + (is_sub ? 0x10000u : 0x100u);
+        out.pos = is_sub ? fac_make_pos(w, jr + 1, jr + 1) : fac_make_pos(w, jr, mr);
         return !FAST || !(out.pen > FLAT_AS_FLOAT(er.w));
     }
+    if (slot < b_sub) {  // exact transition, search.rs:781-798
+        out.node = C.exact; out.pen = C.pen; out.cnt = C.cnt; out.pos = fac_make_pos(w, jr + 1, jr + 1);
+        return true;
+    }
+    if (slot < b_swap) {  // mapping transition, search.rs:883-923
+        const uint32_t m = A.node_map_off[C.node] + (slot - b_map);
+        const uint32_t h0 = A.map_hay_off[m], hlen = A.map_hay_off[m + 1] - h0;
+        if ((uint64_t)j + hlen > text_end) return false;
+        for (uint32_t k = 0; k < hlen; k++)
+            if (T.gid(j + k) != A.map_hay_gid[h0 + k]) return false;
+        const float np = FAC_ADD(C.pen, A.map_pen[m]);
+        if (np > maxpen) return false;
+        out.node = A.map_next[m]; out.pen = np; out.cnt = C.cnt + 0x10000u; out.pos = fac_make_pos(w, jr + hlen, jr + hlen);
+        return true;
+    }
+    if (slot < b_ins) {  // swap, search.rs:941-988
+        const uint32_t k1 = A.has_mappings ? T.gid(j + 1) : T.first(j + 1), k0 = A.has_mappings ? T.gid(j) : T.first(j);
+        const uint32_t x = flat_lookup(A, F, C.node, F.nrec[C.node], k1);
+        if (x == FAC_NONE) return false;
+        const uint32_t n2 = flat_lookup(A, F, x, F.nrec[x], k0);
+        if (n2 == FAC_NONE) return false;
+        out.node = n2; out.pen = FAC_ADD(C.pen, A.pen_swap); out.cnt = C.cnt + 0x1000000u; out.pos = fac_make_pos(w, jr + 2, jr + 2);
+        return true;
+    }
+    // insertion, search.rs:1018-1028
+    out.node = C.node; out.pen = FAC_ADD(C.pen, A.pen_ins); out.cnt = C.cnt + 1u; out.pos = fac_make_pos(w, jr + 1, mr);
+    return true;
 }
 
 // A child that has spent the whole edit budget follows exact transitions only: ceiling (search.rs:638-642), outputs

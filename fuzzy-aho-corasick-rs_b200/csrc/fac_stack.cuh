@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(STK_THREADS) k_expand_stack(const __grid_const
             uint32_t off = 0;              // exclusive prefix of the lanes' slot counts
             bool more = true, fed = false;
             FlatCtx C;
-            C.node = C.cnt = C.pos = C.eoff = C.shape = C.nslots = 0; C.exact = FAC_NONE; C.pen = 0.f;
+            C.node = C.cnt = C.pos = C.eoff = C.shape = C.lists = C.nslots = 0; C.exact = C.row = FAC_NONE; C.pen = 0.f;
             const StkEmit emit{&P, t, win_tag};
             for (;;) {
                 __syncwarp();
@@ -187,6 +187,8 @@ __global__ void __launch_bounds__(STK_THREADS) k_expand_stack(const __grid_const
                     O.exact = __shfl_sync(0xFFFFFFFFu, C.exact, lo);
                     O.eoff = __shfl_sync(0xFFFFFFFFu, C.eoff, lo);
                     O.shape = __shfl_sync(0xFFFFFFFFu, C.shape, lo);
+                    O.lists = __shfl_sync(0xFFFFFFFFu, C.lists, lo);
+                    O.row = __shfl_sync(0xFFFFFFFFu, C.row, lo);
                     O.nslots = 0;
                     const uint32_t r = it - __shfl_sync(0xFFFFFFFFu, off, lo);
                     FacState c;
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(STK_THREADS) k_expand_stack(const __grid_const
                 if (has) { const uint4 v = reinterpret_cast<const uint4 *>(F.nrec)[S.node]; nr.x = v.x; nr.y = v.y; nr.z = v.z; nr.w = v.w; }
                 const bool live = has && !(S.pen > __uint_as_float(nr.z));   // node ceiling, search.rs:638-642
                 const bool last = (int)fac_edits_of(S.cnt) + 1 >= A.mef;
-                C.nslots = 0; C.shape = 0; C.exact = FAC_NONE;
+                C.nslots = 0; C.shape = 0; C.lists = 0; C.exact = FAC_NONE;
                 if (live) flat_make_ctx<true>(A, F, T, P.maxpen, start, text_end, S, nr, C);
                 // stack pushes of this state in the worst case: a state on its last edit keeps only its exact child
                 const uint32_t ub = !live ? 0u : (last ? ((C.shape & FLAT_F_EXACT) ? 1u : 0u) : C.nslots);

@@ -326,10 +326,10 @@ def build_engine(cfg, backend=None, device=None):
         b = b.mapping(a, c)
     if cfg.get("auto_beam"):
         b = b.auto_beam(*cfg["auto_beam"])
+    if device is not None:
+        b = b.device(device)      # an index, or a list of indices (one replica per device for the stream entry points)
     if "pairs" in cfg:
         return b.build_replacer(cfg["pairs"])
-    if device is not None:
-        b = b.device(device)
     if "limit_kinds" in cfg:
         pats = [Pattern(p, w, _limits_of(k)) for p, w, k in zip(cfg["patterns"], cfg["weights"], cfg["limit_kinds"])]
         return b.build(pats)

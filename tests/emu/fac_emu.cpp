@@ -57,7 +57,11 @@ static void segment_host(const HostAutomaton &A, const uint8_t *s, size_t len, E
     T.tv.first = T.first.data(); T.tv.gid = T.gid.data(); T.tv.off64 = T.off.data(); T.tv.n = (uint32_t)n;
 }
 
+static int g_faithful_flat = 0;   // 1: the order-faithful emulation evaluates states with flat_make_ctx<false> / flat_eval_slot<false>
+
 extern "C" {
+
+void emu_set_faithful_flat(int on) { g_faithful_flat = on; }
 
 // segmentation only: returns grapheme count; fills starts/first (cap entries)
 int emu_segment(const fac_config *cfg, const fac_pattern *pats, size_t np, const uint8_t *hay, size_t len, uint64_t *starts,
@@ -94,6 +98,20 @@ int emu_search(const fac_config *cfg, const fac_pattern *pats, size_t np, const 
     if (tile == 0) tile = 32;
     const float maxpen = n ? FAC_SUB(A.node_prune_len[0], FAC_MUL(A.node_prune_low[0], thr)) : 0.f;  // search.rs:487
     typedef std::tuple<uint32_t, uint32_t, uint32_t> Key;
+    // the merged-record helpers in their order-faithful mode (what k_beam_warp runs): same pushes in the same order
+    const bool use_flat = g_faithful_flat && HA.flat_ok && HA.mef != 255;
+    std::vector<FlatRec> nrec, erec;
+    if (use_flat) {
+        nrec.resize(HA.n_nodes()); erec.resize(HA.edge_char.size());
+        for (uint32_t i = 0; i < HA.n_nodes(); i++) {
+            union { float f; uint32_t u; } c;
+            c.f = FAC_SUB(HA.node_prune_len[i], FAC_MUL(HA.node_prune_low[i], thr));
+            nrec[i] = FlatRec{HA.flat_nrec[i * 4], HA.flat_nrec[i * 4 + 1], c.u, HA.flat_nrec[i * 4 + 3]};
+        }
+        for (size_t e = 0; e < erec.size(); e++)
+            erec[e] = FlatRec{HA.flat_erec[e * 4], HA.flat_erec[e * 4 + 1], HA.flat_erec[e * 4 + 2], nrec[HA.flat_erec[e * 4] & 0x7FFFFFFFu].z};
+    }
+    const FlatView F{nrec.data(), erec.data(), HA.flat_ooff.data(), HA.flat_olist.data(), HA.flat_gm_row.data(), (const unsigned long long *)HA.flat_gm.data()};
     for (uint32_t tile_base = 0; tile_base < n; tile_base += tile) {
         const uint32_t cnt = std::min(tile, n - tile_base);
         const uint32_t text_end = n;
@@ -127,10 +145,12 @@ int emu_search(const fac_config *cfg, const fac_pattern *pats, size_t np, const 
                         cands.push_back(FacCand{start, start + mr, A.out_pat[o], sim, S.cnt, (uint32_t)i, 0, 0});
                 }
                 FacCtx C;
-                fac_make_ctx(A, T, maxpen, start, text_end, S, C);
+                FlatCtx FC;
+                if (use_flat) { flat_make_ctx<false>(A, F, T, maxpen, start, text_end, S, nrec[S.node], FC); C.nslots = FC.nslots; }
+                else fac_make_ctx(A, T, maxpen, start, text_end, S, C);
                 for (uint32_t s = 0; s < C.nslots; s++) {
                     FacState child;
-                    if (fac_eval_slot(A, T, maxpen, start, text_end, C, s, child)) {
+                    if (use_flat ? flat_eval_slot<false>(A, F, T, maxpen, start, text_end, FC, s, child) : fac_eval_slot(A, T, maxpen, start, text_end, C, s, child)) {
                         const uint32_t jr = (child.pos >> FAC_POS_J_SHIFT) & FAC_POS_MASK;
                         if (jr >= FAC_MAX_SPAN) { fprintf(stderr, "emu: span overflow\n"); return 100; }
                         queue.push_back(child);

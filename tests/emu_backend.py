@@ -42,6 +42,7 @@ class EmuBackend:
                                                  C.c_size_t, C.c_float, C.POINTER(C.POINTER(fac_match)),
                                                  C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
         self.lib.emu_search_flat.argtypes = self.lib.emu_search_succinct.argtypes
+        self.lib.emu_set_faithful_flat.argtypes = [C.c_int]
         self.flat = False          # True: run the general stack-machine fast path (merged records) where it applies
         self.flat_used = 0
         self._keep = {}

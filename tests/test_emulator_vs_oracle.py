@@ -169,3 +169,32 @@ def test_flat_fast_path_mappings_and_ties(oracle):
         e = mk(emu).search(hay, SearchOptions.new().threshold(thr))
         assert o.tuples() == e.tuples(), (t, pats, edits, ci, thr, hay)
     assert emu.flat_used == 700
+
+
+def test_flat_faithful_mode_matches_oracle_push_for_push(oracle):
+    """flat_make_ctx<false> / flat_eval_slot<false> (what the shared-memory beamed kernel evaluates states with): the
+    order-faithful emulation run on them must reproduce the oracle's matches AND its queue.len() totals -- the
+    output-children lists / survivor masks may only skip slots that push nothing, in unchanged order."""
+    emu = EmuBackend(tile=5)
+    emu.lib.emu_set_faithful_flat(1)
+    try:
+        for seed, unicode_, trials in ((81, False, 900), (82, True, 900)):
+            r1, r2 = random.Random(seed), random.Random(seed)
+            for t in range(trials):
+                eo, hay, thr, desc = rand_case(r1, oracle, unicode_)
+                ee, _, _, _ = rand_case(r2, emu, unicode_)
+                o = eo.search(hay, SearchOptions.new().threshold(thr))
+                e = ee.search(hay, SearchOptions.new().threshold(thr))
+                assert o.tuples() == e.tuples(), (t, desc)
+                assert o.stats["states_pushed"] == e.stats["states_pushed"], (t, desc)
+        r1, r2 = random.Random(377), random.Random(377)
+        for t in range(40):
+            eo, hay, thr, desc = rand_dense_case(r1, oracle)
+            ee, _, _, _ = rand_dense_case(r2, emu)
+            h = hay[:250] + " \u00e9x\u4e2d " + hay[250:350]
+            o = eo.search(h, SearchOptions.new().threshold(thr))
+            e = ee.search(h, SearchOptions.new().threshold(thr))
+            assert o.tuples() == e.tuples(), (t, desc)
+            assert o.stats["states_pushed"] == e.stats["states_pushed"], (t, desc)
+    finally:
+        emu.lib.emu_set_faithful_flat(0)
