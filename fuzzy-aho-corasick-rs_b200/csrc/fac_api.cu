@@ -256,7 +256,7 @@ struct fac_engine {
     const float *d_s_plen = nullptr, *d_s_plow = nullptr, *d_s_subpen = nullptr;
     const uint8_t *d_s_symof = nullptr;
     const void *d_s_masks = nullptr;   // transposed survivor masks (SuccGMDev): gmT then gm2T
-    uint32_t succ_gm2_off = 0;
+    uint32_t succ_gm2_off = 0, succ_gm3_off = 0, succ_pm3_off = 0, succ_pm2_off = 0, succ_pm4_off = 0;
     const uint32_t *d_s_node_lim = nullptr;
     uint32_t succ_nt = 1024, succ_tile = 4096, succ_stack = 0, succ_min_stack = 64;
     int smem_optin = 0;
@@ -395,6 +395,10 @@ fac_status launch_succinct(const fac_engine *E, Workspace *ws, const TextView &t
     P.stack_cap = E->succ_stack ? E->succ_stack : std::max(!deep ? 128u : 384u, E->succ_min_stack);
     P.text_cap = (P.tile + P.lookahead + 32u + 15u) & ~15u;   // + alignment lead (< 16) + 3 positions of context look-ahead
     P.masks = E->d_s_masks; P.gm_nodes = S.gm_nodes; P.gm2_nodes = S.gm2_nodes; P.gm2_off = E->succ_gm2_off;
+    if (!S.wide) {
+        P.n3 = S.n3; P.np2 = S.np2; P.n4 = S.n4; P.r3 = S.r3;
+        P.gm3_off = E->succ_gm3_off; P.pm3_off = E->succ_pm3_off; P.pm2_off = E->succ_pm2_off; P.pm4_off = E->succ_pm4_off;
+    }
     const size_t fixed = (size_t)nw * (P.stack_cap + SUCC_WQ_CAP) * 16 + (S.wide ? 64u : 32u) * SUCC_SP_STRIDE * 4 + (size_t)P.text_cap * (tv.ascii ? 5 : 8) + 256;   // context words + raw tile
     const size_t budget = (size_t)E->smem_optin - 1024;  // static shared + reserve
     if (fixed + 16 * 64 > budget) { set_err("succinct kernel: shared-memory budget too small for the configured stack / tile"); return FAC_UNSUPPORTED; }
@@ -1428,9 +1432,15 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
         for (size_t i = 0; i < Nn; i++) fcsym[i] = S.fc[i] | ((uint32_t)S.insym[i] << (S.wide ? 26 : 27));
         // survivor masks, transposed so that the node index is fastest (SuccGMDev): gmT[y][node], then gm2T[y1][y2][node]
         const uint32_t ROWS = S.wide ? 64u : 32u, n1 = S.gm_nodes, n2 = S.gm2_nodes;
-        const size_t off2 = (size_t)ROWS * n1, total = off2 + (size_t)ROWS * ROWS * n2;
+        const size_t off2 = (size_t)ROWS * n1;
+        // deep tables (narrow layout only): gm3T[y1][y2][y3][node], pm3T[a][b][c][node], pm2T[a][b][node], pm4T[a][b][c][d][node]
+        const uint32_t n3 = S.wide ? 0u : S.n3, np2 = S.wide ? 0u : S.np2, n4 = S.wide ? 0u : S.n4, R3 = S.r3;
+        const size_t r2 = (size_t)R3 * R3, r3 = r2 * R3, r4 = r3 * R3;
+        const size_t off3 = off2 + (size_t)ROWS * ROWS * n2, offp3 = off3 + r3 * n3, offp2 = offp3 + r3 * n3, offp4 = offp2 + r2 * np2;
+        const size_t total = offp4 + r4 * n4;
         if (total >= 0xFFFFFFFFull) { set_err("survivor-mask tables exceed the 32-bit entry index"); return fail(FAC_UNSUPPORTED); }
-        E->succ_gm2_off = (uint32_t)off2;
+        E->succ_gm2_off = (uint32_t)off2; E->succ_gm3_off = (uint32_t)off3; E->succ_pm3_off = (uint32_t)offp3; E->succ_pm2_off = (uint32_t)offp2;
+        E->succ_pm4_off = (uint32_t)offp4;
         auto fill_masks = [&](auto *dst) {
             typedef typename std::remove_pointer<decltype(dst)>::type T;
             for (uint32_t h = 0; h < n1; h++)
@@ -1439,6 +1449,12 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
                 for (uint32_t y1 = 0; y1 < ROWS; y1++)
                     for (uint32_t y2 = 0; y2 < ROWS; y2++)
                         dst[off2 + ((size_t)y1 * ROWS + y2) * n2 + h] = (T)S.gmask2[((size_t)h * ROWS + y1) * ROWS + y2];
+            for (uint32_t h = 0; h < n3; h++)
+                for (size_t k = 0; k < r3; k++) { dst[off3 + k * n3 + h] = (T)S.gmask3[h * r3 + k]; dst[offp3 + k * n3 + h] = (T)S.pmask3[h * r3 + k]; }
+            for (uint32_t h = 0; h < np2; h++)
+                for (size_t k = 0; k < r2; k++) dst[offp2 + k * np2 + h] = (T)S.pmask2[h * r2 + k];
+            for (uint32_t h = 0; h < n4; h++)
+                for (size_t k = 0; k < r4; k++) dst[offp4 + k * n4 + h] = (T)S.pmask4[h * r4 + k];
         };
         if (S.wide) {
             std::vector<uint64_t> bm(Nn), masks(std::max<size_t>(total, 1));
@@ -1472,7 +1488,7 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
     CK(cudaGetDeviceProperties(&prop, device));
     CK(cudaDeviceGetAttribute(&E->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     E->sm_count = prop.multiProcessorCount;
-    E->lookahead = (uint32_t)H.max_match_graphemes + H.max_map_hay + 3;
+    E->lookahead = (uint32_t)H.max_match_graphemes + H.max_map_hay + 4;   // + 1: the deep tables of the succinct kernel read the context word of j + 1
     E->default_tile = (uint32_t)env_int("FAC_TILE", 0);
     E->qcap = (uint32_t)env_int("FAC_QCAP", 1 << 17);
     E->smem_tab = (uint32_t)env_int("FAC_SMEM_TAB", 1024);

@@ -90,6 +90,13 @@ struct HostSuccinct {
     // two-deep masks of the first gm2_nodes BFS nodes: [gm2_nodes * ROW * ROW]
     std::vector<uint64_t> gmask2;
     uint32_t gm2_nodes = 0;
+    // narrow layout only (fac_succinct.h, "deep tables"): three-deep survivor masks and productivity masks over the
+    // compact symbol row r3 = n_syms + 1 (index n_syms = "no symbol")
+    uint32_t r3 = 0;
+    uint32_t n3 = 0;                     // first n3 BFS nodes: gmask3 / pmask3 [n3][r3][r3][r3]
+    uint32_t np2 = 0;                    // first np2 BFS nodes (>= n3): pmask2 [np2][r3][r3] (rows of the first n3 nodes unused)
+    uint32_t n4 = 0;                     // first n4 BFS nodes (<= n3): pmask4 [n4][r3][r3][r3][r3]
+    std::vector<uint32_t> gmask3, pmask3, pmask2, pmask4;
 };
 
 struct HostAutomaton {

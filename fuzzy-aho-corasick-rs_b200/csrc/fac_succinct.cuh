@@ -47,6 +47,7 @@ struct SuccParams {
     uint32_t gm_nodes;       // nodes covered by the one-deep table
     uint32_t gm2_nodes;      // nodes covered by the two-deep table
     uint32_t gm2_off;        // entry offset of the two-deep table inside `masks`
+    uint32_t n3, np2, r3, gm3_off, pm3_off, pm2_off, n4, pm4_off;   // deep tables (SuccGMDev), narrow layout only
     uint32_t stack_cap;      // states per warp stack
     uint32_t text_cap;       // elements of the shared text tile (multiple of 16)
     FacCand *cands;
@@ -92,7 +93,28 @@ struct SuccGMDev {
     typedef typename SuccW<W>::M M;
     const M *buf;
     uint32_t n1, n2, off2;
-    __device__ __forceinline__ bool two_deep(uint32_t node) const { return node < n2; }
+    // deep tables (narrow layout only; 0 nodes otherwise): gm3T[y1][y2][y3][node] at off3, pm3T[a][b][c][node] at offp3 (n3 nodes each),
+    // pm2T[a][b][node] at offp2 (np2 nodes), pm4T[a][b][c][d][node] at offp4 (n4 nodes); symbol row r3, symbols clamped to
+    // r3 - 1 = "no symbol"
+    uint32_t n3, np2, r3, off3, offp3, offp2, n4, offp4;
+    __device__ __forceinline__ bool four(uint32_t node) const { return !W && node < n4; }
+    __device__ __forceinline__ bool two_deep(uint32_t node) const { return node < n2 || node < n3; }
+    __device__ __forceinline__ M row3(uint32_t node, uint32_t y1, uint32_t y2, uint32_t y3) const {
+        if (W) return row2(node, y1, y2);
+        const uint32_t q = r3 - 1u;
+        const uint32_t i3 = off3 + ((min(y1, q) * r3 + min(y2, q)) * r3 + min(y3, q)) * n3 + node;
+        const uint32_t i2 = node < n2 ? off2 + (y1 * SuccW<W>::ROW + y2) * n2 + node : y1 * n1 + node;
+        return node < n1 ? __ldg(buf + (node < n3 ? i3 : i2)) : ~M(0);
+    }
+    __device__ __forceinline__ M pm(uint32_t node, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const {
+        if (W) return ~M(0);
+        const uint32_t q = r3 - 1u;
+        const uint32_t ab = min(a, q) * r3 + min(b, q), abc = ab * r3 + min(c, q);
+        const uint32_t i4 = offp4 + (abc * r3 + min(d, q)) * n4 + node;
+        const uint32_t i3 = offp3 + abc * n3 + node;
+        const uint32_t i2 = offp2 + ab * np2 + node;
+        return node < np2 ? __ldg(buf + (node < n4 ? i4 : (node < n3 ? i3 : i2))) : ~M(0);
+    }
     __device__ __forceinline__ M row(uint32_t node, uint32_t y) const {
         return node < n1 ? __ldg(buf + (y * n1 + node)) : ~M(0);
     }
@@ -156,7 +178,7 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
 
     const SuccConsts K = P.K;
     const SuccRecsDev R{s_rec, P.rec, P.n_smem_nodes};
-    const SuccGMDev<W> G{reinterpret_cast<const M *>(P.masks), P.gm_nodes, P.gm2_nodes, P.gm2_off};
+    const SuccGMDev<W> G{reinterpret_cast<const M *>(P.masks), P.gm_nodes, P.gm2_nodes, P.gm2_off, P.n3, P.np2, P.r3, P.gm3_off, P.pm3_off, P.pm2_off, P.n4, P.pm4_off};
     const SuccOut *out2 = reinterpret_cast<const SuccOut *>(P.out2);
     SuccEmitDev emit{P.cands, P.cand_cap, &P.counters[1], 0u};
     uint4 *const stk = s_stack + (size_t)warp * P.stack_cap;
@@ -359,7 +381,7 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                     succ_make_ctx2<LIM, W>(K, T, G, start, text_end, sv.x, rec, pen, sv.z, sv.w, C);
                     const uint32_t jr = succ_jr(sv.w);
                     const uint32_t cur_s = succ_ctx_s0(C.packed);
-                    if (succ_has_edge<W>(rec, cur_s)) {   // exact transition, search.rs:776-798
+                    if (C.flags & SUCC_F_EXACT) {   // exact transition, search.rs:776-798 (unless the child provably cannot emit)
                         p_ex = true;
                         c_ex.node = succ_child<W>(rec, cur_s); c_ex.pen = pen; c_ex.cnt = sv.z; c_ex.pos = succ_repos(sv.w, jr + 1, jr + 1);
                     }

@@ -158,7 +158,8 @@ FAC_HD uint32_t succ_walk(const SuccConsts &K, const Recs &R, const SuccOut *out
 enum : uint32_t { SUCC_F_IN_TEXT = 1u, SUCC_F_LAST = 2u, SUCC_F_DEL = 4u, SUCC_F_HAS_NXT = 8u, SUCC_F_INS = 16u,
                   SUCC_F_SWAP_MASK = 32u,   // the masks do not rule the swap child out
                   SUCC_F_INS_MASK = 64u,    // the masks do not rule the insertion child out
-                  SUCC_F_SWAP_SURE = 128u   // ... and already prove that an exhausted swap child can reach an output
+                  SUCC_F_SWAP_SURE = 128u,  // ... and already prove that an exhausted swap child can reach an output
+                  SUCC_F_EXACT = 256u       // exact child exists and is not ruled out by the productivity masks
 };
 
 // ---- survivor masks -------------------------------------------------------------------------------
@@ -195,6 +196,15 @@ struct SuccCtx2 {
 //     bit text[j+1] of  outm | gm2[node][text[j+2]][text[j+3]]  says that g has an output, or the edge text[j+2] to a
 //     node with an output or the edge text[j+3].  Without that (and without an output at the node itself) the
 //     insertion child cannot emit.
+// Deep tables (narrow layout, built by build_deep_tables in fac_builder.cpp over the compact symbol row n_syms + 1):
+//   G.row3(node, y1, y2, y3)  one level deeper than row2 for the first n3 nodes: d = child(node, s) has edge y1 and the exact walk
+//                             from g = child(d, y1) over y2, y3 visits an output or is still alive after y3; row2 beyond the table.
+//                             Used exactly where row2 was: substitution (t1,t2,t3), deletion (t0,t1,t2), swap (t0,t2,t3).
+//   G.pm(node, a, b, c, d)    productivity mask: bit s = a state on its LAST edit at child(node, s) whose position reads a, b, c, d can
+//                             still emit (itself, through its exact chain, or through any exhausted edit child; four symbols
+//                             for the first n4 nodes -- G.four(node) --, three for the first n3, two for the first np2, ~0 beyond).  It filters (i) the substitution / deletion
+//                             children of a state whose children will be on their last edit and (ii) the exact child of a state
+//                             that is on its last edit.  A filtered state can emit nothing, now or later: result-neutral.
 // Limits mode: the per-state permissions follow within_limits_*_ahead of the limits of the pattern that created
 // the node (src/search.rs:66-148); with neither pattern nor global limits only a fresh state may substitute
 // (:143-145).  The dead-end filter does not exist on that path, but dropping exhausted children whose exact walk
@@ -209,6 +219,7 @@ FAC_HD void succ_make_ctx2(const SuccConsts &K, const Text &T, const GM &G, uint
     const uint32_t j = start + jr;
     const int edits = (int)fac_edits_of(cnt);
     const bool last = edits + 1 >= K.mef;
+    const bool child_last = edits + 2 >= K.mef;   // the edit children of this state are on their last edit (or exhausted)
     const bool in_text = j < text_end, has_nxt = j + 1 < text_end;
     const uint32_t p = T.ctx(j);
     const uint32_t cur_s = succ_ctx_s0(p), nxt_s = succ_ctx_s1(p), nxt2_s = succ_ctx_s2(p), nxt3_s = succ_ctx_s3(p);
@@ -233,18 +244,25 @@ FAC_HD void succ_make_ctx2(const SuccConsts &K, const Text &T, const GM &G, uint
     const bool ins_pre = in_text && ins_ok && !(mr == 0 && jr == 0) && K.pen_ins <= remaining;
     const bool ins_need = ins_pre && last && !has_out;    // the masks decide
     M outm = 0, m_sub = ~M(0), m_del = ~M(0), m_sw = 0, m_ins = 0;  // states not on their last edit keep every child
+    const bool has_cur_edge = (bm >> cur_s) & 1u;   // exact transition, search.rs:776-798
+    M m_ex = ~M(0);
     if (last) {
         outm = G.row(node, NOSYM);
-        m_sub = G.row2(node, nxt_s, nxt2_s);
-        m_del = G.row2(node, cur_s, nxt_s);
+        m_sub = G.row3(node, nxt_s, nxt2_s, nxt3_s);
+        m_del = G.row3(node, cur_s, nxt_s, nxt2_s);
+        if (has_cur_edge) m_ex = G.pm(node, nxt_s, nxt2_s, nxt3_s, G.four(node) ? succ_ctx_s3(T.ctx(j + 1)) : NOSYM);   // the exact child stays on its last edit
+    } else if (child_last) {
+        m_sub = G.pm(node, nxt_s, nxt2_s, nxt3_s, G.four(node) ? succ_ctx_s3(T.ctx(j + 1)) : NOSYM);
+        m_del = G.pm(node, cur_s, nxt_s, nxt2_s, nxt3_s);
     }
-    m_sw = sw_pre ? (last ? G.row2(node, cur_s, nxt2_s) : G.row(node, cur_s)) : M(0);
+    m_sw = sw_pre ? (last ? G.row3(node, cur_s, nxt2_s, nxt3_s) : G.row(node, cur_s)) : M(0);
     m_ins = (ins_need && has_nxt_edge) ? G.row2(node, nxt2_s, nxt3_s) : M(0);
     const bool swap_m = (m_sw >> nxt_s) & 1u;
     const bool ins_m = ins_pre && (!ins_need || (((outm | m_ins) >> nxt_s) & (M)has_nxt_edge & 1u));
     const uint32_t flags = (last ? SUCC_F_LAST : 0u) | (in_text ? SUCC_F_IN_TEXT : 0u) | (has_nxt ? SUCC_F_HAS_NXT : 0u) |
                            (del_ok ? SUCC_F_DEL : 0u) | (ins_ok ? SUCC_F_INS : 0u) | (swap_m ? SUCC_F_SWAP_MASK : 0u) |
-                           (ins_m ? SUCC_F_INS_MASK : 0u) | ((last && G.two_deep(node)) ? SUCC_F_SWAP_SURE : 0u);
+                           (ins_m ? SUCC_F_INS_MASK : 0u) | ((last && G.two_deep(node)) ? SUCC_F_SWAP_SURE : 0u) |
+                           ((has_cur_edge && ((m_ex >> cur_s) & 1u)) ? SUCC_F_EXACT : 0u);
     C.bm = bm;
     C.sub_m = (in_text && sub_ok) ? (bm & (outm | m_sub) & ~(M(1) << cur_s)) : M(0);
     C.del_m = del_ok ? (bm & (outm | m_del)) : M(0);

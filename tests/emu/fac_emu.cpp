@@ -214,7 +214,20 @@ template <bool W>
 struct EmuGM {   // survivor-mask tables with the kernel's accessor interface (SuccGMDev)
     typedef typename SuccW<W>::M M;
     const uint64_t *gm, *gm2; uint32_t gm_nodes, gm2_nodes;
-    bool two_deep(uint32_t node) const { return node < gm2_nodes; }
+    const uint32_t *gm3, *pm3, *pm2, *pm4; uint32_t n3, np2, r3, n4;   // deep tables (narrow layout), host layout [node][..]
+    bool four(uint32_t node) const { return !W && node < n4; }
+    bool two_deep(uint32_t node) const { return node < gm2_nodes || node < n3; }
+    uint32_t cl(uint32_t y) const { return std::min(y, r3 - 1u); }
+    M row3(uint32_t node, uint32_t y1, uint32_t y2, uint32_t y3) const {
+        if (W || node >= n3 || node >= gm_nodes) return row2(node, y1, y2);
+        return (M)gm3[(((size_t)node * r3 + cl(y1)) * r3 + cl(y2)) * r3 + cl(y3)];
+    }
+    M pm(uint32_t node, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const {
+        if (W || node >= np2) return ~M(0);
+        if (node < n4) return (M)pm4[((((size_t)node * r3 + cl(a)) * r3 + cl(b)) * r3 + cl(c)) * r3 + cl(d)];
+        if (node < n3) return (M)pm3[(((size_t)node * r3 + cl(a)) * r3 + cl(b)) * r3 + cl(c)];
+        return (M)pm2[((size_t)node * r3 + cl(a)) * r3 + cl(b)];
+    }
     M row(uint32_t node, uint32_t y) const { return node < gm_nodes ? (M)gm[(size_t)node * SuccW<W>::ROW + y] : ~M(0); }
     M row2(uint32_t node, uint32_t y1, uint32_t y2) const {
         if (node >= gm_nodes) return ~M(0);
@@ -244,7 +257,7 @@ static void emu_succ_expand(const HostAutomaton &HA, const EmuText &ET, const ui
     K.mef = S.limits_mode ? (int32_t)S.edit_bound : HA.mef;
     K.lim = HA.lim.data(); K.node_lim = S.node_lim.data(); K.has_global = HA.has_global_limits; K.out_idx = S.out_idx.data();
     const EmuRecs R{recs.data()};
-    const EmuGM<W> G{S.gmask.data(), S.gmask2.data(), S.gm_nodes, S.gm2_nodes};
+    const EmuGM<W> G{S.gmask.data(), S.gmask2.data(), S.gm_nodes, S.gm2_nodes, S.gmask3.data(), S.pmask3.data(), S.pmask2.data(), S.pmask4.data(), W ? 0u : S.n3, W ? 0u : S.np2, S.r3, W ? 0u : S.n4};
     const EmuSText T{hay, ET.tv.ascii ? nullptr : ET.first.data(), S.sym_of, HA.ci, n, NOSYM};
     const SuccOut *out2 = (const SuccOut *)S.out2.data();
     EmuEmit emit{&cands};
@@ -277,7 +290,7 @@ static void emu_succ_expand(const HostAutomaton &HA, const EmuText &ET, const ui
                 else stack.push_back(c);
             };
             const uint32_t cur_s = succ_ctx_s0(C.packed);
-            if (succ_has_edge<W>(rec, cur_s)) stack.push_back(FacState{succ_child<W>(rec, cur_s), s.pen, s.cnt, succ_repos(s.pos, jr + 1, jr + 1)});
+            if (C.flags & SUCC_F_EXACT) stack.push_back(FacState{succ_child<W>(rec, cur_s), s.pen, s.cnt, succ_repos(s.pos, jr + 1, jr + 1)});
             FacState c;
             if (succ_swap2<LIMM, W>(K, R, C, c)) child(c);
             if (succ_ins2<LIMM, W>(K, C, s.node, c)) child(c);
