@@ -182,20 +182,22 @@ static bool k_from_limits(const FacLimits &l, size_t &k) {  // src/prefilter.rs:
 //   pmask2[p][a][b]         bit s:  L(child(p, s); a, b)              (first np2 nodes)
 static void build_deep_tables(HostSuccinct &S) {
     const uint32_t N = (uint32_t)S.bm.size();
-    const uint32_t R = S.n_syms + 1u;
-    size_t RP[5] = {1, R, (size_t)R * R, (size_t)R * R * R, (size_t)R * R * R * R};
+    const uint32_t R = S.n_syms + 1u;   // <= 32 (narrow layout)
+    const size_t RP[5] = {1, R, (size_t)R * R, (size_t)R * R * R, (size_t)R * R * R * R};
     auto envn = [](const char *name, size_t dflt) { const char *ev = getenv(name); return ev && *ev ? (size_t)atoll(ev) : dflt; };
     S.r3 = R;
-    S.n3 = (uint32_t)std::min<size_t>(std::min<uint32_t>(N, S.gm_nodes), envn("FAC_GM3_NODES", ((size_t)4 << 20) / (RP[3] * 4)));
-    S.np2 = (uint32_t)std::min<size_t>(N, envn("FAC_PM2_NODES", ((size_t)8 << 20) / (RP[2] * 4)));
-    S.n4 = (uint32_t)std::min<size_t>(S.n3, envn("FAC_PM4_NODES", ((size_t)4 << 20) / (RP[4] * 4)));
+    S.n3 = (uint32_t)std::min<size_t>(std::min<uint32_t>(N, S.gm_nodes), envn("FAC_GM3_NODES", ((size_t)48 << 20) / (RP[3] * 4)));
+    S.np2 = (uint32_t)std::min<size_t>(N, envn("FAC_PM2_NODES", ((size_t)32 << 20) / (RP[2] * 4)));
+    S.n4 = (uint32_t)std::min<size_t>(S.n3, envn("FAC_PM4_NODES", ((size_t)64 << 20) / (RP[4] * 4)));
     S.np2 = std::max(S.np2, S.n3);
     S.gmask3.assign(std::max<size_t>((size_t)S.n3 * RP[3], 1), 0);
     S.pmask3.assign(std::max<size_t>((size_t)S.n3 * RP[3], 1), 0);
     S.pmask2.assign(std::max<size_t>((size_t)S.np2 * RP[2], 1), 0);
     S.pmask4.assign(std::max<size_t>((size_t)S.n4 * RP[4], 1), 0);
     if (S.np2 == 0) return;
-    typedef std::vector<uint8_t> Bytes;
+    // A k-symbol map (k >= 1) is R^(k-1) words; bit y of word (t0 .. t_{k-2}) is the value at (t0 .. t_{k-2}, y).
+    typedef std::vector<uint32_t> Words;
+    const uint32_t ALL = R >= 32u ? 0xFFFFFFFFu : ((1u << R) - 1u);
     auto out = [&](uint32_t n) { return S.out_idx[n] != FAC_NONE; };
     auto has = [&](uint32_t n, uint32_t y) { return y < S.n_syms && ((S.bm[n] >> y) & 1u) != 0; };
     auto kid = [&](uint32_t n, uint32_t y) { return S.fc[n] + (uint32_t)__builtin_popcountll(S.bm[n] & ((1ull << y) - 1ull)); };
@@ -204,63 +206,67 @@ static void build_deep_tables(HostSuccinct &S) {
         uint32_t k = 0;
         while (bmv) { const uint32_t sy = (uint32_t)__builtin_ctzll(bmv); bmv &= bmv - 1; fn(sy, S.fc[h] + k++); }
     };
-    auto or_into = [](uint8_t *dst, const uint8_t *src, size_t n) { for (size_t i = 0; i < n; i++) dst[i] |= src[i]; };
-    // byte maps of R^k entries, index (((t0 * R + t1) * R + ..) ; memoised per (node, k) for k <= 2
-    std::unordered_map<uint64_t, Bytes> memo_w, memo_l;
-    std::function<Bytes(uint32_t, int)> Wf;
-    std::function<const Bytes &(uint32_t, int)> Wm = [&](uint32_t d, int k) -> const Bytes & {
-        const uint64_t key = ((uint64_t)d << 3) | (uint64_t)k;
-        auto it = memo_w.find(key);
-        if (it != memo_w.end()) return it->second;
-        Bytes v = Wf(d, k);
-        return memo_w.emplace(key, std::move(v)).first->second;
+    auto or_into = [](uint32_t *dst, const uint32_t *src, size_t n) { for (size_t i = 0; i < n; i++) dst[i] |= src[i]; };
+    std::unordered_map<uint64_t, Words> memo_w, memo_l;   // key = node << 3 | k, kept for k <= 3
+    std::function<Words(uint32_t, int)> Wf, Lf;
+    auto W_or = [&](uint32_t d, int k, uint32_t *dst) {   // dst |= W(d; k symbols), k >= 1
+        if (k <= 3) {
+            const uint64_t key = ((uint64_t)d << 3) | (uint64_t)k;
+            auto it = memo_w.find(key);
+            if (it == memo_w.end()) { Words v = Wf(d, k); it = memo_w.emplace(key, std::move(v)).first; }
+            or_into(dst, it->second.data(), RP[k - 1]);
+        } else { const Words v = Wf(d, k); or_into(dst, v.data(), RP[k - 1]); }
     };
-    auto W_or = [&](uint32_t d, int k, uint8_t *dst) {   // dst |= W(d, k)
-        if (k <= 2) or_into(dst, Wm(d, k).data(), RP[k]);
-        else { const Bytes v = Wf(d, k); or_into(dst, v.data(), RP[k]); }
-    };
-    Wf = [&](uint32_t d, int k) -> Bytes {
-        Bytes v(RP[k], (out(d) || k == 0) ? 1 : 0);
-        if (!out(d) && k > 0) for_children(d, [&](uint32_t y1, uint32_t g) { W_or(g, k - 1, &v[(size_t)y1 * RP[k - 1]]); });
+    Wf = [&](uint32_t d, int k) -> Words {
+        Words v(RP[k - 1], out(d) ? ALL : 0u);
+        if (out(d)) return v;
+        if (k == 1) { v[0] = (uint32_t)S.bm[d]; return v; }
+        for_children(d, [&](uint32_t y1, uint32_t g) { W_or(g, k - 1, &v[(size_t)y1 * RP[k - 2]]); });
         return v;
     };
-    std::function<Bytes(uint32_t, int)> Lf;
-    auto L_or = [&](uint32_t c, int k, uint8_t *dst) {
-        if (k <= 2) {
+    auto L_or = [&](uint32_t c, int k, uint32_t *dst) {
+        if (k <= 3) {
             const uint64_t key = ((uint64_t)c << 3) | (uint64_t)k;
             auto it = memo_l.find(key);
-            if (it == memo_l.end()) { Bytes v = Lf(c, k); it = memo_l.emplace(key, std::move(v)).first; }
-            or_into(dst, it->second.data(), RP[k]);
-        } else { const Bytes v = Lf(c, k); or_into(dst, v.data(), RP[k]); }
+            if (it == memo_l.end()) { Words v = Lf(c, k); it = memo_l.emplace(key, std::move(v)).first; }
+            or_into(dst, it->second.data(), RP[k - 1]);
+        } else { const Words v = Lf(c, k); or_into(dst, v.data(), RP[k - 1]); }
     };
-    Lf = [&](uint32_t c, int k) -> Bytes {
-        Bytes v(RP[k], (out(c) || k == 0) ? 1 : 0);
-        if (out(c) || k == 0) return v;
-        Bytes sub_all(RP[k - 1], 0);
+    Lf = [&](uint32_t c, int k) -> Words {
+        // k == 1: a node without an output has children, and then the exact child (or any substitution child) keeps it alive
+        Words v(RP[k - 1], (out(c) || k == 1) ? ALL : 0u);
+        if (out(c) || k == 1) return v;
+        const size_t bs = RP[k - 2];   // words of one t0-block
+        Words sub_all(bs, 0), ins(bs, 0);
         for_children(c, [&](uint32_t, uint32_t d) { W_or(d, k, v.data()); W_or(d, k - 1, sub_all.data()); });   // deletion children
-        Bytes ins(RP[k - 1], 0);
         W_or(c, k - 1, ins.data());                                                                            // insertion child
         for (uint32_t a = 0; a < R; a++) {
-            uint8_t *blk = &v[(size_t)a * RP[k - 1]];
+            uint32_t *blk = &v[(size_t)a * bs];
             if (has(c, a)) {
                 L_or(kid(c, a), k - 1, blk);                                                                   // exact child
                 for_children(c, [&](uint32_t s, uint32_t d) { if (s != a) W_or(d, k - 1, blk); });             // substitution children
-            } else or_into(blk, sub_all.data(), RP[k - 1]);
-            or_into(blk, ins.data(), RP[k - 1]);
+            } else or_into(blk, sub_all.data(), bs);
+            or_into(blk, ins.data(), bs);
         }
         for_children(c, [&](uint32_t b, uint32_t x) {                                                          // swap child
             for_children(x, [&](uint32_t a, uint32_t n2) {
-                if (k >= 2) W_or(n2, k - 2, &v[((size_t)a * R + b) * RP[k - 2]]);
-                else v[a] = 1;
+                if (k == 2) v[a] |= 1u << b;
+                else W_or(n2, k - 2, &v[((size_t)a * R + b) * RP[k - 3]]);
             });
         });
         return v;
     };
+    auto scatter = [&](const uint32_t *w, size_t nw, uint32_t s, uint32_t *dst) {   // dst[word * R + bit] |= 1 << s
+        for (size_t i = 0; i < nw; i++) {
+            uint32_t m = w[i] & ALL;
+            while (m) { const uint32_t y = (uint32_t)__builtin_ctz(m); m &= m - 1; dst[i * R + y] |= 1u << s; }
+        }
+    };
     auto fold = [&](uint32_t p, int k, uint32_t *dst) {   // dst[R^k] bit s = L(child(p, s); k symbols)
         for_children(p, [&](uint32_t s, uint32_t c) {
-            Bytes tmp(RP[k], 0);
+            Words tmp(RP[k - 1], 0);
             L_or(c, k, tmp.data());
-            for (size_t i = 0; i < RP[k]; i++) if (tmp[i]) dst[i] |= 1u << s;
+            scatter(tmp.data(), RP[k - 1], s, dst);
         });
     };
     for (uint32_t p = 0; p < S.n4; p++) fold(p, 4, &S.pmask4[(size_t)p * RP[4]]);
@@ -269,9 +275,9 @@ static void build_deep_tables(HostSuccinct &S) {
         uint32_t *gm = &S.gmask3[(size_t)p * RP[3]];
         for_children(p, [&](uint32_t s, uint32_t d) {
             for_children(d, [&](uint32_t y1, uint32_t g) {
-                const Bytes &w = Wm(g, 2);
-                uint32_t *slab = gm + (size_t)y1 * RP[2];
-                for (size_t i = 0; i < RP[2]; i++) if (w[i]) slab[i] |= 1u << s;
+                Words w(RP[1], 0);
+                W_or(g, 2, w.data());
+                scatter(w.data(), RP[1], s, gm + (size_t)y1 * RP[2]);
             });
         });
     }

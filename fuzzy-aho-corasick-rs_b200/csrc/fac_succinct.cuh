@@ -106,6 +106,15 @@ struct SuccGMDev {
         const uint32_t i2 = node < n2 ? off2 + (y1 * SuccW<W>::ROW + y2) * n2 + node : y1 * n1 + node;
         return node < n1 ? __ldg(buf + (node < n3 ? i3 : i2)) : ~M(0);
     }
+    __device__ __forceinline__ M deep(uint32_t node, bool q_pm, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const {
+        if (W) return q_pm ? ~M(0) : row2(node, a, b);
+        const uint32_t q = r3 - 1u;
+        const uint32_t ab = min(a, q) * r3 + min(b, q), abc = ab * r3 + min(c, q);
+        const uint32_t ip = node < n4 ? offp4 + (abc * r3 + min(d, q)) * n4 + node : (node < n3 ? offp3 + abc * n3 + node : offp2 + ab * np2 + node);
+        const uint32_t ig = node < n3 ? off3 + abc * n3 + node : (node < n2 ? off2 + (a * SuccW<W>::ROW + b) * n2 + node : a * n1 + node);
+        const bool valid = q_pm ? node < np2 : node < n1;
+        return valid ? __ldg(buf + (q_pm ? ip : ig)) : ~M(0);
+    }
     __device__ __forceinline__ M pm(uint32_t node, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const {
         if (W) return ~M(0);
         const uint32_t q = r3 - 1u;

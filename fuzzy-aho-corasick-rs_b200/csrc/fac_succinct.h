@@ -200,6 +200,7 @@ struct SuccCtx2 {
 //   G.row3(node, y1, y2, y3)  one level deeper than row2 for the first n3 nodes: d = child(node, s) has edge y1 and the exact walk
 //                             from g = child(d, y1) over y2, y3 visits an output or is still alive after y3; row2 beyond the table.
 //                             Used exactly where row2 was: substitution (t1,t2,t3), deletion (t0,t1,t2), swap (t0,t2,t3).
+//   G.deep(node, q, a, b, c, d)  = q ? G.pm(node, a, b, c, d) : G.row3(node, a, b, c)   (one load, table selected by index)
 //   G.pm(node, a, b, c, d)    productivity mask: bit s = a state on its LAST edit at child(node, s) whose position reads a, b, c, d can
 //                             still emit (itself, through its exact chain, or through any exhausted edit child; four symbols
 //                             for the first n4 nodes -- G.four(node) --, three for the first n3, two for the first np2, ~0 beyond).  It filters (i) the substitution / deletion
@@ -246,14 +247,14 @@ FAC_HD void succ_make_ctx2(const SuccConsts &K, const Text &T, const GM &G, uint
     M outm = 0, m_sub = ~M(0), m_del = ~M(0), m_sw = 0, m_ins = 0;  // states not on their last edit keep every child
     const bool has_cur_edge = (bm >> cur_s) & 1u;   // exact transition, search.rs:776-798
     M m_ex = ~M(0);
-    if (last) {
-        outm = G.row(node, NOSYM);
-        m_sub = G.row3(node, nxt_s, nxt2_s, nxt3_s);
-        m_del = G.row3(node, cur_s, nxt_s, nxt2_s);
-        if (has_cur_edge) m_ex = G.pm(node, nxt_s, nxt2_s, nxt3_s, G.four(node) ? succ_ctx_s3(T.ctx(j + 1)) : NOSYM);   // the exact child stays on its last edit
-    } else if (child_last) {
-        m_sub = G.pm(node, nxt_s, nxt2_s, nxt3_s, G.four(node) ? succ_ctx_s3(T.ctx(j + 1)) : NOSYM);
-        m_del = G.pm(node, cur_s, nxt_s, nxt2_s, nxt3_s);
+    if (last || child_last) {
+        // one code path for both kinds of state: a state on its last edit reads survivor rows (row3), a state whose edit
+        // children will be on their last edit reads productivity rows (pm) -- G.deep selects the table by index
+        const uint32_t nxt4_s = succ_ctx_s3(T.ctx(j + 1));
+        if (last) outm = G.row(node, NOSYM);
+        m_sub = G.deep(node, !last, nxt_s, nxt2_s, nxt3_s, nxt4_s);
+        m_del = G.deep(node, !last, cur_s, nxt_s, nxt2_s, nxt3_s);
+        if (last && has_cur_edge) m_ex = G.pm(node, nxt_s, nxt2_s, nxt3_s, nxt4_s);   // the exact child stays on its last edit
     }
     m_sw = sw_pre ? (last ? G.row3(node, cur_s, nxt2_s, nxt3_s) : G.row(node, cur_s)) : M(0);
     m_ins = (ins_need && has_nxt_edge) ? G.row2(node, nxt2_s, nxt3_s) : M(0);

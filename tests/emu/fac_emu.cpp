@@ -222,6 +222,7 @@ struct EmuGM {   // survivor-mask tables with the kernel's accessor interface (S
         if (W || node >= n3 || node >= gm_nodes) return row2(node, y1, y2);
         return (M)gm3[(((size_t)node * r3 + cl(y1)) * r3 + cl(y2)) * r3 + cl(y3)];
     }
+    M deep(uint32_t node, bool q_pm, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const { return q_pm ? pm(node, a, b, c, d) : row3(node, a, b, c); }
     M pm(uint32_t node, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const {
         if (W || node >= np2) return ~M(0);
         if (node < n4) return (M)pm4[((((size_t)node * r3 + cl(a)) * r3 + cl(b)) * r3 + cl(c)) * r3 + cl(d)];
