@@ -258,7 +258,7 @@ struct fac_engine {
     const void *d_s_masks = nullptr;   // transposed survivor masks (SuccGMDev): gmT then gm2T
     uint32_t succ_gm2_off = 0, succ_gm3_off = 0, succ_pm3_off = 0, succ_pm2_off = 0, succ_pm4_off = 0;
     const uint32_t *d_s_node_lim = nullptr;
-    uint32_t succ_nt = 1024, succ_tile = 4096, succ_stack = 0, succ_min_stack = 64;
+    uint32_t succ_nt = 1024, succ_tile = 4096, succ_stack = 0, succ_min_stack = 64, succ_feed = 1;
     int smem_optin = 0;
     const uint32_t *d_flat_nrec = nullptr, *d_flat_erec = nullptr, *d_flat_ooff = nullptr, *d_flat_olist = nullptr, *d_flat_gm_row = nullptr;
     const uint64_t *d_flat_gm = nullptr;   // static parts of the merged records (fac_flat.h)
@@ -393,6 +393,7 @@ fac_status launch_succinct(const fac_engine *E, Workspace *ws, const TextView &t
     const uint32_t nt = deep ? std::min<uint32_t>(E->succ_nt, 512u) : E->succ_nt;
     const uint32_t nw = nt / 32;
     P.stack_cap = E->succ_stack ? E->succ_stack : std::max(!deep ? 128u : 384u, E->succ_min_stack);
+    P.feed = E->succ_feed;
     P.text_cap = (P.tile + P.lookahead + 32u + 15u) & ~15u;   // + alignment lead (< 16) + 3 positions of context look-ahead
     P.masks = E->d_s_masks; P.gm_nodes = S.gm_nodes; P.gm2_nodes = S.gm2_nodes; P.gm2_off = E->succ_gm2_off;
     if (!S.wide) {
@@ -1528,6 +1529,9 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
     E->succ_nt = (uint32_t)env_int("FAC_SUCC_THREADS", 1024);
     E->succ_tile = (uint32_t)std::min(4096, std::max(32, env_int("FAC_SUCC_TILE", 4096)));  // 12-bit window field of a state
     E->succ_stack = (uint32_t)env_int("FAC_SUCC_STACK", 0);
+    // start windows fed at once: engines whose roots' children are on their last edit push few states per root (the
+    // productivity masks leave ~20 of 55), deeper budgets fan out again
+    E->succ_feed = (uint32_t)std::min(32, std::max(1, env_int("FAC_SUCC_FEED", (H.mef <= 2 && !H.succ.limits_mode) ? 8 : 1)));
     if (H.succ.ok) {
         // a popped state that is not on its last edit reserves 2 * children + 3 stack slots and roots are fed while
         // fewer than 32 states are stacked: the stack must hold the widest node on top of those 32

@@ -49,6 +49,7 @@ struct SuccParams {
     uint32_t gm2_off;        // entry offset of the two-deep table inside `masks`
     uint32_t n3, np2, r3, gm3_off, pm3_off, pm2_off, n4, pm4_off;   // deep tables (SuccGMDev), narrow layout only
     uint32_t stack_cap;      // states per warp stack
+    uint32_t feed;           // start windows fed at once when the stack runs low (engines with more than one edit)
     uint32_t text_cap;       // elements of the shared text tile (multiple of 16)
     FacCand *cands;
     uint32_t cand_cap;
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                 // (3) feed more start windows when the stack runs low: one root at a time when a root fans out into
                 //     dozens of children, a whole warp's worth when the root is already on its last edit (edits(1))
                 if (more && !fed && top < 32u) {
-                    const uint32_t nf = K.mef <= 1 ? 32u - top : 1u;
+                    const uint32_t nf = K.mef <= 1 ? 32u - top : min(P.feed, 32u - top);
                     uint32_t w0 = 0;
                     if (lane == 0) w0 = atomicAdd(&s_next_win, nf);
                     w0 = __shfl_sync(0xFFFFFFFFu, w0, 0);
@@ -353,10 +354,29 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                 const float pen = __uint_as_float(sv.y);
                 const bool dead = !has || pen > succ_ceil<W>(rec);   // node ceiling, search.rs:638-642
                 const bool last = (int)fac_edits_of(sv.z) + 1 >= K.mef;
-                // worst-case stack pushes of this state: only the exact child when its edit-children are exhausted
-                const uint32_t ub = dead ? 0u : (last ? 1u : 2u * succ_popc(succ_bm<W>(rec)) + 3u);
+                // children of every live candidate first (no side effects), so that the stack check below uses the exact
+                // number of pushes instead of the worst case 2 * fan-out + 3
+                bool p_ex = false, p_sw = false, p_in = false;
+                FacState c_ex, c_sw, c_in;
+                c_ex.node = c_sw.node = c_in.node = 0; c_ex.pen = c_sw.pen = c_in.pen = 0.f;
+                c_ex.cnt = c_sw.cnt = c_in.cnt = 0; c_ex.pos = c_sw.pos = c_in.pos = 0;
+                C.sub_m = C.del_m = 0;
+                if (!dead) {
+                    succ_make_ctx2<LIM, W>(K, T, G, start, text_end, sv.x, rec, pen, sv.z, sv.w, C);
+                    const uint32_t jr = succ_jr(sv.w);
+                    const uint32_t cur_s = succ_ctx_s0(C.packed);
+                    if (C.flags & SUCC_F_EXACT) {   // exact transition, search.rs:776-798 (unless the child provably cannot emit)
+                        p_ex = true;
+                        c_ex.node = succ_child<W>(rec, cur_s); c_ex.pen = pen; c_ex.cnt = sv.z; c_ex.pos = succ_repos(sv.w, jr + 1, jr + 1);
+                    }
+                    p_sw = succ_swap2<LIM, W>(K, R, C, c_sw);
+                    p_in = succ_ins2<LIM, W>(K, C, sv.x, c_in);
+                }
+                uint32_t n_items = succ_popc(C.sub_m) + succ_popc(C.del_m);
+                // stack pushes of this state: a state on its last edit only pushes its exact child (the rest goes to the walk queue)
+                const uint32_t ub = (uint32_t)p_ex + (last ? 0u : (uint32_t)p_sw + (uint32_t)p_in + n_items);
                 uint32_t n_pop = navail;
-                if (__any_sync(0xFFFFFFFFu, ub > 1u)) {  // states on their last edit push at most the exact child: always fits
+                if (__any_sync(0xFFFFFFFFu, ub > 1u)) {
                     uint32_t incl = ub;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
@@ -373,29 +393,19 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                         atomicAdd(&P.counters[7], 1ull);
                     }
                     top -= 1u;
+                    b0 = total = 0;
                     continue;
                 }
                 const bool active = lane < n_pop && !dead;
                 top -= n_pop;
                 __syncwarp();
-
-                bool p_ex = false, p_sw = false, p_in = false;
-                FacState c_ex, c_sw, c_in;
-                c_ex.node = c_sw.node = c_in.node = 0; c_ex.pen = c_sw.pen = c_in.pen = 0.f;
-                c_ex.cnt = c_sw.cnt = c_in.cnt = 0; c_ex.pos = c_sw.pos = c_in.pos = 0;
-                C.sub_m = C.del_m = 0;
                 if (active) {
                     n_states++;
                     if (succ_has_out<W>(rec)) succ_outputs<LIM>(K, out2, emit, succ_out_idx<W>(K, rec, sv.x), pen, sv.z, start, start + succ_mr(sv.w));
-                    succ_make_ctx2<LIM, W>(K, T, G, start, text_end, sv.x, rec, pen, sv.z, sv.w, C);
-                    const uint32_t jr = succ_jr(sv.w);
-                    const uint32_t cur_s = succ_ctx_s0(C.packed);
-                    if (C.flags & SUCC_F_EXACT) {   // exact transition, search.rs:776-798 (unless the child provably cannot emit)
-                        p_ex = true;
-                        c_ex.node = succ_child<W>(rec, cur_s); c_ex.pen = pen; c_ex.cnt = sv.z; c_ex.pos = succ_repos(sv.w, jr + 1, jr + 1);
-                    }
-                    p_sw = succ_swap2<LIM, W>(K, R, C, c_sw);
-                    p_in = succ_ins2<LIM, W>(K, C, sv.x, c_in);
+                } else {   // not popped in this round (or dead): nothing to push
+                    p_ex = p_sw = p_in = false;
+                    C.sub_m = C.del_m = 0;
+                    n_items = 0;
                 }
                 {
                     // exact children and the swap / insertion children of states with budget left go back on the stack,
@@ -419,7 +429,6 @@ __global__ void __launch_bounds__(NT, 1) k_expand_succinct(const __grid_constant
                         top += __popc(b_in_s);
                     }
                 }
-                const uint32_t n_items = succ_popc(C.sub_m) + succ_popc(C.del_m);
                 off = n_items;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
