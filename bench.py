@@ -37,8 +37,10 @@ sys.path.insert(0, os.path.join(ROOT, "fuzzy-aho-corasick-rs_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "haystack GB/s (fuzzy, edits=2)"
-# dram bytes of one k_expand_succinct launch from the ncu --set full capture under profiles/ (per 2^25-window launch)
-TRAFFIC_NOTE = 404099584
+# dram bytes (read + written) of one 2^25-window k_expand_succinct launch from the ncu --set full capture under profiles/
+# (r2f_k_expand_succinct_raw_selected.txt: 1.735 GB read -- mostly rows of the 200 MB deep tables that miss the 126 MB L2 --
+# + 381 MB written: the raw candidates)
+TRAFFIC_NOTE = 2116422584
 
 
 def peaks():
@@ -272,7 +274,12 @@ def main():
     ORDER, OVERLAP = 0, 0
     gpu = GpuBackend()
     total = args.bytes
-    procs = max(1, min(16, (os.cpu_count() or 1) // max(world, 1)))
+    # generator processes: rank 0 also produces the WHOLE haystack for the step-0 check, so it gets the cores the other ranks
+    # (one shard each, 2 processes) leave free
+    ncpu = os.cpu_count() or 1
+    procs = max(1, min(16, ncpu // max(world, 1)))
+    if world > 1:
+        procs = max(2, min(16, ncpu - 2 * (world - 1))) if rank == 0 and not args.no_verify else max(1, min(2, ncpu // world))
     verify = not args.no_verify
     # engine first (the shard plan needs max_match_graphemes), then this rank's slice of the haystack
     recipe = config_text(args.config, args, 0, 0, 1)

@@ -5,6 +5,7 @@
 // needs (classification flag, counters).  There is NO CPU implementation of the search path here:
 // every entry point fails with FAC_CUDA_ERROR when no device is usable.
 #include <cub/cub.cuh>
+#include <atomic>
 
 #include <algorithm>
 #include <cmath>
@@ -101,6 +102,7 @@ struct Workspace {
     uint32_t grid = 0, qcap = 0, gtab_size = 0;
     DBuf cands, counters, failed_tiles, failed_bitmap, tiles;
     DBuf best_rep, best_val, cslot, tab_sim, tab_cmin, tab_cmax, tab_first, dirty;
+    DBuf keys_a, keys_b;
     DBuf m_a, m_b, idx_a, idx_b, winend, st_a, st_b, flags8, sel, nsel, outm, keep8, windows, misc, cubtmp, used;
     uint64_t *h_counters = nullptr;  // pinned
     uint32_t *h_flags = nullptr;     // pinned
@@ -113,7 +115,7 @@ struct Workspace {
     }
     void destroy() {
         for (DBuf *b : {&flat_n, &flat_e, &hay, &mark, &gidx, &first, &gid, &off, &pfsym, &srec, &cov, &covcnt, &covoff, &sl_gs, &sl_ge, &bp_k, &queue, &nxt, &hslot, &gtab_rep, &gtab_head, &gtab_min, &cands, &counters,
-                        &failed_tiles, &failed_bitmap, &tiles, &best_rep, &best_val, &cslot, &tab_sim, &tab_cmin, &tab_cmax, &tab_first, &dirty, &m_a, &m_b, &idx_a, &idx_b, &winend, &st_a, &st_b,
+                        &failed_tiles, &failed_bitmap, &tiles, &best_rep, &best_val, &cslot, &tab_sim, &tab_cmin, &tab_cmax, &tab_first, &dirty, &keys_a, &keys_b, &m_a, &m_b, &idx_a, &idx_b, &winend, &st_a, &st_b,
                         &flags8, &sel, &nsel, &outm, &keep8, &windows, &misc, &cubtmp, &used})
             b->release();
         if (h_counters) cudaFreeHost(h_counters);
@@ -150,7 +152,14 @@ struct PinnedPool {
             }
         }
         void *p = nullptr;
-        if (cudaHostAlloc(&p, cls, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return malloc(bytes); }
+        if (cudaHostAlloc(&p, cls, cudaHostAllocPortable) != cudaSuccess) {
+            // pageable fallback: the device-to-host copy of the result list drops to a few GB/s -- say so (once per process)
+            cudaGetLastError();
+            static std::atomic<bool> warned{false};
+            if (!warned.exchange(true))
+                fprintf(stderr, "libfacgpu: warning: cudaHostAlloc(%zu bytes) failed; match lists are returned in pageable memory (slow device-to-host copies)\n", cls);
+            return malloc(bytes);
+        }
         std::lock_guard<std::mutex> g(mu);
         live_[p] = cls;
         return p;
@@ -259,6 +268,7 @@ struct fac_engine {
     uint32_t succ_gm2_off = 0, succ_gm3_off = 0, succ_pm3_off = 0, succ_pm2_off = 0, succ_pm4_off = 0;
     const uint32_t *d_s_node_lim = nullptr;
     uint32_t succ_nt = 1024, succ_tile = 4096, succ_stack = 0, succ_min_stack = 64, succ_feed = 1;
+    bool radix_unsorted = true;   // FAC_RADIX_UNSORTED=0: Order::Unsorted always through the comparison merge sort
     int smem_optin = 0;
     const uint32_t *d_flat_nrec = nullptr, *d_flat_erec = nullptr, *d_flat_ooff = nullptr, *d_flat_olist = nullptr, *d_flat_gm_row = nullptr;
     const uint64_t *d_flat_gm = nullptr;   // static parts of the merged records (fac_flat.h)
@@ -790,19 +800,58 @@ fac_status merge_sort(Workspace *ws, T *d, uint32_t n, Cmp cmp) {
     return FAC_OK;
 }
 
+// Order::Unsorted (ascending (start, end, pattern), oracle rule U2) of a single-window list as an LSD radix sort of
+// (64-bit key, index) pairs followed by one gather of the 32-byte records: ~4x less DRAM traffic than the comparison
+// merge sort of the records themselves on the 10^8-match lists of dense workloads.  *done = false when the key fields do
+// not fit 64 bits (the caller falls back to the merge sort).
+fac_status radix_sort_unsorted(Workspace *ws, uint32_t n, bool *done, SearchStats &stats) {
+    cudaStream_t s = ws->stream;
+    *done = false;
+    CKS(ws->misc.ensure(64));
+    CK(cudaMemsetAsync(ws->misc.p, 0, 32, s));
+    k_key_bounds<<<std::min<uint32_t>(cdiv(n, 256), 148 * 16), 256, 0, s>>>(ws->m_a.as<WMatch>(), n, ws->misc.as<unsigned long long>());
+    unsigned long long hb[4];
+    CK(cudaMemcpyAsync(hb, ws->misc.p, 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    auto bits = [](unsigned long long v) { uint32_t b = 0; while (v) { b++; v >>= 1; } return b; };
+    const uint32_t pat_bits = std::max(1u, bits(hb[2])), len_bits = std::max(1u, bits(hb[1])), start_bits = std::max(1u, bits(hb[0]));
+    if (hb[3] != 0 || pat_bits + len_bits + start_bits > 64) return FAC_OK;
+    CKS(ws->keys_a.ensure((size_t)n * 8)); CKS(ws->keys_b.ensure((size_t)n * 8));
+    CKS(ws->idx_a.ensure((size_t)n * 4)); CKS(ws->idx_b.ensure((size_t)n * 4));
+    CKS(ws->m_b.ensure((size_t)n * sizeof(WMatch)));
+    k_make_keys<<<cdiv(n, 256), 256, 0, s>>>(ws->m_a.as<WMatch>(), n, pat_bits, pat_bits + len_bits, ws->keys_a.as<unsigned long long>(), ws->idx_a.as<uint32_t>());
+    cub::DoubleBuffer<unsigned long long> dk(ws->keys_a.as<unsigned long long>(), ws->keys_b.as<unsigned long long>());
+    cub::DoubleBuffer<uint32_t> dv(ws->idx_a.as<uint32_t>(), ws->idx_b.as<uint32_t>());
+    size_t tb = 0;
+    const int end_bit = (int)(pat_bits + len_bits + start_bits);
+    CK(cub::DeviceRadixSort::SortPairs((void *)nullptr, tb, dk, dv, (int)n, 0, end_bit, s));
+    CKS(ws->cubtmp.ensure(tb));
+    CK(cub::DeviceRadixSort::SortPairs(ws->cubtmp.p, tb, dk, dv, (int)n, 0, end_bit, s));
+    k_gather_matches16<<<cdiv((uint64_t)n * 2, 256), 256, 0, s>>>(ws->m_a.as<WMatch>(), dv.Current(), n, ws->m_b.as<WMatch>());
+    CK(cudaGetLastError());
+    std::swap(ws->m_a, ws->m_b);
+    stats.launches += 4 + (uint32_t)((end_bit + 7) / 8);
+    *done = true;
+    return FAC_OK;
+}
+
 // FuzzyMatches::apply on the device.  In: ws->m_a[0..n) (any order).  Out: ws->m_a[0..*n_out) in final order.
 fac_status apply_device(const fac_engine *E, Workspace *ws, uint32_t n, int order, int overlap, uint32_t n_windows, uint32_t *n_out,
                         SearchStats &stats, bool presorted = false) {
     cudaStream_t s = ws->stream;
     *n_out = n;
     if (n == 0) return FAC_OK;
-    WMatch *R = ws->m_a.as<WMatch>();
     RankLess rl{order, E->d_pat_bytes};
     if (!presorted) {
-        CKS(merge_sort(ws, R, n, rl));
-        stats.launches += 2;
+        bool done = false;
+        if (order == 0 && n >= 4096u && E->radix_unsorted) CKS(radix_sort_unsorted(ws, n, &done, stats));
+        if (!done) {
+            CKS(merge_sort(ws, ws->m_a.as<WMatch>(), n, rl));
+            stats.launches += 2;
+        }
     }
     if (overlap == FAC_OVERLAP_KEEP) return FAC_OK;
+    WMatch *R = ws->m_a.as<WMatch>();
     // position order
     CKS(ws->idx_a.ensure((size_t)n * 4));
     CKS(ws->winend.ensure((size_t)n * sizeof(WinEnd)));
@@ -1529,6 +1578,7 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
     E->succ_nt = (uint32_t)env_int("FAC_SUCC_THREADS", 1024);
     E->succ_tile = (uint32_t)std::min(4096, std::max(32, env_int("FAC_SUCC_TILE", 4096)));  // 12-bit window field of a state
     E->succ_stack = (uint32_t)env_int("FAC_SUCC_STACK", 0);
+    E->radix_unsorted = env_int("FAC_RADIX_UNSORTED", 1) != 0;
     // start windows fed at once: engines whose roots' children are on their last edit push few states per root (the
     // productivity masks leave ~20 of 55), deeper budgets fan out again
     E->succ_feed = (uint32_t)std::min(32, std::max(1, env_int("FAC_SUCC_FEED", (H.mef <= 2 && !H.succ.limits_mode) ? 8 : 1)));

@@ -239,6 +239,43 @@ __global__ void k_accept_flags(const uint8_t *st, uint8_t *flags, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) flags[i] = st[i] == OV_ACCEPTED;
 }
+// ---- Order::Unsorted as a radix sort: key = start | (end - start) | pattern packed into 64 bits ----
+// bounds[0..3] = max start, max (end - start), max pattern, max window of the list (sizes the key fields)
+__global__ void __launch_bounds__(256) k_key_bounds(const WMatch *__restrict__ m, uint32_t n, unsigned long long *__restrict__ bounds) {
+    unsigned long long ms = 0, ml = 0;
+    uint32_t mp = 0, mw = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 a = reinterpret_cast<const uint4 *>(m)[2 * (size_t)i], b = reinterpret_cast<const uint4 *>(m)[2 * (size_t)i + 1];
+        const unsigned long long st = ((unsigned long long)a.y << 32) | a.x, en = ((unsigned long long)a.w << 32) | a.z;
+        ms = max(ms, st); ml = max(ml, en - st); mp = max(mp, b.x); mw = max(mw, b.w);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        ms = max(ms, __shfl_xor_sync(0xFFFFFFFFu, ms, d)); ml = max(ml, __shfl_xor_sync(0xFFFFFFFFu, ml, d));
+        mp = max(mp, __shfl_xor_sync(0xFFFFFFFFu, mp, d)); mw = max(mw, __shfl_xor_sync(0xFFFFFFFFu, mw, d));
+    }
+    if ((threadIdx.x & 31u) == 0) {
+        atomicMax(&bounds[0], ms); atomicMax(&bounds[1], ml);
+        atomicMax(&bounds[2], (unsigned long long)mp); atomicMax(&bounds[3], (unsigned long long)mw);
+    }
+}
+__global__ void __launch_bounds__(256) k_make_keys(const WMatch *__restrict__ m, uint32_t n, uint32_t len_shift, uint32_t start_shift,
+                                                   unsigned long long *__restrict__ keys, uint32_t *__restrict__ idx) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 a = reinterpret_cast<const uint4 *>(m)[2 * (size_t)i];
+    const uint32_t pat = reinterpret_cast<const uint32_t *>(m)[8 * (size_t)i + 4];
+    const unsigned long long st = ((unsigned long long)a.y << 32) | a.x, en = ((unsigned long long)a.w << 32) | a.z;
+    keys[i] = (st << start_shift) | ((en - st) << len_shift) | pat;
+    idx[i] = i;
+}
+// 32-byte records moved as two 128-bit halves
+__global__ void __launch_bounds__(256) k_gather_matches16(const WMatch *__restrict__ R, const uint32_t *__restrict__ sel, uint32_t n, WMatch *__restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = t >> 1, h = t & 1u;
+    if (i < n) reinterpret_cast<uint4 *>(out)[2 * (size_t)i + h] = reinterpret_cast<const uint4 *>(R)[2 * (size_t)sel[i] + h];
+}
+
 // kept matches in position order -> final records
 __global__ void k_gather_matches(const WMatch *R, const uint32_t *sel, uint32_t n, WMatch *out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -184,11 +184,16 @@ static void build_deep_tables(HostSuccinct &S) {
     const uint32_t N = (uint32_t)S.bm.size();
     const uint32_t R = S.n_syms + 1u;   // <= 32 (narrow layout)
     const size_t RP[5] = {1, R, (size_t)R * R, (size_t)R * R * R, (size_t)R * R * R * R};
-    auto envn = [](const char *name, size_t dflt) { const char *ev = getenv(name); return ev && *ev ? (size_t)atoll(ev) : dflt; };
+    // node counts: default = what fits the per-table budget (sized against the 126 MB L2), overridable, never above 256 MB a table
+    auto envn = [](const char *name, size_t entries_per_node, size_t budget) {
+        const char *ev = getenv(name);
+        const size_t cap = ((size_t)256 << 20) / (entries_per_node * 4);
+        return std::min(cap, ev && *ev ? (size_t)atoll(ev) : budget / (entries_per_node * 4));
+    };
     S.r3 = R;
-    S.n3 = (uint32_t)std::min<size_t>(std::min<uint32_t>(N, S.gm_nodes), envn("FAC_GM3_NODES", ((size_t)48 << 20) / (RP[3] * 4)));
-    S.np2 = (uint32_t)std::min<size_t>(N, envn("FAC_PM2_NODES", ((size_t)32 << 20) / (RP[2] * 4)));
-    S.n4 = (uint32_t)std::min<size_t>(S.n3, envn("FAC_PM4_NODES", ((size_t)64 << 20) / (RP[4] * 4)));
+    S.n3 = (uint32_t)std::min<size_t>(std::min<uint32_t>(N, S.gm_nodes), envn("FAC_GM3_NODES", RP[3], (size_t)48 << 20));
+    S.np2 = (uint32_t)std::min<size_t>(N, envn("FAC_PM2_NODES", RP[2], (size_t)32 << 20));
+    S.n4 = (uint32_t)std::min<size_t>(S.n3, envn("FAC_PM4_NODES", RP[4], (size_t)64 << 20));
     S.np2 = std::max(S.np2, S.n3);
     S.gmask3.assign(std::max<size_t>((size_t)S.n3 * RP[3], 1), 0);
     S.pmask3.assign(std::max<size_t>((size_t)S.n3 * RP[3], 1), 0);

@@ -92,6 +92,34 @@ def test_succinct_dense_tries(oracle):
     assert emu.succinct_used == 40 and modes == {0, 1, 2, 3}
 
 
+@pytest.mark.parametrize("sizes", [("0", "0", "0"), ("1", "1", "1"), ("7", "40", "3"), ("60", "300", "12"), ("100000", "100000", "100000")])
+def test_succinct_deep_tables_are_result_neutral(oracle, monkeypatch, sizes):
+    """The three-deep survivor masks and the 2/3/4-symbol productivity masks (build_deep_tables, fac_succinct.h) only drop
+    states that cannot emit: whatever part of the trie they cover (none, the root only, table boundaries inside the trie,
+    every node), the result equals the oracle's, and covering more nodes never visits more states."""
+    monkeypatch.setenv("FAC_GM3_NODES", sizes[0])
+    monkeypatch.setenv("FAC_PM2_NODES", sizes[1])
+    monkeypatch.setenv("FAC_PM4_NODES", sizes[2])
+    emu = EmuBackend(tile=16)
+    emu.succinct = True
+    r1, r2 = random.Random(4242), random.Random(4242)
+    states = 0
+    for t in range(24):
+        eo, hay, thr, desc = rand_dense_case(r1, oracle)
+        ee, _, _, _ = rand_dense_case(r2, emu)
+        o = eo.search(hay[:300], SearchOptions.new().threshold(thr))
+        e = ee.search(hay[:300], SearchOptions.new().threshold(thr))
+        assert o.tuples() == e.tuples(), (t, desc, sizes)
+        states += e.stats["states_pushed"]
+    assert emu.succinct_used == 24
+    _DEEP_STATES[sizes] = states
+    if ("0", "0", "0") in _DEEP_STATES and ("100000", "100000", "100000") in _DEEP_STATES:
+        assert _DEEP_STATES[("100000", "100000", "100000")] < _DEEP_STATES[("0", "0", "0")]
+
+
+_DEEP_STATES = {}
+
+
 def test_succinct_on_unicode_haystacks(oracle):
     """ASCII-alphabet engines on non-ASCII haystacks: the fast formulation reads the K1 first-char stream
     (first-char identity, src/structs.rs:512-519; dead-end filter blind to non-ASCII chars, :471-475)."""

@@ -286,6 +286,34 @@ def test_succinct_stack_overflow_goes_to_faithful_redo(oracle, gpu, monkeypatch)
     assert o.tuples() == g.tuples()
 
 
+def test_succinct_deep_tables_result_neutral_on_gpu(oracle, gpu, monkeypatch):
+    # the deep survivor / productivity tables (build_deep_tables) with none, partial and default coverage: identical
+    # full lists on a 1 MiB cfg2 slice at 10 000 patterns, fewer visited states with more coverage, and the oracle's
+    # result on a prefix; several start windows fed at once must not change anything either
+    monkeypatch.setenv("FAC_FAITHFUL", "0")
+    cfg = workload.cfg2(1 << 20)
+    text = bytes(cfg["text"])
+    opts = SearchOptions.new().threshold(cfg["threshold"])
+    res = {}
+    for name, env in (("none", {"FAC_GM3_NODES": "0", "FAC_PM2_NODES": "0", "FAC_PM4_NODES": "0"}),
+                      ("partial", {"FAC_GM3_NODES": "20", "FAC_PM2_NODES": "300", "FAC_PM4_NODES": "1", "FAC_SUCC_FEED": "1"}),
+                      ("default", {}), ("feed32", {"FAC_SUCC_FEED": "32"}), ("mergesort", {"FAC_RADIX_UNSORTED": "0"})):
+        for k in ("FAC_GM3_NODES", "FAC_PM2_NODES", "FAC_PM4_NODES", "FAC_SUCC_FEED", "FAC_RADIX_UNSORTED"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        g = workload.build_engine(cfg, gpu).search(text, opts)
+        res[name] = (g.tuples(), g.stats["states_pushed"])
+    assert len(res["none"][0]) > 100000
+    assert res["none"][0] == res["partial"][0] == res["default"][0] == res["feed32"][0] == res["mergesort"][0]   # radix == merge order
+    assert res["default"][1] < res["partial"][1] < res["none"][1]
+    assert res["default"][1] * 3 < res["none"][1]
+    n = 1 << 14
+    o = workload.build_engine(cfg, oracle).search(text[:n], opts)
+    g = workload.build_engine(cfg, gpu).search(text[:n], opts)
+    assert o.tuples() == g.tuples()
+
+
 @pytest.mark.parametrize("edits", [1, 3, 4])
 def test_succinct_other_edit_budgets(oracle, gpu, edits, monkeypatch):
     monkeypatch.setenv("FAC_FAITHFUL", "0")
