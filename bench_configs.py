@@ -28,10 +28,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 
 
 def _cut_utf8(b):
-    while b and (b[-1] & 0xC0) == 0x80:
-        b = b[:-1]
-    if b and b[-1] >= 0xC0:
-        b = b[:-1]
+    """Trim a byte slice to whole UTF-8 scalars: continuation bytes at its start (the slice began inside a scalar) and an
+    incomplete scalar at its end."""
+    k = 0
+    while k < len(b) and (b[k] & 0xC0) == 0x80:
+        k += 1
+    b = b[k:]
+    k = len(b)
+    while k and (b[k - 1] & 0xC0) == 0x80:
+        k -= 1
+    if k and b[k - 1] >= 0xC0:      # the last lead byte: keep it only if its scalar is complete
+        need = 2 if b[k - 1] < 0xE0 else 3 if b[k - 1] < 0xF0 else 4
+        if len(b) - (k - 1) < need:
+            b = b[:k - 1]
     return b
 
 
