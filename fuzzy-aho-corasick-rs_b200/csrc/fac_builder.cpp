@@ -729,6 +729,56 @@ fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_
             }
         }
         if (A.flat_gm.empty()) A.flat_gm.assign(128, 0);
+        // Root productivity masks (fac_flat.h, FlatView::pm_root) for engines with mappings whose first-level states are on
+        // their last edit (edits(2)): L(c; a, b) for every child c of the root over the grapheme-id pairs (a, b), with
+        //     L = out(c) | c has mapping transitions | edge(c, a)                                   (itself / mapping child / exact child)
+        //       | some child d of c has an output or edge b | edge(c, b)                            (substitution child at j+1 / insertion child)
+        //       | some child d of c has edge a to a node with an output or edge b                   (deletion child)
+        //       | c -b-> x -a-> exists                                                              (swap child)
+        // (exhausted children only follow exact transitions, search.rs:810, 937, 1003, 1043; penalties, ceilings and
+        // similarity only remove states, so leaving them out is conservative).  Id 0 = unknown grapheme / end of text.
+        A.flat_pm.clear(); A.flat_pm_g = 0; A.flat_pm_words = 0;
+        {
+            const uint32_t e0 = A.node_edge_off[0], deg0 = A.node_edge_off[1] - e0;
+            const size_t G = gid_syms.size() + 1;
+            const size_t words = (deg0 + 63) / 64;
+            const char *ev = getenv("FAC_FLAT_ROOT_PM");
+            if (A.flat_ok && A.has_mappings && A.mef >= 2 && A.mef <= 6 && deg0 >= 2 && deg0 <= 1024 && G * G * words <= ((size_t)8 << 20) &&
+                !(ev && *ev == '0')) {
+                A.flat_pm_g = (uint32_t)G; A.flat_pm_words = (uint32_t)words;
+                A.flat_pm.assign(G * G * words, 0);
+                auto n_out = [&](uint32_t n) { return A.node_out_off[n + 1] - A.node_out_off[n]; };
+                auto for_edges = [&](uint32_t n, const std::function<void(uint32_t, uint32_t)> &fn) {   // fn(grapheme id, child)
+                    for (uint32_t e = A.node_edge_off[n]; e < A.node_edge_off[n + 1]; e++) fn(A.edge_sym[e], A.edge_next[e] & 0x7FFFFFFFu);
+                };
+                std::vector<uint8_t> row_all(G), col_all(G);
+                std::vector<std::pair<uint32_t, uint32_t>> cells;
+                for (uint32_t e = 0; e < deg0; e++) {
+                    const uint32_t c = A.edge_next[e0 + e] & 0x7FFFFFFFu;
+                    bool all = n_out(c) != 0 || A.node_map_off[c + 1] != A.node_map_off[c];
+                    std::fill(row_all.begin(), row_all.end(), 0); std::fill(col_all.begin(), col_all.end(), 0);
+                    cells.clear();
+                    for_edges(c, [&](uint32_t ka, uint32_t d) {
+                        if (ka < G) { row_all[ka] = 1; col_all[ka] = 1; }                       // exact child on a = ka; insertion child walks edge b = ka
+                        if (n_out(d) != 0) all = true;                                           // a substitution / deletion child with an output
+                        for_edges(d, [&](uint32_t kb, uint32_t g) {
+                            if (kb < G) col_all[kb] = 1;                                         // substitution child d walks edge b = kb
+                            // deletion child d reads a = kb, then b: g has an output (any b) or an edge b
+                            if (kb < G) { if (n_out(g) != 0) row_all[kb] = 1; else for_edges(g, [&](uint32_t k2, uint32_t) { if (k2 < G) cells.emplace_back(kb, k2); }); }
+                            if (ka < G && kb < G) cells.emplace_back(kb, ka);                    // swap: c -b = ka-> d -a = kb-> g
+                        });
+                    });
+                    const uint64_t bit = 1ull << (e & 63);
+                    const size_t w = e >> 6;
+                    if (all) { for (size_t k = 0; k < G * G; k++) A.flat_pm[k * words + w] |= bit; continue; }
+                    for (size_t a = 0; a < G; a++)
+                        for (size_t b = 0; b < G; b++)
+                            if (row_all[a] || col_all[b]) A.flat_pm[(a * G + b) * words + w] |= bit;
+                    for (auto &ab : cells) A.flat_pm[((size_t)ab.first * G + ab.second) * words + w] |= bit;
+                }
+            }
+        }
+        if (A.flat_pm.empty()) A.flat_pm.assign(1, 0);
         for (size_t e = 0; e < A.edge_char.size(); e++) {
             A.flat_erec[e * 4 + 0] = A.edge_next[e]; A.flat_erec[e * 4 + 1] = A.edge_char[e]; A.flat_erec[e * 4 + 2] = A.edge_sym[e];
         }

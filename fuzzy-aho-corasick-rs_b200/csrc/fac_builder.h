@@ -138,6 +138,8 @@ struct HostAutomaton {
     std::vector<uint32_t> flat_nrec, flat_erec;   // 4 words per node / edge (ceilings are filled per call)
     std::vector<uint32_t> flat_ooff, flat_olist;  // per node: node-relative edges whose child has outputs (build order)
     std::vector<uint32_t> flat_gm_row;            // [N] survivor-mask row of a branching node (3..64 edges) or FAC_NONE
+    std::vector<uint64_t> flat_pm;                // root productivity masks [(a * flat_pm_g + b) * flat_pm_words + w] (fac_flat.h); flat_pm_g == 0: none
+    uint32_t flat_pm_g = 0, flat_pm_words = 0;
     std::vector<uint64_t> flat_gm;                // [rows * 128] per ASCII look-ahead char: edges whose child has an output or that byte edge
 
     uint32_t n_nodes() const { return (uint32_t)node_prune_len.size(); }

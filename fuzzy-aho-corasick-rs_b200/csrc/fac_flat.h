@@ -39,7 +39,18 @@ struct FlatView {
     // single-byte edge c.  gm_row[node] = row of the node or FAC_NONE; gm[row * 128 + c].
     const uint32_t *gm_row;  // [N]
     const unsigned long long *gm;
+    // Root productivity masks (engines with mappings, i.e. text compared by grapheme id; build_flat_root_pm in
+    // fac_builder.cpp): pm_root[(a * pm_g + b) * pm_words + w], bit e of the row = a state on its LAST edit at the
+    // child of root edge e whose position reads the grapheme ids a, b can still emit something -- through its own
+    // outputs, its exact child, a mapping transition, or an exhausted substitution / deletion / insertion / swap child
+    // that has an output or an exact edge for what it reads next.  Everything else the root would push for an
+    // edits(2) engine (two slots per root edge) can emit nothing, now or later: dropping it is result-neutral.
+    // null = no table (engines without mappings, edit budgets other than 2..6, roots wider than 1024 edges).
+    const unsigned long long *pm_root;
+    uint32_t pm_g;           // row length = number of grapheme ids + 1 (id 0 = unknown grapheme / end of text)
+    uint32_t pm_words;       // 64-bit words per row = ceil(root degree / 64)
 };
+#define FLAT_ROW_ROOT 0xFFFFFFFEu   // FlatCtx::row of a root state whose substitution / deletion slots run over pm_root rows
 #define FLAT_SUBF 0x40000000u   // substitution slots run over the output-children list
 #define FLAT_DELF 0x80000000u   // deletion slots run over the output-children list
 #define FLAT_SUBM 0x10000000u   // substitution slots run over the set bits of the survivor mask of the look-ahead char
@@ -65,6 +76,28 @@ FAC_HD uint32_t flat_nth_bit64(unsigned long long m, uint32_t n) {
     if (n >= c) { n -= c; pos += 2; m >>= 2; }
     if (n >= (uint32_t)(m & 1ull)) pos += 1;
     return pos;
+}
+
+// pm_root row of the state at position j reading the grapheme ids of j and j + 1 (0 beyond the text)
+template <class Text>
+FAC_HD const unsigned long long *flat_pm_row(const FlatView &F, const Text &T, uint32_t j, uint32_t text_end) {
+    const uint32_t a = j < text_end ? T.gid(j) : 0u, b = j + 1u < text_end ? T.gid(j + 1u) : 0u;
+    return F.pm_root + ((size_t)a * F.pm_g + b) * F.pm_words;
+}
+FAC_HD uint32_t flat_pm_count(const unsigned long long *row, uint32_t words) {
+    uint32_t n = 0;
+    for (uint32_t w = 0; w < words; w++) n += FLAT_POPC64(row[w]);
+    return n;
+}
+// position of the k-th (0-based) set bit of a multi-word row; the row must have more than k bits set
+FAC_HD uint32_t flat_pm_nth(const unsigned long long *row, uint32_t words, uint32_t k) {
+    for (uint32_t w = 0; w + 1u < words; w++) {
+        const unsigned long long m = row[w];
+        const uint32_t c = FLAT_POPC64(m);
+        if (k < c) return w * 64u + flat_nth_bit64(m, k);
+        k -= c;
+    }
+    return (words - 1u) * 64u + flat_nth_bit64(row[words - 1u], k);
 }
 
 FAC_HD uint32_t flat_deg(const FlatRec &n) { return n.y & 0xFFFu; }
@@ -127,7 +160,9 @@ FAC_HD void flat_make_ctx(const AutomatonView &A, const FlatView &F, const Text 
     // a state on its last edit keeps a child only if it has an output or a single-ASCII-byte edge for the look-ahead
     // char: branching nodes enumerate just those children (output-children list / survivor mask of the char)
     const bool filt = is_last && deg > 2u;
-    const uint32_t row = filt ? F.gm_row[S.node] : FAC_NONE;
+    // the root of an engine whose first-level states are on their last edit: only the productive children (pm_root)
+    const bool root_pm = FAST && S.node == 0u && F.pm_root != nullptr && !is_last && edits + 2 >= A.mef;
+    const uint32_t row = filt ? F.gm_row[S.node] : (root_pm ? FLAT_ROW_ROOT : FAC_NONE);
     const uint32_t n_out_children = filt ? F.ooff[S.node + 1] - F.ooff[S.node] : 0u;
     if (in_text) {
         flags |= FLAT_F_IN_TEXT;
@@ -138,7 +173,8 @@ FAC_HD void flat_make_ctx(const AutomatonView &A, const FlatView &F, const Text 
         if (can_edit) {   // substitutions + mapping transitions, search.rs:803-811
             flags |= FLAT_F_SUB;
             const uint32_t c1 = has_nxt ? T.first(j + 1) : 0xFFFFFFFFu;
-            if (filt && c1 >= 128u) { flags |= FLAT_SUBF; n_sub = n_out_children; }
+            if (root_pm) { flags |= FLAT_SUBM; n_sub = flat_pm_count(flat_pm_row(F, T, j + 1u, text_end), F.pm_words); }   // children sit at j + 1
+            else if (filt && c1 >= 128u) { flags |= FLAT_SUBF; n_sub = n_out_children; }
             else if (filt && row != FAC_NONE) { flags |= FLAT_SUBM; n_sub = FLAT_POPC64(F.gm[(size_t)row * 128u + c1]); }
             else n_sub = deg;
             nslots += n_sub + nmaps;
@@ -153,7 +189,8 @@ FAC_HD void flat_make_ctx(const AutomatonView &A, const FlatView &F, const Text 
     if (can_edit && A.pen_del <= remaining) {   // search.rs:1035-1045
         flags |= FLAT_F_DEL;
         const uint32_t c0 = in_text ? T.first(j) : 0xFFFFFFFFu;
-        if (filt && c0 >= 128u) { flags |= FLAT_DELF; n_del = n_out_children; }
+        if (root_pm) { flags |= FLAT_DELM; n_del = flat_pm_count(flat_pm_row(F, T, j, text_end), F.pm_words); }   // children stay at j
+        else if (filt && c0 >= 128u) { flags |= FLAT_DELF; n_del = n_out_children; }
         else if (filt && row != FAC_NONE) { flags |= FLAT_DELM; n_del = FLAT_POPC64(F.gm[(size_t)row * 128u + c0]); }
         else n_del = deg;
         nslots += n_del;
@@ -186,7 +223,9 @@ FAC_HD bool flat_eval_slot(const AutomatonView &A, const FlatView &F, const Text
         const bool look_ok = is_sub ? has_nxt : in_text;
         uint32_t e = k;
         if (mode & FLAT_SUBF) e = F.olist[F.ooff[C.node] + k];
-        else if (mode & FLAT_SUBM) e = flat_nth_bit64(F.gm[(size_t)C.row * 128u + T.first(look_j)], k);
+        else if (mode & FLAT_SUBM)
+            e = C.row == FLAT_ROW_ROOT ? flat_pm_nth(flat_pm_row(F, T, look_j, text_end), F.pm_words, k)
+                                       : flat_nth_bit64(F.gm[(size_t)C.row * 128u + T.first(look_j)], k);
         const FlatRec er = F.erec[C.eoff + e];
         const uint32_t nx = er.x & 0x7FFFFFFFu;
         if (is_sub && nx == C.exact) return false;

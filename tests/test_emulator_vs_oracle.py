@@ -199,6 +199,27 @@ def test_flat_fast_path_mappings_and_ties(oracle):
     assert emu.flat_used == 700
 
 
+def test_flat_root_productivity_masks_are_result_neutral(oracle, monkeypatch):
+    """cfg3 (Unicode patterns + mappings, edits(2)): the root productivity masks of the general stack-machine path
+    (FlatView::pm_root) halve the visited states and change no result."""
+    from fac_b200 import workload
+    cfg = workload.cfg3(1 << 13)
+    text = bytes(cfg["text"])
+    opts = SearchOptions.new().threshold(cfg["threshold"])
+    o = workload.build_engine(cfg, oracle).search(text, opts)
+    assert len(o) > 500
+    states = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("FAC_FLAT_ROOT_PM", flag)
+        emu = EmuBackend(tile=16)
+        emu.flat = True
+        e = workload.build_engine(cfg, emu).search(text, opts)
+        assert emu.flat_used == 1
+        assert o.tuples() == e.tuples(), flag
+        states[flag] = e.stats["states_pushed"]
+    assert states["1"] * 2 < states["0"], states
+
+
 def test_flat_faithful_mode_matches_oracle_push_for_push(oracle):
     """flat_make_ctx<false> / flat_eval_slot<false> (what the shared-memory beamed kernel evaluates states with): the
     order-faithful emulation run on them must reproduce the oracle's matches AND its queue.len() totals -- the
