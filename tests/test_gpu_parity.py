@@ -473,6 +473,30 @@ def test_cfg3_unicode_mappings_slice_parity(oracle, gpu, monkeypatch):
     assert fo.tuples() == fg.tuples() and fo.stats["states_pushed"] == fg.stats["states_pushed"]
 
 
+def test_cfg3_4MiB_fast_equals_faithful_full_list(oracle, gpu, monkeypatch):
+    # cfg3 at 4 MiB: the stack-machine kernel with the root productivity masks, the same kernel without them and the
+    # order-faithful kernel return the same full list (bit-exact records); the oracle agrees on a 48 KiB slice
+    from bench_configs import _cut_utf8
+    cfg = workload.cfg3(4 << 20, n_patterns=1000)
+    text = bytes(cfg["text"])
+    opts = SearchOptions.new().threshold(0.8)
+    monkeypatch.setenv("FAC_FAITHFUL", "0")
+    fast = workload.build_engine(cfg, gpu).search(text, opts)
+    monkeypatch.setenv("FAC_FLAT_ROOT_PM", "0")
+    nopm = workload.build_engine(cfg, gpu).search(text, opts)
+    monkeypatch.delenv("FAC_FLAT_ROOT_PM")
+    monkeypatch.setenv("FAC_FAITHFUL", "1")
+    faithful = workload.build_engine(cfg, gpu).search(text, opts)
+    assert len(fast) > 100000
+    assert fast.tuples() == nopm.tuples() == faithful.tuples()
+    assert fast.stats["states_pushed"] * 2 < nopm.stats["states_pushed"]
+    monkeypatch.setenv("FAC_FAITHFUL", "0")
+    piece = _cut_utf8(text[2 << 20:(2 << 20) + (48 << 10)])
+    o = workload.build_engine(cfg, oracle).search(piece, opts)
+    g = workload.build_engine(cfg, gpu).search(piece, opts)
+    assert len(o) > 1000 and o.tuples() == g.tuples()
+
+
 def test_cfg5_streaming_replacer_parity(oracle, gpu):
     # BASELINE config 5 in miniature: repeating-block Read source, auto_beam, FuzzyReplacer::replace_stream,
     # absolute offsets; three 256 KiB windows
