@@ -271,7 +271,8 @@ struct fac_engine {
     bool radix_unsorted = true;   // FAC_RADIX_UNSORTED=0: Order::Unsorted always through the comparison merge sort
     int smem_optin = 0;
     const uint32_t *d_flat_nrec = nullptr, *d_flat_erec = nullptr, *d_flat_ooff = nullptr, *d_flat_olist = nullptr, *d_flat_gm_row = nullptr;
-    const uint64_t *d_flat_gm = nullptr, *d_flat_pm = nullptr;   // static parts of the merged records (fac_flat.h)
+    const uint64_t *d_flat_gm = nullptr, *d_flat_pm = nullptr, *d_flat_px = nullptr;
+    const uint32_t *d_flat_px_row = nullptr;   // static parts of the merged records (fac_flat.h)
     bool beam2_ok = false;          // shared-memory beamed kernel (fac_beam2.cuh)
     uint32_t beam2_warps = 5, beam2_vcap = 1024, beam2_ctas = 8;
     uint32_t max_fan = 0;           // most children one state can push (2 * widest node + mapping transitions + 3)
@@ -449,7 +450,8 @@ fac_status prepare_flat(const fac_engine *E, Workspace *ws, float thr, FlatView 
     CK(cudaGetLastError());
     F.nrec = ws->flat_n.as<FlatRec>(); F.erec = ws->flat_e.as<FlatRec>(); F.ooff = E->d_flat_ooff; F.olist = E->d_flat_olist;
     F.gm_row = E->d_flat_gm_row; F.gm = (const unsigned long long *)E->d_flat_gm;
-    F.pm_root = E->host.flat_pm_g ? (const unsigned long long *)E->d_flat_pm : nullptr; F.pm_g = E->host.flat_pm_g; F.pm_words = E->host.flat_pm_words;
+    F.pm_root = E->host.flat_pm_g ? (const unsigned long long *)E->d_flat_pm : nullptr; F.pm_g = E->host.flat_pm_g; F.pm_words = E->host.flat_pm_words; F.pm_k = E->host.flat_pm_k;
+    F.px_row = E->host.flat_px_row.empty() ? nullptr : E->d_flat_px_row; F.px_bits = (const unsigned long long *)E->d_flat_px;
     return FAC_OK;
 }
 fac_status launch_beam2(const fac_engine *E, Workspace *ws, const ExpandParams &P, uint32_t bw, uint32_t n_tiles, cudaStream_t s) {
@@ -1559,6 +1561,10 @@ fac_status fac_engine_create_on(int device, const fac_config *cfg, const fac_pat
         if ((st = upload(E, H.flat_gm_row, &E->d_flat_gm_row)) != FAC_OK) return fail(st);
         if ((st = upload(E, H.flat_gm, &E->d_flat_gm)) != FAC_OK) return fail(st);
         if ((st = upload(E, H.flat_pm, &E->d_flat_pm)) != FAC_OK) return fail(st);
+        if (!H.flat_px_row.empty()) {
+            if ((st = upload(E, H.flat_px_row, &E->d_flat_px_row)) != FAC_OK) return fail(st);
+            if ((st = upload(E, H.flat_px, &E->d_flat_px)) != FAC_OK) return fail(st);
+        }
     }
     E->stack_ok = E->fast_ok && H.flat_ok && env_int("FAC_STACK", 1) != 0;
     {

@@ -289,6 +289,143 @@ static void build_deep_tables(HostSuccinct &S) {
     for (uint32_t p = S.n3; p < S.np2; p++) fold(p, 2, &S.pmask2[(size_t)p * RP[2]]);
 }
 
+// Productivity tables of the general stack-machine kernel (fac_flat.h: FlatView::pm_root, px_row / px_bits) for engines with
+// mappings (text compared by grapheme id; id 0 = unknown grapheme / end of text) whose first-level states are on their last
+// edit or later (edit budgets 2..6; the tables are only consulted for states whose children are on their last edit).
+//
+//   W(d; y1..yk)   an exhausted state (exact transitions only, search.rs:810, 937, 1003, 1043) at node d reading y1..yk can
+//                  emit: out(d) | (k == 0 ? true : edge(d, y1) & W(child; y2..yk))
+//   L(c; a, b, c3) a state on its LAST edit at c reading a b c3 can emit: out(c) | c has mapping transitions (search.rs:883-923,
+//                  counted as "can emit") | its exact child (L one symbol later; true once the symbols run out) | a substitution
+//                  child W(d; b, c3) | a deletion child W(d; a, b, c3) | the insertion child W(c; b, c3) | the swap child
+//                  (c -b-> x -a-> n2, W(n2; c3))
+//   pm_root[(a, b[, c3])]  bit e:  L(child of root edge e; a, b[, c3])      (3 symbols when the table fits 64 MB, else 2)
+//   px_bits[row(x)][b][c3] bit  :  L(x; b, c3) for the nodes x two levels below the root -- the exact child of a last-edit
+//                                  state is only pushed when its bit is set
+// Penalties, ceilings, similarity and the reference's own dead-end filter only remove states, so leaving them out keeps the
+// tables conservative: a state they rule out can emit nothing, now or later.  The true cells are enumerated from the trie as
+// patterns with wildcards (a fixed prefix of the symbols a walk has consumed), never by evaluating L per cell.
+static void build_flat_pm(HostAutomaton &A, size_t G) {
+    A.flat_pm.clear(); A.flat_pm_g = 0; A.flat_pm_words = 0; A.flat_pm_k = 0;
+    A.flat_px_row.clear(); A.flat_px.clear();
+    const uint32_t N = A.n_nodes();
+    const uint32_t e0 = A.node_edge_off[0], deg0 = A.node_edge_off[1] - e0;
+    const size_t words = (deg0 + 63) / 64;
+    const char *ev = getenv("FAC_FLAT_ROOT_PM");
+    int mode = ev && *ev ? atoi(ev) : 3;   // 0 = off, 2 = two-symbol root table only, anything else = three symbols + second-level table
+    if (mode != 0 && mode != 2) mode = 3;
+    if (!(A.flat_ok && A.has_mappings && A.mef >= 2 && A.mef <= 6 && deg0 >= 2 && deg0 <= 1024 && G * G * words <= ((size_t)8 << 20) && mode != 0)) return;
+    const int K = (mode >= 3 && G * G * G * words <= ((size_t)8 << 20)) ? 3 : 2;
+    const uint32_t WILD = 0xFFFFFFFFu;
+    struct Sym3 { uint32_t v[3]; };
+    struct PSet {
+        size_t G; bool all = false;
+        std::vector<uint8_t> A1, B1, C1, AB, BC, AC;
+        std::vector<Sym3> cells;
+        explicit PSet(size_t g) : G(g), A1(g), B1(g), C1(g), AB(g * g), BC(g * g), AC(g * g) {}
+        void clear() { all = false; for (auto *v : {&A1, &B1, &C1, &AB, &BC, &AC}) std::fill(v->begin(), v->end(), 0); cells.clear(); }
+        void emit(const Sym3 &f) {
+            const bool a = f.v[0] != WILD, b = f.v[1] != WILD, c = f.v[2] != WILD;
+            if (!a && !b && !c) all = true;
+            else if (a && !b && !c) A1[f.v[0]] = 1;
+            else if (!a && b && !c) B1[f.v[1]] = 1;
+            else if (!a && !b && c) C1[f.v[2]] = 1;
+            else if (a && b && !c) AB[f.v[0] * G + f.v[1]] = 1;
+            else if (!a && b && c) BC[f.v[1] * G + f.v[2]] = 1;
+            else if (a && !b && c) AC[f.v[0] * G + f.v[2]] = 1;
+            else cells.push_back(f);
+        }
+        bool base(size_t a, size_t b) const { return all || A1[a] || B1[b] || AB[a * G + b]; }
+        bool at(size_t a, size_t b, size_t c) const { return base(a, b) || C1[c] || BC[b * G + c] || AC[a * G + c]; }   // + cells
+    };
+    auto n_out = [&](uint32_t n) { return A.node_out_off[n + 1] - A.node_out_off[n]; };
+    auto n_maps = [&](uint32_t n) { return A.node_map_off[n + 1] - A.node_map_off[n]; };
+    auto for_edges = [&](uint32_t n, const std::function<void(uint32_t, uint32_t)> &fn) {   // fn(grapheme id, child); ids beyond the table never occur
+        for (uint32_t e = A.node_edge_off[n]; e < A.node_edge_off[n + 1]; e++)
+            if (A.edge_sym[e] < G) fn(A.edge_sym[e], A.edge_next[e] & 0x7FFFFFFFu);
+    };
+    // W(d; symbols idx .. last-1): emits one pattern per way the walk can stay alive
+    std::function<void(PSet &, uint32_t, int, int, Sym3)> walk = [&](PSet &P, uint32_t d, int idx, int last, Sym3 fix) {
+        if (n_out(d) != 0 || idx >= last) { P.emit(fix); return; }
+        for_edges(d, [&](uint32_t k, uint32_t g) { Sym3 f = fix; f.v[idx] = k; walk(P, g, idx + 1, last, f); });
+    };
+    // L(x) for a state reading symbols idx, idx+1 (idx + 1 may be beyond `last`): the caller has fixed the earlier symbols
+    auto last_state = [&](PSet &P, uint32_t x, int idx, int last, Sym3 fix) {
+        if (n_out(x) != 0 || n_maps(x) != 0 || idx >= last) { P.emit(fix); return; }
+        for_edges(x, [&](uint32_t k, uint32_t y) {
+            Sym3 f = fix; f.v[idx] = k;
+            P.emit(f);                                                  // exact child: alive (its own L is not expanded further)
+            walk(P, y, idx + 1, last, fix);                             // substitution child y at the next position
+            walk(P, y, idx, last, fix);                                 // deletion child y at this position
+        });
+        walk(P, x, idx + 1, last, fix);                                 // insertion child (x has no output here)
+        for_edges(x, [&](uint32_t k1, uint32_t y) {                     // swap child: x -sym[idx+1]-> y -sym[idx]-> n2, then idx + 2
+            for_edges(y, [&](uint32_t k0, uint32_t n2) {
+                Sym3 f = fix; f.v[idx] = k0;
+                if (idx + 1 < last) { f.v[idx + 1] = k1; walk(P, n2, idx + 2, last, f); }
+                else P.emit(f);
+            });
+        });
+    };
+    A.flat_pm_g = (uint32_t)G; A.flat_pm_words = (uint32_t)words; A.flat_pm_k = (uint32_t)K;
+    const size_t rows = K == 3 ? G * G * G : G * G;
+    A.flat_pm.assign(rows * words, 0);
+    PSet P(G);
+    const Sym3 none{{WILD, WILD, WILD}};
+    for (uint32_t e = 0; e < deg0; e++) {
+        const uint32_t c = A.edge_next[e0 + e] & 0x7FFFFFFFu;
+        P.clear();
+        // L(c; a, b, c3): like last_state, but the exact child x is expanded one level (L(x; b, c3))
+        if (n_out(c) != 0 || n_maps(c) != 0) P.all = true;
+        else {
+            for_edges(c, [&](uint32_t ka, uint32_t x) {
+                Sym3 f = none; f.v[0] = ka;
+                last_state(P, x, 1, K, f);                      // exact child
+                walk(P, x, 1, K, none);                                // substitution child (any child; the exact one is covered above)
+                walk(P, x, 0, K, none);                                // deletion child
+            });
+            walk(P, c, 1, K, none);                                    // insertion child
+            for_edges(c, [&](uint32_t kb, uint32_t x) {                // swap child
+                for_edges(x, [&](uint32_t ka, uint32_t n2) { Sym3 f = none; f.v[0] = ka; f.v[1] = kb; walk(P, n2, 2, K, f); });
+            });
+        }
+        const uint64_t bit = 1ull << (e & 63);
+        const size_t w = e >> 6;
+        for (size_t a = 0; a < G; a++)
+            for (size_t b = 0; b < G; b++) {
+                const bool base = P.base(a, b);
+                if (K == 2) { if (base) A.flat_pm[(a * G + b) * words + w] |= bit; continue; }
+                uint64_t *row = &A.flat_pm[((a * G + b) * G) * words + w];
+                for (size_t c3 = 0; c3 < G; c3++)
+                    if (base || P.C1[c3] || P.BC[b * G + c3] || P.AC[a * G + c3]) row[c3 * words] |= bit;
+            }
+        for (const Sym3 &f : P.cells) A.flat_pm[(((size_t)f.v[0] * G + f.v[1]) * G + f.v[2]) * words + w] |= bit;
+    }
+    // exact-child filter: L(x; b, c3) for the nodes two levels below the root
+    if (mode >= 3) {
+        std::vector<uint32_t> xs;
+        for (uint32_t e = 0; e < deg0; e++) {
+            const uint32_t c = A.edge_next[e0 + e] & 0x7FFFFFFFu;
+            for (uint32_t e2 = A.node_edge_off[c]; e2 < A.node_edge_off[c + 1]; e2++) xs.push_back(A.edge_next[e2] & 0x7FFFFFFFu);
+        }
+        const size_t row_words = (G * G + 63) / 64;
+        if (!xs.empty() && xs.size() * row_words <= ((size_t)4 << 20)) {
+            A.flat_px_row.assign(N, FAC_NONE);
+            A.flat_px.assign(xs.size() * row_words, 0);
+            for (size_t r = 0; r < xs.size(); r++) {
+                const uint32_t x = xs[r];
+                A.flat_px_row[x] = (uint32_t)r;
+                P.clear();
+                last_state(P, x, 1, 3, none);   // reads b (index 1) and c3 (index 2)
+                uint64_t *row = &A.flat_px[r * row_words];
+                for (size_t b = 0; b < G; b++)
+                    for (size_t c3 = 0; c3 < G; c3++)
+                        if (P.all || P.B1[b] || P.C1[c3] || P.BC[b * G + c3]) row[(b * G + c3) >> 6] |= 1ull << ((b * G + c3) & 63);
+            }
+        }
+    }
+}
+
 fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_t np, HostAutomaton &A, std::string &err) {
     if (!cfg || (np && !pats)) { err = "null config or patterns"; return FAC_INVALID_ARGUMENT; }
     A.ci = cfg->case_insensitive != 0;
@@ -729,55 +866,7 @@ fac_status build_automaton(const fac_config *cfg, const fac_pattern *pats, size_
             }
         }
         if (A.flat_gm.empty()) A.flat_gm.assign(128, 0);
-        // Root productivity masks (fac_flat.h, FlatView::pm_root) for engines with mappings whose first-level states are on
-        // their last edit (edits(2)): L(c; a, b) for every child c of the root over the grapheme-id pairs (a, b), with
-        //     L = out(c) | c has mapping transitions | edge(c, a)                                   (itself / mapping child / exact child)
-        //       | some child d of c has an output or edge b | edge(c, b)                            (substitution child at j+1 / insertion child)
-        //       | some child d of c has edge a to a node with an output or edge b                   (deletion child)
-        //       | c -b-> x -a-> exists                                                              (swap child)
-        // (exhausted children only follow exact transitions, search.rs:810, 937, 1003, 1043; penalties, ceilings and
-        // similarity only remove states, so leaving them out is conservative).  Id 0 = unknown grapheme / end of text.
-        A.flat_pm.clear(); A.flat_pm_g = 0; A.flat_pm_words = 0;
-        {
-            const uint32_t e0 = A.node_edge_off[0], deg0 = A.node_edge_off[1] - e0;
-            const size_t G = gid_syms.size() + 1;
-            const size_t words = (deg0 + 63) / 64;
-            const char *ev = getenv("FAC_FLAT_ROOT_PM");
-            if (A.flat_ok && A.has_mappings && A.mef >= 2 && A.mef <= 6 && deg0 >= 2 && deg0 <= 1024 && G * G * words <= ((size_t)8 << 20) &&
-                !(ev && *ev == '0')) {
-                A.flat_pm_g = (uint32_t)G; A.flat_pm_words = (uint32_t)words;
-                A.flat_pm.assign(G * G * words, 0);
-                auto n_out = [&](uint32_t n) { return A.node_out_off[n + 1] - A.node_out_off[n]; };
-                auto for_edges = [&](uint32_t n, const std::function<void(uint32_t, uint32_t)> &fn) {   // fn(grapheme id, child)
-                    for (uint32_t e = A.node_edge_off[n]; e < A.node_edge_off[n + 1]; e++) fn(A.edge_sym[e], A.edge_next[e] & 0x7FFFFFFFu);
-                };
-                std::vector<uint8_t> row_all(G), col_all(G);
-                std::vector<std::pair<uint32_t, uint32_t>> cells;
-                for (uint32_t e = 0; e < deg0; e++) {
-                    const uint32_t c = A.edge_next[e0 + e] & 0x7FFFFFFFu;
-                    bool all = n_out(c) != 0 || A.node_map_off[c + 1] != A.node_map_off[c];
-                    std::fill(row_all.begin(), row_all.end(), 0); std::fill(col_all.begin(), col_all.end(), 0);
-                    cells.clear();
-                    for_edges(c, [&](uint32_t ka, uint32_t d) {
-                        if (ka < G) { row_all[ka] = 1; col_all[ka] = 1; }                       // exact child on a = ka; insertion child walks edge b = ka
-                        if (n_out(d) != 0) all = true;                                           // a substitution / deletion child with an output
-                        for_edges(d, [&](uint32_t kb, uint32_t g) {
-                            if (kb < G) col_all[kb] = 1;                                         // substitution child d walks edge b = kb
-                            // deletion child d reads a = kb, then b: g has an output (any b) or an edge b
-                            if (kb < G) { if (n_out(g) != 0) row_all[kb] = 1; else for_edges(g, [&](uint32_t k2, uint32_t) { if (k2 < G) cells.emplace_back(kb, k2); }); }
-                            if (ka < G && kb < G) cells.emplace_back(kb, ka);                    // swap: c -b = ka-> d -a = kb-> g
-                        });
-                    });
-                    const uint64_t bit = 1ull << (e & 63);
-                    const size_t w = e >> 6;
-                    if (all) { for (size_t k = 0; k < G * G; k++) A.flat_pm[k * words + w] |= bit; continue; }
-                    for (size_t a = 0; a < G; a++)
-                        for (size_t b = 0; b < G; b++)
-                            if (row_all[a] || col_all[b]) A.flat_pm[(a * G + b) * words + w] |= bit;
-                    for (auto &ab : cells) A.flat_pm[((size_t)ab.first * G + ab.second) * words + w] |= bit;
-                }
-            }
-        }
+        build_flat_pm(A, gid_syms.size() + 1);
         if (A.flat_pm.empty()) A.flat_pm.assign(1, 0);
         for (size_t e = 0; e < A.edge_char.size(); e++) {
             A.flat_erec[e * 4 + 0] = A.edge_next[e]; A.flat_erec[e * 4 + 1] = A.edge_char[e]; A.flat_erec[e * 4 + 2] = A.edge_sym[e];

@@ -139,7 +139,9 @@ struct HostAutomaton {
     std::vector<uint32_t> flat_ooff, flat_olist;  // per node: node-relative edges whose child has outputs (build order)
     std::vector<uint32_t> flat_gm_row;            // [N] survivor-mask row of a branching node (3..64 edges) or FAC_NONE
     std::vector<uint64_t> flat_pm;                // root productivity masks [(a * flat_pm_g + b) * flat_pm_words + w] (fac_flat.h); flat_pm_g == 0: none
-    uint32_t flat_pm_g = 0, flat_pm_words = 0;
+    uint32_t flat_pm_g = 0, flat_pm_words = 0, flat_pm_k = 0;   // k = symbols per row (2 or 3)
+    std::vector<uint32_t> flat_px_row;            // [N] row of the exact-child table or FAC_NONE (empty: no table)
+    std::vector<uint64_t> flat_px;                // [rows][ceil(g * g / 64)] bit (b * g + c3)
     std::vector<uint64_t> flat_gm;                // [rows * 128] per ASCII look-ahead char: edges whose child has an output or that byte edge
 
     uint32_t n_nodes() const { return (uint32_t)node_prune_len.size(); }

@@ -49,6 +49,13 @@ struct FlatView {
     const unsigned long long *pm_root;
     uint32_t pm_g;           // row length = number of grapheme ids + 1 (id 0 = unknown grapheme / end of text)
     uint32_t pm_words;       // 64-bit words per row = ceil(root degree / 64)
+    uint32_t pm_k;           // symbols per row: 2 = rows (a, b), 3 = rows (a, b, c3)
+    // Second-level table: px_bits[px_row[x] * ceil(g * g / 64)] bit (b * g + c3) = a state on its last edit at node x reading
+    // b, c3 can still emit; rows exist for the nodes two levels below the root.  A last-edit state pushes its exact child,
+    // and a state whose children are on their last edit pushes a substitution / deletion child, only when the child's bit
+    // is set (result-neutral for the same reason).  null = no table.
+    const uint32_t *px_row;  // [N] or null
+    const unsigned long long *px_bits;
 };
 #define FLAT_ROW_ROOT 0xFFFFFFFEu   // FlatCtx::row of a root state whose substitution / deletion slots run over pm_root rows
 #define FLAT_SUBF 0x40000000u   // substitution slots run over the output-children list
@@ -82,8 +89,21 @@ FAC_HD uint32_t flat_nth_bit64(unsigned long long m, uint32_t n) {
 template <class Text>
 FAC_HD const unsigned long long *flat_pm_row(const FlatView &F, const Text &T, uint32_t j, uint32_t text_end) {
     const uint32_t a = j < text_end ? T.gid(j) : 0u, b = j + 1u < text_end ? T.gid(j + 1u) : 0u;
-    return F.pm_root + ((size_t)a * F.pm_g + b) * F.pm_words;
+    size_t r = (size_t)a * F.pm_g + b;
+    if (F.pm_k == 3u) r = r * F.pm_g + (j + 2u < text_end ? T.gid(j + 2u) : 0u);
+    return F.pm_root + r * F.pm_words;
 }
+// productivity of a last-edit state at node x sitting at position p (it reads the grapheme ids of p and p + 1)
+template <class Text>
+FAC_HD bool flat_px_alive(const FlatView &F, const Text &T, uint32_t x, uint32_t p, uint32_t text_end) {
+    if (F.px_row == nullptr) return true;
+    const uint32_t r = F.px_row[x];
+    if (r == FAC_NONE) return true;
+    const uint32_t b = p < text_end ? T.gid(p) : 0u, c3 = p + 1u < text_end ? T.gid(p + 1u) : 0u;
+    const size_t bitpos = (size_t)b * F.pm_g + c3, row_words = ((size_t)F.pm_g * F.pm_g + 63u) / 64u;
+    return (F.px_bits[(size_t)r * row_words + (bitpos >> 6)] >> (bitpos & 63u)) & 1ull;
+}
+
 FAC_HD uint32_t flat_pm_count(const unsigned long long *row, uint32_t words) {
     uint32_t n = 0;
     for (uint32_t w = 0; w < words; w++) n += FLAT_POPC64(row[w]);
@@ -169,6 +189,7 @@ FAC_HD void flat_make_ctx(const AutomatonView &A, const FlatView &F, const Text 
         const bool has_nxt = is_last && can_edit && (j + 1 < text_end);  // search.rs:758-765
         if (has_nxt) flags |= FLAT_F_HAS_NXT;
         exact = flat_lookup(A, F, S.node, nr, A.has_mappings ? T.gid(j) : T.first(j));   // search.rs:776-780
+        if (FAST && is_last && exact != FAC_NONE && !flat_px_alive(F, T, exact, j + 1u, text_end)) exact = FAC_NONE;   // the child (at j + 1, still on its last edit) cannot emit
         if (exact != FAC_NONE) { flags |= FLAT_F_EXACT; nslots += 1; }
         if (can_edit) {   // substitutions + mapping transitions, search.rs:803-811
             flags |= FLAT_F_SUB;
@@ -237,6 +258,8 @@ FAC_HD bool flat_eval_slot(const AutomatonView &A, const FlatView &F, const Text
             if (pp > FAC_SUB(maxpen, C.pen)) return false;
         }
         if (is_last && !(er.x >> 31) && (!look_ok || !fac_has_byte_edge(A, nx, T.first(look_j)))) return false;
+        // a child that will be on its last edit and provably cannot emit (substitution child at j + 1, deletion child at j)
+        if (FAST && !is_last && (int)fac_edits_of(C.cnt) + 2 >= A.mef && !flat_px_alive(F, T, nx, look_j, text_end)) return false;
         out.node = nx; out.pen = FAC_ADD(C.pen, pp); out.cnt = C.cnt + (is_sub ? 0x10000u : 0x100u);
         out.pos = is_sub ? fac_make_pos(w, jr + 1, jr + 1) : fac_make_pos(w, jr, mr);
         return !FAST || !(out.pen > FLAT_AS_FLOAT(er.w));

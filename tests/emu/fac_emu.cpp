@@ -112,7 +112,8 @@ int emu_search(const fac_config *cfg, const fac_pattern *pats, size_t np, const 
             erec[e] = FlatRec{HA.flat_erec[e * 4], HA.flat_erec[e * 4 + 1], HA.flat_erec[e * 4 + 2], nrec[HA.flat_erec[e * 4] & 0x7FFFFFFFu].z};
     }
     const FlatView F{nrec.data(), erec.data(), HA.flat_ooff.data(), HA.flat_olist.data(), HA.flat_gm_row.data(), (const unsigned long long *)HA.flat_gm.data(),
-                     HA.flat_pm_g ? (const unsigned long long *)HA.flat_pm.data() : nullptr, HA.flat_pm_g, HA.flat_pm_words};
+                     HA.flat_pm_g ? (const unsigned long long *)HA.flat_pm.data() : nullptr, HA.flat_pm_g, HA.flat_pm_words, HA.flat_pm_k,
+                     HA.flat_px_row.empty() ? nullptr : HA.flat_px_row.data(), (const unsigned long long *)HA.flat_px.data()};
     for (uint32_t tile_base = 0; tile_base < n; tile_base += tile) {
         const uint32_t cnt = std::min(tile, n - tile_base);
         const uint32_t text_end = n;
@@ -389,7 +390,8 @@ int emu_search_flat(const fac_config *cfg, const fac_pattern *pats, size_t np, c
     for (size_t e = 0; e < erec.size(); e++)
         erec[e] = FlatRec{HA.flat_erec[e * 4], HA.flat_erec[e * 4 + 1], HA.flat_erec[e * 4 + 2], nrec[HA.flat_erec[e * 4] & 0x7FFFFFFFu].z};
     const FlatView F{nrec.data(), erec.data(), HA.flat_ooff.data(), HA.flat_olist.data(), HA.flat_gm_row.data(), (const unsigned long long *)HA.flat_gm.data(),
-                     HA.flat_pm_g ? (const unsigned long long *)HA.flat_pm.data() : nullptr, HA.flat_pm_g, HA.flat_pm_words};
+                     HA.flat_pm_g ? (const unsigned long long *)HA.flat_pm.data() : nullptr, HA.flat_pm_g, HA.flat_pm_words, HA.flat_pm_k,
+                     HA.flat_px_row.empty() ? nullptr : HA.flat_px_row.data(), (const unsigned long long *)HA.flat_px.data()};
     std::vector<FacCand> cands;
     EmuEmit emit{&cands};
     uint64_t states = 0;

@@ -201,7 +201,8 @@ def test_flat_fast_path_mappings_and_ties(oracle):
 
 def test_flat_root_productivity_masks_are_result_neutral(oracle, monkeypatch):
     """cfg3 (Unicode patterns + mappings, edits(2)): the root productivity masks of the general stack-machine path
-    (FlatView::pm_root) halve the visited states and change no result."""
+    (FlatView::pm_root: two symbols, or three symbols plus the second-level table) cut the visited states and change no
+    result."""
     from fac_b200 import workload
     cfg = workload.cfg3(1 << 13)
     text = bytes(cfg["text"])
@@ -209,7 +210,7 @@ def test_flat_root_productivity_masks_are_result_neutral(oracle, monkeypatch):
     o = workload.build_engine(cfg, oracle).search(text, opts)
     assert len(o) > 500
     states = {}
-    for flag in ("0", "1"):
+    for flag in ("0", "2", "3"):
         monkeypatch.setenv("FAC_FLAT_ROOT_PM", flag)
         emu = EmuBackend(tile=16)
         emu.flat = True
@@ -217,7 +218,7 @@ def test_flat_root_productivity_masks_are_result_neutral(oracle, monkeypatch):
         assert emu.flat_used == 1
         assert o.tuples() == e.tuples(), flag
         states[flag] = e.stats["states_pushed"]
-    assert states["1"] * 2 < states["0"], states
+    assert states["2"] * 2 < states["0"] and states["3"] * 2 < states["2"], states
 
 
 def test_flat_faithful_mode_matches_oracle_push_for_push(oracle):
