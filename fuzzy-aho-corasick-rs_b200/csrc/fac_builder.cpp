@@ -184,11 +184,15 @@ static void build_deep_tables(HostSuccinct &S) {
     const uint32_t N = (uint32_t)S.bm.size();
     const uint32_t R = S.n_syms + 1u;   // <= 32 (narrow layout)
     const size_t RP[5] = {1, R, (size_t)R * R, (size_t)R * R * R, (size_t)R * R * R * R};
-    // node counts: default = what fits the per-table budget (sized against the 126 MB L2), overridable, never above 256 MB a table
-    auto envn = [](const char *name, size_t entries_per_node, size_t budget) {
+    // node counts: default = what fits the per-table budget (sized on the measured cfg2 throughput), overridable, never above
+    // 256 MB a table.
+    // Small tries get proportionally smaller tables (64 KB of table per trie node, at least 1 MB): creating a 30-node engine
+    // must not allocate and upload 200 MB.
+    const size_t scaled = std::max<size_t>((size_t)1 << 20, (size_t)N * (64u << 10));
+    auto envn = [&](const char *name, size_t entries_per_node, size_t budget) {
         const char *ev = getenv(name);
         const size_t cap = ((size_t)256 << 20) / (entries_per_node * 4);
-        return std::min(cap, ev && *ev ? (size_t)atoll(ev) : budget / (entries_per_node * 4));
+        return std::min(cap, ev && *ev ? (size_t)atoll(ev) : std::min(budget, scaled) / (entries_per_node * 4));
     };
     S.r3 = R;
     S.n3 = (uint32_t)std::min<size_t>(std::min<uint32_t>(N, S.gm_nodes), envn("FAC_GM3_NODES", RP[3], (size_t)48 << 20));
