@@ -376,6 +376,10 @@ static void build_flat_pm(HostAutomaton &A, size_t G) {
     A.flat_pm.assign(rows * words, 0);
     PSet P(G);
     const Sym3 none{{WILD, WILD, WILD}};
+    // the patterns of all root children, transposed into masks over the root edges (one bit per child), so that the table
+    // is filled with a handful of word ORs per cell instead of one test per cell and child
+    std::vector<uint64_t> m_all(words, 0), m_a(G * words, 0), m_b(G * words, 0), m_c(G * words, 0), m_ab(G * G * words, 0), m_bc(G * G * words, 0),
+        m_ac(G * G * words, 0);
     for (uint32_t e = 0; e < deg0; e++) {
         const uint32_t c = A.edge_next[e0 + e] & 0x7FFFFFFFu;
         P.clear();
@@ -384,7 +388,7 @@ static void build_flat_pm(HostAutomaton &A, size_t G) {
         else {
             for_edges(c, [&](uint32_t ka, uint32_t x) {
                 Sym3 f = none; f.v[0] = ka;
-                last_state(P, x, 1, K, f);                      // exact child
+                last_state(P, x, 1, K, f);                             // exact child
                 walk(P, x, 1, K, none);                                // substitution child (any child; the exact one is covered above)
                 walk(P, x, 0, K, none);                                // deletion child
             });
@@ -395,16 +399,27 @@ static void build_flat_pm(HostAutomaton &A, size_t G) {
         }
         const uint64_t bit = 1ull << (e & 63);
         const size_t w = e >> 6;
-        for (size_t a = 0; a < G; a++)
-            for (size_t b = 0; b < G; b++) {
-                const bool base = P.base(a, b);
-                if (K == 2) { if (base) A.flat_pm[(a * G + b) * words + w] |= bit; continue; }
-                uint64_t *row = &A.flat_pm[((a * G + b) * G) * words + w];
-                for (size_t c3 = 0; c3 < G; c3++)
-                    if (base || P.C1[c3] || P.BC[b * G + c3] || P.AC[a * G + c3]) row[c3 * words] |= bit;
-            }
-        for (const Sym3 &f : P.cells) A.flat_pm[(((size_t)f.v[0] * G + f.v[1]) * G + f.v[2]) * words + w] |= bit;
+        if (P.all) { m_all[w] |= bit; continue; }
+        for (size_t k = 0; k < G; k++) {
+            if (P.A1[k]) m_a[k * words + w] |= bit;
+            if (P.B1[k]) m_b[k * words + w] |= bit;
+            if (P.C1[k]) m_c[k * words + w] |= bit;
+        }
+        for (size_t k = 0; k < G * G; k++) {
+            if (P.AB[k]) m_ab[k * words + w] |= bit;
+            if (P.BC[k]) m_bc[k * words + w] |= bit;
+            if (P.AC[k]) m_ac[k * words + w] |= bit;
+        }
+        for (const Sym3 &f : P.cells) A.flat_pm[(((size_t)f.v[0] * G + f.v[1]) * G + f.v[2]) * words + w] |= bit;   // only with K == 3
     }
+    for (size_t a = 0; a < G; a++)
+        for (size_t b = 0; b < G; b++)
+            for (size_t w = 0; w < words; w++) {
+                const uint64_t base = m_all[w] | m_a[a * words + w] | m_b[b * words + w] | m_ab[(a * G + b) * words + w];
+                if (K == 2) { A.flat_pm[(a * G + b) * words + w] |= base; continue; }
+                for (size_t c3 = 0; c3 < G; c3++)
+                    A.flat_pm[((a * G + b) * G + c3) * words + w] |= base | m_c[c3 * words + w] | m_bc[(b * G + c3) * words + w] | m_ac[(a * G + c3) * words + w];
+            }
     // exact-child filter: L(x; b, c3) for the nodes two levels below the root
     if (mode >= 3) {
         std::vector<uint32_t> xs;
