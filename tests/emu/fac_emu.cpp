@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 #include <tuple>
@@ -471,3 +472,170 @@ int emu_search_flat(const fac_config *cfg, const fac_pattern *pats, size_t np, c
 void emu_free(void *p) { free(p); }
 
 }  // extern "C"
+
+// ---- definition checks of the builder's productivity / survivor tables (TEST CODE) ----
+// The builder constructs the tables by bit-parallel / pattern enumeration; here every cell is recomputed by evaluating the
+// definition written in the header of build_deep_tables / build_flat_pm directly (plain recursion), on engines small
+// enough that all cells can be visited.  info[0] = cells compared, info[1] = mismatches, info[2..] = table sizes.
+namespace {
+struct SuccDef {
+    const HostSuccinct &S; uint32_t R;
+    bool out(uint32_t n) const { return S.out_idx[n] != FAC_NONE; }
+    bool edge(uint32_t n, uint32_t y) const { return y < S.n_syms && ((S.bm[n] >> y) & 1u); }
+    uint32_t kid(uint32_t n, uint32_t y) const { return S.fc[n] + (uint32_t)__builtin_popcountll(S.bm[n] & ((1ull << y) - 1ull)); }
+    bool W(uint32_t d, const uint32_t *sy, int k) const {
+        if (out(d)) return true;
+        if (k == 0) return true;
+        return edge(d, sy[0]) && W(kid(d, sy[0]), sy + 1, k - 1);
+    }
+    bool L(uint32_t c, const uint32_t *sy, int k) const {
+        if (out(c) || k == 0) return true;
+        const uint32_t a = sy[0];
+        if (edge(c, a) && L(kid(c, a), sy + 1, k - 1)) return true;                       // exact child
+        for (uint32_t s = 0; s < S.n_syms; s++) {
+            if (!edge(c, s)) continue;
+            const uint32_t d = kid(c, s);
+            if (s != a && W(d, sy + 1, k - 1)) return true;                                // substitution child
+            if (W(d, sy, k)) return true;                                                  // deletion child
+        }
+        if (W(c, sy + 1, k - 1)) return true;                                              // insertion child
+        for (uint32_t b = 0; b < S.n_syms; b++) {                                          // swap child: c -b-> x -a-> n2
+            if (!edge(c, b) || (k >= 2 && sy[1] != b)) continue;
+            const uint32_t x = kid(c, b);
+            if (edge(x, a) && (k < 2 || W(kid(x, a), sy + 2, k - 2))) return true;
+        }
+        return false;
+    }
+};
+}  // namespace
+
+extern "C" int emu_check_deep_tables(const fac_config *cfg, const fac_pattern *pats, size_t np, uint64_t *info /*[8]*/) {
+    HostAutomaton HA; std::string err;
+    fac_status st = build_automaton(cfg, pats, np, HA, err);
+    if (st != FAC_OK) return (int)st;
+    const HostSuccinct &S = HA.succ;
+    if (!S.ok || S.wide || S.exact_only || S.r3 == 0) return -3;
+    const uint32_t R = S.r3;
+    const SuccDef D{S, R};
+    uint64_t cells = 0, bad = 0;
+    auto children_mask = [&](uint32_t p, const std::function<bool(uint32_t)> &f) {
+        uint32_t m = 0;
+        for (uint32_t s = 0; s < S.n_syms; s++) if (D.edge(p, s) && f(D.kid(p, s))) m |= 1u << s;
+        return m;
+    };
+    uint32_t sy[4];
+    for (uint32_t p = 0; p < S.np2; p++) {
+        const int k = p < S.n4 ? 4 : (p < S.n3 ? 3 : 2);
+        size_t total = 1; for (int i = 0; i < k; i++) total *= R;
+        for (size_t idx = 0; idx < total; idx++) {
+            size_t t = idx; for (int i = k - 1; i >= 0; i--) { sy[i] = (uint32_t)(t % R); t /= R; }
+            const uint32_t want = children_mask(p, [&](uint32_t c) { return D.L(c, sy, k); });
+            const uint32_t got = k == 4 ? S.pmask4[(size_t)p * total + idx] : (k == 3 ? S.pmask3[(size_t)p * total + idx] : S.pmask2[(size_t)p * total + idx]);
+            cells++; if (want != got) bad++;
+        }
+        if (p < S.n3 && p < S.n4) {   // nodes of the 4-symbol table also own 3-symbol rows
+            size_t t3 = (size_t)R * R * R;
+            for (size_t idx = 0; idx < t3; idx++) {
+                size_t t = idx; for (int i = 2; i >= 0; i--) { sy[i] = (uint32_t)(t % R); t /= R; }
+                const uint32_t want = children_mask(p, [&](uint32_t c) { return D.L(c, sy, 3); });
+                cells++; if (want != S.pmask3[(size_t)p * t3 + idx]) bad++;
+            }
+        }
+    }
+    for (uint32_t p = 0; p < S.n3; p++) {   // gmask3[p][y1][y2][y3] bit s: d = child(p, s) has edge y1 and W(child(d, y1); y2, y3)
+        const size_t t3 = (size_t)R * R * R;
+        for (size_t idx = 0; idx < t3; idx++) {
+            size_t t = idx; for (int i = 2; i >= 0; i--) { sy[i] = (uint32_t)(t % R); t /= R; }
+            const uint32_t want = children_mask(p, [&](uint32_t d) { return D.edge(d, sy[0]) && D.W(D.kid(d, sy[0]), sy + 1, 2); });
+            cells++; if (want != S.gmask3[(size_t)p * t3 + idx]) bad++;
+        }
+    }
+    info[0] = cells; info[1] = bad; info[2] = S.n3; info[3] = S.np2; info[4] = S.n4; info[5] = R; info[6] = S.bm.size();
+    return 0;
+}
+
+namespace {
+struct FlatDef {
+    const HostAutomaton &A; uint32_t G;
+    bool out(uint32_t n) const { return A.node_out_off[n + 1] != A.node_out_off[n]; }
+    bool maps(uint32_t n) const { return A.node_map_off[n + 1] != A.node_map_off[n]; }
+    uint32_t next(uint32_t n, uint32_t key) const {
+        for (uint32_t e = A.node_edge_off[n]; e < A.node_edge_off[n + 1]; e++) if (A.edge_sym[e] == key) return A.edge_next[e] & 0x7FFFFFFFu;
+        return FAC_NONE;
+    }
+    template <class F> bool any_child(uint32_t n, F f) const {
+        for (uint32_t e = A.node_edge_off[n]; e < A.node_edge_off[n + 1]; e++) if (f(A.edge_next[e] & 0x7FFFFFFFu)) return true;
+        return false;
+    }
+    bool W(uint32_t d, const uint32_t *sy, int k) const {
+        if (out(d) || k == 0) return true;
+        const uint32_t g = sy[0] ? next(d, sy[0]) : FAC_NONE;
+        return g != FAC_NONE && W(g, sy + 1, k - 1);
+    }
+    // a last-edit state at x whose exact child is not expanded further (the builder's last_state)
+    bool Lx(uint32_t x, const uint32_t *sy, int k) const {
+        if (out(x) || maps(x) || k == 0) return true;
+        if (sy[0] && next(x, sy[0]) != FAC_NONE) return true;                                                   // exact child
+        if (any_child(x, [&](uint32_t d) { return W(d, sy + 1, k - 1) || W(d, sy, k); })) return true;           // substitution / deletion
+        if (W(x, sy + 1, k - 1)) return true;                                                                   // insertion
+        for (uint32_t e = A.node_edge_off[x]; e < A.node_edge_off[x + 1]; e++) {                                // swap: x -sy[1]-> y -sy[0]-> n2
+            if (k >= 2 && A.edge_sym[e] != sy[1]) continue;
+            const uint32_t y = A.edge_next[e] & 0x7FFFFFFFu;
+            const uint32_t n2 = sy[0] ? next(y, sy[0]) : FAC_NONE;
+            if (n2 != FAC_NONE && (k < 2 || W(n2, sy + 2, k - 2))) return true;
+        }
+        return false;
+    }
+    // a root child: same, with the exact child expanded one level
+    bool Lc(uint32_t c, const uint32_t *sy, int k) const {
+        if (out(c) || maps(c)) return true;
+        const uint32_t x = sy[0] ? next(c, sy[0]) : FAC_NONE;
+        if (x != FAC_NONE && Lx(x, sy + 1, k - 1)) return true;
+        if (any_child(c, [&](uint32_t d) { return W(d, sy + 1, k - 1) || W(d, sy, k); })) return true;
+        if (W(c, sy + 1, k - 1)) return true;
+        const uint32_t x1 = sy[1] ? next(c, sy[1]) : FAC_NONE;
+        if (x1 != FAC_NONE) { const uint32_t n2 = sy[0] ? next(x1, sy[0]) : FAC_NONE; if (n2 != FAC_NONE && W(n2, sy + 2, k - 2)) return true; }
+        return false;
+    }
+};
+}  // namespace
+
+extern "C" int emu_check_flat_pm(const fac_config *cfg, const fac_pattern *pats, size_t np, uint64_t *info /*[8]*/) {
+    HostAutomaton A; std::string err;
+    fac_status st = build_automaton(cfg, pats, np, A, err);
+    if (st != FAC_OK) return (int)st;
+    if (A.flat_pm_g == 0) return -3;
+    const uint32_t G = A.flat_pm_g, K = A.flat_pm_k, words = A.flat_pm_words;
+    const FlatDef D{A, G};
+    const uint32_t e0 = A.node_edge_off[0], deg0 = A.node_edge_off[1] - e0;
+    uint64_t cells = 0, bad = 0;
+    uint32_t sy[3];
+    size_t total = 1; for (uint32_t i = 0; i < K; i++) total *= G;
+    for (size_t idx = 0; idx < total; idx++) {
+        size_t t = idx; for (int i = (int)K - 1; i >= 0; i--) { sy[i] = (uint32_t)(t % G); t /= G; }
+        for (uint32_t e = 0; e < deg0; e++) {
+            const bool want = D.Lc(A.edge_next[e0 + e] & 0x7FFFFFFFu, sy, (int)K);
+            const bool got = (A.flat_pm[idx * words + (e >> 6)] >> (e & 63)) & 1ull;
+            cells++; if (want != got) bad++;
+        }
+    }
+    uint64_t rows = 0;
+    if (!A.flat_px_row.empty()) {
+        const size_t row_words = ((size_t)G * G + 63) / 64;
+        for (uint32_t x = 0; x < A.n_nodes(); x++) {
+            const uint32_t r = A.flat_px_row[x];
+            if (r == FAC_NONE) continue;
+            rows++;
+            for (uint32_t b = 0; b < G; b++)
+                for (uint32_t c3 = 0; c3 < G; c3++) {
+                    const uint32_t s2[2] = {b, c3};
+                    const bool want = D.Lx(x, s2, 2);
+                    const size_t bp = (size_t)b * G + c3;
+                    const bool got = (A.flat_px[r * row_words + (bp >> 6)] >> (bp & 63)) & 1ull;
+                    cells++; if (want != got) bad++;
+                }
+        }
+    }
+    info[0] = cells; info[1] = bad; info[2] = G; info[3] = K; info[4] = deg0; info[5] = rows;
+    return 0;
+}
