@@ -5,6 +5,11 @@ random engines / haystacks, beyond the fixed seeds of tests/test_emulator_vs_ora
     tools/soak_emulator.py succ|flat <first seed> <seconds>
 
 Round 2 (deep survivor / productivity tables, root productivity tables): 4 processes x 15 min, 87 000 cases, no mismatch."""
+import os
+import random
+import sys
+import time
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "fuzzy-aho-corasick-rs_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from fac_b200 import SearchOptions
